@@ -1,0 +1,122 @@
+// asm_internal.h -- shared between the translation units of libasmgpu.so.  Not part of the ABI.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/asmgpu.h"
+
+// ---- layout constants shared by host and kernels -------------------------------------------------
+constexpr int kTileRows = 128;     // rows of one distance tile (both kernels)
+constexpr int kBlockRows = 256;    // chain segments are padded to this many rows
+constexpr int kBitsPad = 1024;     // dictionary width is padded to this many bits (16 words = one
+                                   // 128-byte K chunk of the popcount kernel; 8 K-chunks of the int8 one)
+constexpr int kMaxSegments = 2 * ASM_MAX_CHAINS;
+
+// flags of a 128-row tile / 256-row block of the padded, chain-major operand matrix
+constexpr uint32_t kFlagCol = 1;   // its trees are columns (post-burn-in) of their chain
+constexpr uint32_t kFlagRows = 2;  // it contains at least one row (tree index >= row_start)
+
+struct Segment {        // a run of thinned trees of one chain in the padded operand
+  int64_t dst_off;      // first padded row
+  int64_t n;            // live rows (the rest up to the next segment is zero padding)
+  int64_t src_first;    // tree index of the first live row
+  int32_t chain;
+  int32_t is_col;       // 1: B segment (columns), 0: A segment (burn-in trees that are rows only)
+};
+
+struct PsrfLayout {
+  int32_t C = 0, delta = 1, row_start = 0, end = 0;
+  int32_t n_rows = 0;             // output rows per chain
+  int32_t n_seg = 0;
+  Segment seg[kMaxSegments];
+  int64_t Tp = 0;                 // padded rows, multiple of 256
+  int32_t Wp = 0;                 // padded words per row, multiple of 16
+  int64_t row_pos0[ASM_MAX_CHAINS];   // padded position of output row r of chain a:
+  int64_t row_posB[ASM_MAX_CHAINS];   //   r < rowsA[a] ? row_pos0[a] + r : row_posB[a] + (r - rowsA[a])
+  int32_t rowsA[ASM_MAX_CHAINS];
+  int64_t padB[ASM_MAX_CHAINS];   // zero-padding rows inside the column segment of chain c
+  int64_t tiles_total = 0, tiles_done = 0;
+};
+
+struct ChainTrees {
+  uint64_t* d_bits = nullptr;  // [cap][ctx->words]
+  int64_t n = 0, cap = 0;
+};
+
+struct ChainTraces {
+  double* d_vals = nullptr;  // row-major [cap][n_cols]
+  int64_t n = 0, cap = 0;
+  int32_t n_cols = 0;
+};
+
+struct DevBuf {  // grow-only device scratch
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+struct asm_ctx {
+  int device = 0;
+  int n_chains = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  int32_t words = 0;  // stored row width of every chain (uint64 words)
+  std::vector<ChainTrees> trees;
+  std::vector<ChainTraces> traces;
+  // scratch
+  DevBuf opnd_bits, opnd_i8, nbits, S_pad, blk_meta, seg_dev, S_compact, psrf_rows, psrf_mean, misc, flush, ess_tr,
+      ess_sls, ess_out, tile_counter, rf_out;
+  PsrfLayout layout;
+  // measurement
+  cudaEvent_t timer[16] = {};
+  bool profile = false;
+  cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+  double prof_ms[ASM_K_COUNT] = {};
+  int64_t prof_n[ASM_K_COUNT] = {};
+  int64_t launches = 0;
+  std::string err;
+};
+
+// ---- error plumbing ---------------------------------------------------------------------------------
+int32_t asm_fail(asm_ctx* ctx, int32_t code, const char* fmt, ...);
+#define ASM_CUDA(ctx, call)                                                                          \
+  do {                                                                                               \
+    cudaError_t e_ = (call);                                                                         \
+    if (e_ != cudaSuccess)                                                                           \
+      return asm_fail((ctx), ASM_E_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+int32_t asm_reserve(asm_ctx* ctx, DevBuf& b, size_t bytes);
+
+// profile bracket around one launch
+struct LaunchScope {
+  asm_ctx* ctx;
+  int family;
+  LaunchScope(asm_ctx* c, int f);
+  ~LaunchScope();
+};
+
+// ---- kernels (launchers live next to their kernels) ---------------------------------------------------
+// psrf_layout.cu
+int32_t psrf_build_layout(asm_ctx* ctx, const int32_t* burnin, int32_t row_start, int32_t end, int32_t delta);
+int32_t psrf_gather_bits(asm_ctx* ctx);  // layout -> opnd_bits [Tp][Wp], nbits [Tp], blk_meta
+int32_t psrf_expand_i8(asm_ctx* ctx);    // opnd_bits -> opnd_i8 [Tp][64*Wp]
+int32_t psrf_compact(asm_ctx* ctx, asm_shard shard, int64_t* d_S_out);  // S_pad -> [C][n_rows][C], pad-corrected
+int32_t psrf_finish(asm_ctx* ctx, const int64_t* d_S, int32_t n_rows, double* psrf_rows_host, double* psrf_mean_host);
+// rf_popc.cu
+int32_t rf_popc_sums(asm_ctx* ctx, asm_shard shard);
+int32_t rf_popc_block(asm_ctx* ctx, int32_t chainA, int64_t r0, int64_t r1, int32_t chainB, int64_t c0, int64_t c1,
+                      uint16_t* out_host);
+// rf_i8.cu
+int32_t rf_i8_sums(asm_ctx* ctx, asm_shard shard);
+int32_t rf_i8_block(asm_ctx* ctx, int32_t chainA, int64_t r0, int64_t r1, int32_t chainB, int64_t c0, int64_t c1,
+                    uint16_t* out_host);
+// clade.cu
+int32_t clade_counts(asm_ctx* ctx, int32_t chain, int64_t from, int64_t to, int32_t* out_host);
+// ess.cu
+int32_t ess_batch_device(asm_ctx* ctx, int32_t n_traces, int64_t n_samples, int64_t stride, const double* d_traces,
+                         int32_t max_lag, double* act_out_host, double* ess_out_host);
+int32_t ess_eval_stream(asm_ctx* ctx, const int32_t* burnin, int32_t end, const int32_t* cols, int32_t n_cols,
+                        double* ess_out_host);

@@ -1,0 +1,307 @@
+// psrf_layout.cu -- operand layout, gather / expand, S compaction and the PSRF finish kernels.
+//
+// Data layout in HBM for one PSRF evaluation:
+//   operand  bits [Tp][Wp] uint64   thinned trees of all chains, chain-major; per chain an optional
+//                                   "A" segment (burn-in trees that are rows but not columns) and a
+//                                   "B" segment (column trees), each zero-padded to 256 rows, so that
+//                                   every 128-row tile belongs to one chain and one class
+//   operand  i8   [Tp][64*Wp] int8  the same matrix as 0/1 bytes (tcgen05 path only)
+//   nbits    [Tp] int32             popcount of every row (= number of clades of the tree)
+//   S_pad    [Tp][C] int64          sum over the column trees i of chain c of (RF(p,i)+1)^2
+//   S        [C][n_rows][C] int64   the rows the caller asked for, zero-padding removed in closed form
+#include <algorithm>
+#include <cmath>
+
+#include "asm_internal.h"
+
+namespace {
+
+struct SegTableDev {
+  int32_t n_seg;
+  int32_t delta;
+  int32_t words;   // stored words per source row
+  int32_t Wp;      // padded words per operand row
+  int64_t Tp;
+  const uint64_t* chain_bits[ASM_MAX_CHAINS];
+  Segment seg[kMaxSegments];
+};
+
+// One warp per padded row: copy (zero-extended) or zero-fill, and count the set bits.
+__global__ void __launch_bounds__(256) gather_bits_kernel(const SegTableDev* __restrict__ tab,
+                                                           uint64_t* __restrict__ out, int32_t* __restrict__ nbits) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const int64_t Tp = tab->Tp;
+  const int Wp = tab->Wp, words = tab->words, delta = tab->delta, n_seg = tab->n_seg;
+  for (int64_t p = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); p < Tp;
+       p += (int64_t)gridDim.x * warps_per_block) {
+    // binary search: last segment with dst_off <= p
+    int lo = 0, hi = n_seg - 1;
+    while (lo < hi) {
+      int mid = (lo + hi + 1) >> 1;
+      if (tab->seg[mid].dst_off <= p) lo = mid; else hi = mid - 1;
+    }
+    const Segment& s = tab->seg[lo];
+    const int64_t j = p - s.dst_off;
+    const bool live = j < s.n;
+    const uint64_t* src = live ? tab->chain_bits[s.chain] + (size_t)(s.src_first + j * delta) * words : nullptr;
+    int cnt = 0;
+    for (int w = lane; w < Wp; w += 32) {
+      uint64_t v = (live && w < words) ? __ldg(src + w) : 0ULL;
+      out[(size_t)p * Wp + w] = v;
+      cnt += __popcll(v);
+    }
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) nbits[p] = cnt;
+  }
+}
+
+// bits -> 0/1 bytes.  One thread expands one 64-bit word into 64 bytes (four 16-byte stores).
+__global__ void __launch_bounds__(256) expand_i8_kernel(const uint64_t* __restrict__ bits, uint4* __restrict__ out,
+                                                         size_t n_words) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i < n_words; i += (size_t)gridDim.x * blockDim.x) {
+    uint64_t w = bits[i];
+    uint4 q[4];
+    uint32_t* o = reinterpret_cast<uint32_t*>(q);
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      uint32_t b = (uint32_t)(w >> (4 * k)) & 0xFu;
+      o[k] = (b * 0x00204081u) & 0x01010101u;  // bit t of the nibble -> byte t
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) out[i * 4 + k] = q[k];
+  }
+}
+
+struct CompactParams {
+  int32_t C, n_rows, subtract_pad;
+  int64_t row_pos0[ASM_MAX_CHAINS], row_posB[ASM_MAX_CHAINS], padB[ASM_MAX_CHAINS];
+  int32_t rowsA[ASM_MAX_CHAINS];
+};
+
+__global__ void __launch_bounds__(256) compact_kernel(const CompactParams* __restrict__ prm,
+                                                       const long long* __restrict__ S_pad,
+                                                       const int32_t* __restrict__ nbits, long long* __restrict__ out) {
+  const int C = prm->C, n_rows = prm->n_rows;
+  const int64_t total = (int64_t)C * n_rows * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t ar = i / C;
+    int r = (int)(ar % n_rows);
+    int a = (int)(ar / n_rows);
+    int64_t p = r < prm->rowsA[a] ? prm->row_pos0[a] + r : prm->row_posB[a] + (r - prm->rowsA[a]);
+    long long v = S_pad[p * C + c];
+    if (prm->subtract_pad) {
+      long long e = (long long)nbits[p] + 1;  // RF(tree, empty row) + 1
+      v -= prm->padB[c] * e * e;
+    }
+    out[i] = v;
+  }
+}
+
+// One block per ordered chain pair (a, b).  The per-row values are produced in parallel into shared
+// memory, then thread 0 adds them in ascending row order: the sequential sum of TreePSRF.mean
+// (TreePSRF.java:264-271).  Row value: TreePSRF.java:287-292.
+constexpr int kFinishChunk = 1024;
+__global__ void __launch_bounds__(256) psrf_finish_kernel(const long long* __restrict__ S, int C, int n_rows,
+                                                           double* __restrict__ psrf_rows,
+                                                           double* __restrict__ psrf_mean) {
+  __shared__ double vals[kFinishChunk];
+  const int a = blockIdx.x / C, b = blockIdx.x % C;
+  double sum = 0;
+  for (int r0 = 0; r0 < n_rows; r0 += kFinishChunk) {
+    const int n = min(kFinishChunk, n_rows - r0);
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+      const long long* row = S + ((size_t)a * n_rows + (r0 + k)) * C;
+      const double varIn = (double)row[a];
+      const double varBetween = (double)row[b];
+      double psrf;
+      if (varIn != 0) {
+        psrf = sqrt(varBetween / varIn);
+      } else {
+        psrf = sqrt(varBetween);
+      }
+      vals[k] = psrf;
+      if (psrf_rows) psrf_rows[((size_t)a * n_rows + (r0 + k)) * C + b] = psrf;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int k = 0; k < n; k++) sum = __dadd_rn(sum, vals[k]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) psrf_mean[a * C + b] = sum / (double)n_rows;  // 0/0 = NaN for no rows, as in Java
+}
+
+inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+}  // namespace
+
+int32_t psrf_build_layout(asm_ctx* ctx, const int32_t* burnin, int32_t row_start, int32_t end, int32_t delta) {
+  PsrfLayout& L = ctx->layout;
+  const int C = ctx->n_chains;
+  if (delta < 1) return asm_fail(ctx, ASM_E_INVALID, "psrf: delta must be >= 1, not %d", delta);
+  if (row_start < 0 || row_start % delta != 0)
+    return asm_fail(ctx, ASM_E_INVALID, "psrf: row_start %d must be a non-negative multiple of delta %d", row_start, delta);
+  if (end < 0) return asm_fail(ctx, ASM_E_INVALID, "psrf: negative end");
+  for (int c = 0; c < C; c++) {
+    if (burnin[c] < 0) return asm_fail(ctx, ASM_E_RANGE, "psrf: negative burn-in for chain %d", c);
+    if (end > ctx->trees[c].n)
+      return asm_fail(ctx, ASM_E_RANGE, "psrf: end %d past chain %d's %lld trees", end, c, (long long)ctx->trees[c].n);
+  }
+  L = PsrfLayout();
+  L.C = C;
+  L.delta = delta;
+  L.row_start = row_start;
+  L.end = end;
+  L.n_rows = end > row_start ? (end - row_start + delta - 1) / delta : 0;
+  L.Wp = (int32_t)round_up(ctx->words > 0 ? ctx->words : 1, kBitsPad / 64);
+  if (L.n_rows == 0) return ASM_OK;
+  int64_t off = 0;
+  for (int c = 0; c < C; c++) {
+    int64_t q = round_up(burnin[c], delta);         // TreePSRF.java:296-301
+    int64_t u = std::min<int64_t>(row_start, q);
+    int64_t m = (end - u + delta - 1) / delta;       // thinned trees u, u+delta, ... < end
+    int64_t kq = std::min<int64_t>((q - u) / delta, m);
+    int64_t kr = (row_start - u) / delta;
+    int64_t nA = kq, nB = m - kq;
+    int64_t offA = off;
+    if (nA > 0) {
+      L.seg[L.n_seg++] = Segment{off, nA, u, c, 0};
+      off += round_up(nA, kBlockRows);
+    }
+    int64_t offB = off;
+    if (nB > 0) {
+      L.seg[L.n_seg++] = Segment{off, nB, u + kq * delta, c, 1};
+      off += round_up(nB, kBlockRows);
+      L.padB[c] = round_up(nB, kBlockRows) - nB;
+    } else {
+      L.padB[c] = 0;
+    }
+    L.rowsA[c] = (int32_t)std::max<int64_t>(0, kq - kr);
+    L.row_pos0[c] = offA + kr;
+    L.row_posB[c] = offB + std::max<int64_t>(kr - kq, 0);
+  }
+  L.Tp = off;
+  return ASM_OK;
+}
+
+int32_t psrf_gather_bits(asm_ctx* ctx) {
+  PsrfLayout& L = ctx->layout;
+  int32_t rc;
+  if ((rc = asm_reserve(ctx, ctx->opnd_bits, sizeof(uint64_t) * (size_t)L.Tp * L.Wp)) != ASM_OK) return rc;
+  if ((rc = asm_reserve(ctx, ctx->nbits, sizeof(int32_t) * (size_t)L.Tp)) != ASM_OK) return rc;
+  if ((rc = asm_reserve(ctx, ctx->seg_dev, sizeof(SegTableDev))) != ASM_OK) return rc;
+  const int64_t n_tiles = L.Tp / kTileRows;
+  if ((rc = asm_reserve(ctx, ctx->blk_meta, sizeof(int2) * (size_t)n_tiles)) != ASM_OK) return rc;
+
+  SegTableDev tab;
+  tab.n_seg = L.n_seg;
+  tab.delta = L.delta;
+  tab.words = ctx->words;
+  tab.Wp = L.Wp;
+  tab.Tp = L.Tp;
+  for (int c = 0; c < ctx->n_chains; c++) tab.chain_bits[c] = ctx->trees[c].d_bits;
+  for (int s = 0; s < L.n_seg; s++) tab.seg[s] = L.seg[s];
+  // pinned-less small upload: cudaMemcpyAsync from pageable memory is synchronous w.r.t. the host copy
+  ASM_CUDA(ctx, cudaMemcpyAsync(ctx->seg_dev.p, &tab, sizeof tab, cudaMemcpyHostToDevice, ctx->stream));
+
+  // per-tile metadata {chain, flags}
+  std::vector<int2> meta((size_t)n_tiles);
+  for (int s = 0; s < L.n_seg; s++) {
+    const Segment& g = L.seg[s];
+    const int64_t padded = round_up(g.n, kBlockRows);
+    // first live position (within the segment) that is an output row
+    int64_t first_row;
+    if (!g.is_col) {
+      first_row = (L.rowsA[g.chain] > 0) ? (L.row_pos0[g.chain] - g.dst_off) : g.n;
+    } else {
+      first_row = L.row_posB[g.chain] - g.dst_off;
+      if (L.n_rows - L.rowsA[g.chain] <= 0) first_row = g.n;
+    }
+    for (int64_t t = 0; t < padded / kTileRows; t++) {
+      int64_t lo = t * kTileRows, hi = std::min<int64_t>(lo + kTileRows, g.n);
+      uint32_t f = g.is_col ? kFlagCol : 0;
+      if (hi > lo && hi > first_row) f |= kFlagRows;
+      meta[(size_t)(g.dst_off / kTileRows + t)] = make_int2(g.chain, (int)f);
+    }
+  }
+  ASM_CUDA(ctx, cudaMemcpyAsync(ctx->blk_meta.p, meta.data(), sizeof(int2) * (size_t)n_tiles, cudaMemcpyHostToDevice,
+                                ctx->stream));
+  ASM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `tab` and `meta` live on this frame
+  {
+    LaunchScope ls(ctx, ASM_K_GATHER);
+    int blocks = (int)std::min<int64_t>((L.Tp + 7) / 8, (int64_t)ctx->sm_count * 16);
+    gather_bits_kernel<<<blocks, 256, 0, ctx->stream>>>((const SegTableDev*)ctx->seg_dev.p, (uint64_t*)ctx->opnd_bits.p,
+                                                        (int32_t*)ctx->nbits.p);
+  }
+  ASM_CUDA(ctx, cudaGetLastError());
+  // S_pad starts at zero; the distance kernels accumulate into it with integer atomics
+  if ((rc = asm_reserve(ctx, ctx->S_pad, sizeof(int64_t) * (size_t)L.Tp * L.C)) != ASM_OK) return rc;
+  ASM_CUDA(ctx, cudaMemsetAsync(ctx->S_pad.p, 0, sizeof(int64_t) * (size_t)L.Tp * L.C, ctx->stream));
+  return ASM_OK;
+}
+
+int32_t psrf_expand_i8(asm_ctx* ctx) {
+  PsrfLayout& L = ctx->layout;
+  const size_t n_words = (size_t)L.Tp * L.Wp;
+  int32_t rc = asm_reserve(ctx, ctx->opnd_i8, n_words * 64);
+  if (rc != ASM_OK) return rc;
+  {
+    LaunchScope ls(ctx, ASM_K_GATHER);
+    int blocks = (int)std::min<size_t>((n_words + 255) / 256, (size_t)ctx->sm_count * 32);
+    expand_i8_kernel<<<blocks, 256, 0, ctx->stream>>>((const uint64_t*)ctx->opnd_bits.p, (uint4*)ctx->opnd_i8.p, n_words);
+  }
+  ASM_CUDA(ctx, cudaGetLastError());
+  return ASM_OK;
+}
+
+int32_t psrf_compact(asm_ctx* ctx, asm_shard shard, int64_t* d_S_out) {
+  PsrfLayout& L = ctx->layout;
+  CompactParams prm;
+  prm.C = L.C;
+  prm.n_rows = L.n_rows;
+  prm.subtract_pad = shard.shard_index == 0 ? 1 : 0;  // the closed-form pad term is removed exactly once
+  for (int c = 0; c < L.C; c++) {
+    prm.row_pos0[c] = L.row_pos0[c];
+    prm.row_posB[c] = L.row_posB[c];
+    prm.padB[c] = L.padB[c];
+    prm.rowsA[c] = L.rowsA[c];
+  }
+  int32_t rc = asm_reserve(ctx, ctx->misc, sizeof prm);
+  if (rc != ASM_OK) return rc;
+  ASM_CUDA(ctx, cudaMemcpyAsync(ctx->misc.p, &prm, sizeof prm, cudaMemcpyHostToDevice, ctx->stream));
+  ASM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  {
+    LaunchScope ls(ctx, ASM_K_PSRF_FINISH);
+    int64_t total = (int64_t)L.C * L.n_rows * L.C;
+    int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)ctx->sm_count * 16);
+    compact_kernel<<<blocks, 256, 0, ctx->stream>>>((const CompactParams*)ctx->misc.p, (const long long*)ctx->S_pad.p,
+                                                    (const int32_t*)ctx->nbits.p, (long long*)d_S_out);
+  }
+  ASM_CUDA(ctx, cudaGetLastError());
+  return ASM_OK;
+}
+
+int32_t psrf_finish(asm_ctx* ctx, const int64_t* d_S, int32_t n_rows, double* psrf_rows_host, double* psrf_mean_host) {
+  const int C = ctx->n_chains;
+  int32_t rc;
+  const size_t rows_bytes = sizeof(double) * (size_t)C * (size_t)n_rows * (size_t)C;
+  if ((rc = asm_reserve(ctx, ctx->psrf_mean, sizeof(double) * (size_t)C * C)) != ASM_OK) return rc;
+  double* d_rows = nullptr;
+  if (psrf_rows_host && rows_bytes) {
+    if ((rc = asm_reserve(ctx, ctx->psrf_rows, rows_bytes)) != ASM_OK) return rc;
+    d_rows = (double*)ctx->psrf_rows.p;
+  }
+  {
+    LaunchScope ls(ctx, ASM_K_PSRF_FINISH);
+    psrf_finish_kernel<<<C * C, 256, 0, ctx->stream>>>((const long long*)d_S, C, n_rows, d_rows, (double*)ctx->psrf_mean.p);
+  }
+  ASM_CUDA(ctx, cudaGetLastError());
+  ASM_CUDA(ctx, cudaMemcpyAsync(psrf_mean_host, ctx->psrf_mean.p, sizeof(double) * (size_t)C * C, cudaMemcpyDeviceToHost,
+                                ctx->stream));
+  if (d_rows) ASM_CUDA(ctx, cudaMemcpyAsync(psrf_rows_host, d_rows, rows_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  ASM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return ASM_OK;
+}

@@ -1,0 +1,509 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the ASM convergence-diagnostic hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload psrf|ess|cfg5] [--method i8|popc]
+
+Prints ONE JSON line (rank 0).  A "step" is one full pass of the hot path over one batch of
+synthetic input:
+
+  psrf (default; BASELINE.json configs[1], "cfg2"): 4 chains x 10,000 trees x 100 taxa, all-pairs
+      RF + the (d+1)^2 within/between-chain sums + per-row PSRF + per-pair means, i.e. everything
+      TreePSRF.converged2sided (TreePSRF.java:141-158) asks of the device for every ordered chain
+      pair.  metric = tree-pairs/sec, counting the ordered (row tree, column tree) pairs whose
+      distance enters the sums (T*T per step; the GPU evaluates each unordered pair once).
+      With N > 1 ranks the tile pairs are dealt round-robin to the ranks, partial S tables are
+      combined with one NCCL all-reduce, and per-GPU work is held fixed (trees per chain scale with
+      sqrt(N)): "scaling": "weak".
+  ess  (configs[2], "cfg3"): 1,000 traces x 1,000,000 samples, TraceESS.ACT/calcESS per trace.
+      metric = trace-samples/sec.  Traces shard over ranks (weak: 1,000 traces per rank).
+
+`value` is measured with the inputs resident in HBM; `e2e` goes through the C ABI with host
+buffers (pinned), host->device and device->host copies inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG2 = dict(n_chains=4, n_trees=10000, n_taxa=100, beta=3.3, moves=2, start_seed=1, seed0=20240001)
+CFG5 = dict(n_chains=32, n_trees=50000, n_taxa=500, beta=4.3, moves=2, start_seed=1, seed0=20240100)
+CFG3 = dict(n_traces=1000, n_samples=1_000_000, seed0=777)
+PHIS, MUS = [0.0, 0.5, 0.9, 0.99], [0.0, 1.0, -1e4]
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU while the timed region runs (NVML)."""
+
+    def __init__(self, index: int, period_s: float = 0.02):
+        self.index, self.period = index, period_s
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    _NAMES = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+              0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self._NAMES.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------------
+def gen_psrf_input(cfg, n_trees, want_topologies=False):
+    """Synthetic chains -> (encoder, [bits per chain], [topologies per chain] or None)."""
+    import asm_b200 as A
+    from asm_b200 import _lib as L
+    enc = A.Encoder(cfg["n_taxa"])
+    ids, topo = [], []
+    for c in range(cfg["n_chains"]):
+        l, r, root, i = L.synth_tree_chain(cfg["n_taxa"], n_trees, cfg["start_seed"], cfg["seed0"] + c, cfg["moves"],
+                                           cfg["beta"], topologies=want_topologies, encoder=enc)
+        ids.append(i)
+        topo.append((l, r, root))
+    words = enc.words
+    bits = [enc.bits(i, words) for i in ids]
+    return enc, bits, (topo if want_topologies else None)
+
+
+def gen_traces(n_traces, n_samples, seed0, first=0, out=None):
+    from concurrent.futures import ThreadPoolExecutor
+    from asm_b200 import _lib as L
+    x = np.empty((n_traces, n_samples), dtype=np.float64) if out is None else out
+
+    def one(j):
+        g = first + j
+        L.synth_ar1(n_samples, MUS[g % 3], PHIS[g % 4], seed0 + g, out=x[j])
+
+    with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 1)) as ex:
+        list(ex.map(one, range(n_traces)))
+    return x
+
+
+def pinned_like(a: np.ndarray):
+    """Copy `a` into page-locked host memory (torch is plumbing here) and return (tensor, ndarray view)."""
+    import torch
+    t = torch.from_numpy(a)
+    try:
+        t = t.pin_memory()
+    except Exception:
+        pass
+    return t, t.numpy()
+
+
+# --------------------------------------------------------------------------------------------------
+def cpu_baseline_psrf(cfg, n_trees, sample_rows=2048):
+    """The reference's CPU path for this workload, as restated by the oracle (Java cannot run here):
+    calcPSRF's two column loops (TreePSRF.java:274-286) for `sample_rows` row trees against every
+    column tree of every chain, OpenMP over rows."""
+    import oracle as O
+    from asm_b200 import _lib as L
+    ts = O.TreeSet(cfg["n_chains"], cfg["n_taxa"])
+    for c in range(cfg["n_chains"]):
+        l, r, root, _ = L.synth_tree_chain(cfg["n_taxa"], n_trees, cfg["start_seed"], cfg["seed0"] + c, cfg["moves"],
+                                           cfg["beta"])
+        ts.add(c, l, r, root)
+    rows = min(sample_rows, n_trees)
+    burnin = [0] * cfg["n_chains"]
+    T = cfg["n_chains"] * n_trees
+    t0 = time.perf_counter()
+    # rows [n_trees-rows, n_trees) of chain 0 against all columns of all chains
+    S = ts.psrf_sums(burnin, n_trees - rows, n_trees, 1)
+    dt_all = time.perf_counter() - t0  # this evaluated C chains x rows rows
+    pairs = cfg["n_chains"] * rows * T
+    return {"value": pairs / dt_all, "unit": "tree-pairs/s", "cores": O.num_threads(), "kind": "port",
+            "sample": f"{cfg['n_chains']}x{rows} row trees x {T} column trees ({pairs:.3g} ordered pairs) in {dt_all:.2f}s; "
+                      f"C restatement of TreePSRF.calcPSRF with set-intersection RF, OpenMP", "seconds": dt_all,
+            "checksum": float(S.sum())}
+
+
+def cpu_baseline_ess(n_samples, seed0, budget_traces=None):
+    import oracle as O
+    cores = O.num_threads()
+    n_tr = budget_traces or max(cores, 4)
+    x = gen_traces(n_tr, n_samples, seed0)
+    t0 = time.perf_counter()
+    act, ess = O.ess_batch(x, literal=False)
+    dt = time.perf_counter() - t0
+    out = {"value": n_tr * n_samples / dt, "unit": "trace-samples/s", "cores": cores, "kind": "port",
+           "sample": f"{n_tr} traces x {n_samples} samples in {dt:.2f}s; C restatement of TraceESS.ACT, closed-form final "
+                     f"pass (the literal per-sample recomputation the JVM executes is ~6x slower), OpenMP over traces",
+           "seconds": dt}
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+def dist_setup(n_gpus):
+    """One process per GPU under torchrun; single process otherwise."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        return rank, world, local, dist
+    return 0, 1, 0, None
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the Java itself
+    cannot run in this image), bounded sample per step, all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warm = args.steps, args.warmup
+    if args.workload == "ess":
+        n = CFG3["n_samples"]
+        vals = []
+        for s in range(warm + steps):
+            r = cpu_baseline_ess(n, CFG3["seed0"])
+            if s >= warm:
+                vals.append(r)
+        v = float(np.mean([r["value"] for r in vals]))
+        line = {"metric": "trace-samples/sec (ESS)", "value": v, "unit": "trace-samples/s", "n_gpus": args.gpus,
+                "steps": steps, "warmup": warm, "ms_per_step": 1e3 * float(np.mean([r["seconds"] for r in vals])),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "impl": "reference", "config": {"workload": "cfg3: 1000 traces x 1M samples (bounded sample per step)"},
+                "cpu_baseline": {k: vals[-1][k] for k in ("kind", "cores", "sample")} | {"value": v, "unit": "trace-samples/s"},
+                "e2e": {"value": v, "unit": "trace-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    else:
+        cfg = CFG5 if args.workload == "cfg5" else CFG2
+        n_trees = cfg["n_trees"] if args.workload == "cfg5" else int(round(cfg["n_trees"] * math.sqrt(args.gpus)))
+        vals = []
+        for s in range(warm + steps):
+            r = cpu_baseline_psrf(cfg, n_trees, sample_rows=args.cpu_rows)
+            if s >= warm:
+                vals.append(r)
+        v = float(np.mean([r["value"] for r in vals]))
+        line = {"metric": "tree-pairs/sec (RF+PSRF)", "value": v, "unit": "tree-pairs/s", "n_gpus": args.gpus,
+                "steps": steps, "warmup": warm, "ms_per_step": 1e3 * float(np.mean([r["seconds"] for r in vals])),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64/int64", "data": "synthetic",
+                "impl": "reference",
+                "config": {"workload": f"{cfg['n_chains']} chains x {n_trees} trees x {cfg['n_taxa']} taxa (bounded row sample per step)"},
+                "cpu_baseline": {k: vals[-1][k] for k in ("kind", "cores", "sample")} | {"value": v, "unit": "tree-pairs/s"},
+                "e2e": {"value": v, "unit": "tree-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+def bench_psrf(args, rank, world, local, dist):
+    import asm_b200 as A
+    from asm_b200 import _lib as L
+    peaks = measured_peaks()
+    cfg = CFG5 if args.workload == "cfg5" else CFG2
+    n_trees = cfg["n_trees"] if args.workload == "cfg5" else int(round(cfg["n_trees"] * math.sqrt(world)))
+    method = L.ASM_RF_I8 if args.method == "i8" else L.ASM_RF_POPC
+    C = cfg["n_chains"]
+    T = C * n_trees
+    enc, bits, _ = gen_psrf_input(cfg, n_trees)
+    words = enc.words
+    burnin = [0] * C
+    ctx = A.GpuContext(C, device=local)
+    pinned = [pinned_like(b) for b in bits]
+    h2d_bytes = sum(b.nbytes for b in bits)
+
+    torch = None
+    d_S = None
+    if world > 1:
+        import torch
+        d_S = torch.zeros((C, n_trees, C), dtype=torch.int64, device=f"cuda:{local}")
+
+    def upload():
+        for c in range(C):
+            ctx.trees_set(c, pinned[c][1])
+
+    def step_resident():
+        if world == 1:
+            return ctx.psrf_eval(burnin, 0, n_trees, 1, method)
+        ctx.psrf_sums_device(burnin, 0, n_trees, 1, method, (rank, world), d_S.data_ptr())
+        dist.all_reduce(d_S, op=dist.ReduceOp.SUM)  # exact: int64 partial sums
+        torch.cuda.current_stream().synchronize()
+        return ctx.psrf_finish_device(d_S.data_ptr(), n_trees)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+        ctx.sync()
+
+    upload()
+    for _ in range(args.warmup):
+        mean = step_resident()
+        ctx.flush_l2()
+    # ---- timed: inputs resident in HBM --------------------------------------------------------------
+    ctx.profile_enable(False)
+    sampler = ClockSampler(local)
+    per_step = []
+    barrier()
+    launches0 = ctx.launch_count()
+    sampler.start()
+    for _ in range(args.steps):
+        ctx.flush_l2()  # L2 flushed between timed steps, outside the timed bracket
+        barrier()
+        t0 = time.perf_counter()
+        ctx.timer_mark(0)
+        mean = step_resident()
+        ctx.timer_mark(1)
+        dev_ms = ctx.timer_elapsed_ms(0, 1)
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        per_step.append(max(dev_ms, 0.0) if world == 1 else wall_ms)
+    clocks = sampler.stop()
+    launches = (ctx.launch_count() - launches0 - args.steps) // max(args.steps, 1)  # minus the flush kernel
+    ms = float(np.mean(per_step))
+    if world > 1:
+        t = torch.tensor([ms], device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = T * T / (ms * 1e-3)
+
+    # ---- kernel-only time for the roofline (CUDA events around the dominant kernel, same stream) ------
+    ctx.profile_enable(True)
+    ctx.profile_reset()
+    for _ in range(max(3, min(args.steps, 10))):
+        ctx.flush_l2()
+        step_resident()
+    fam = L.K_RF_I8 if method == L.ASM_RF_I8 else L.K_RF_POPC
+    k_ms, k_n = ctx.profile_get(fam)
+    fam_ms = {name: ctx.profile_get(f)[0] / max(k_n, 1) for name, f in
+              [("gather", L.K_GATHER), ("rf", fam), ("finish", L.K_PSRF_FINISH)]}
+    ctx.profile_enable(False)
+    k_ms /= max(k_n, 1)
+    lay = ctx.last_layout()
+    Dp, Tp = lay["padded_bits"], lay["padded_rows"]
+    D = enc.num_clades
+    if method == L.ASM_RF_I8:
+        # algorithmic int8 flops: D * T * (T-1) over unordered pairs, per launch / shards
+        alg = D * T * (T - 1) / world
+        achieved = alg / (k_ms * 1e-3) / 1e12
+        peak = 2.0 * peaks["bf16_tflops"]  # int8 dense = 2 x bf16 dense on B200; bf16 is the measured figure
+        roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "rf_i8_psrf_kernel", "kernel_ms": k_ms,
+                "peak_source": f"2 x bf16_tflops ({peaks['source']}); int8 dense is 2x bf16 dense on B200",
+                "algorithmic": "D*T*(T-1) int8 flop per launch (unordered pairs, 2 flop per MAC)"}
+    else:
+        # popcount variant: integer-pipe bound; HBM algorithmic bytes = operand read once + S written
+        alg_bytes = (Tp * Dp / 8 + 8 * Tp * C) / world
+        achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+        words_pairs = (D / 64.0) * T * (T - 1) / 2 / world
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "kernel": "rf_popc_psrf_kernel", "kernel_ms": k_ms,
+                "peak_source": f"hbm_gbs ({peaks['source']})",
+                "algorithmic": "T*D/8 operand bytes + 8*T*C S bytes per launch",
+                "note": "integer-pipe (LOP3+POPC) bound, not HBM bound: see int_pipe",
+                "int_pipe": {"xor_popc64_per_s": words_pairs / (k_ms * 1e-3), "unit": "64-bit XOR-popcounts/s"}}
+
+    # ---- e2e: host buffers through the C ABI, H2D + D2H inside the timed region ------------------------
+    e2e_steps = []
+    for i in range(args.warmup + args.steps):
+        ctx.flush_l2()
+        barrier()
+        t0 = time.perf_counter()
+        upload()
+        mean_e = step_resident()
+        dt = (time.perf_counter() - t0) * 1e3
+        if i >= args.warmup:
+            e2e_steps.append(dt)
+    e_ms = float(np.mean(e2e_steps))
+    if world > 1:
+        t = torch.tensor([e_ms], device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e_ms = float(t.item())
+    e2e = {"value": T * T / (e_ms * 1e-3), "unit": "tree-pairs/s", "h2d_bytes_per_step": int(h2d_bytes),
+           "d2h_bytes_per_step": int(C * C * 8), "ms_per_step": e_ms}
+
+    line = {"metric": "tree-pairs/sec (RF+PSRF)", "value": value, "unit": "tree-pairs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int8->s32 (tcgen05), int64 sums, f64 psrf" if method == L.ASM_RF_I8 else "u64 popc, int64 sums, f64 psrf",
+            "data": "synthetic",
+            "config": {"workload": f"{'cfg5' if args.workload == 'cfg5' else 'cfg2'}: {C} chains x {n_trees} trees x {cfg['n_taxa']} taxa, "
+                                   f"burnin=0 smoothing=1 delta=1", "method": args.method, "clades_D": int(D),
+                       "padded_bits": int(Dp), "padded_rows": int(Tp), "trees_T": int(T),
+                       "l2": "L2 flushed (256 MiB write) between timed steps, outside the timed bracket",
+                       "timing": "CUDA events on the library stream per step" if world == 1 else "host bracket after device sync, max over ranks",
+                       "generator": {k: cfg[k] for k in ("beta", "moves", "start_seed", "seed0")},
+                       "psrf_mean_01": float(mean[0, 1]), "psrf_mean_10": float(mean[1, 0])},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
+            "step_breakdown_ms": fam_ms}
+    return line, ctx
+
+
+def bench_ess(args, rank, world, local, dist, n_traces=None):
+    import asm_b200 as A
+    from asm_b200 import _lib as L
+    import torch
+    peaks = measured_peaks()
+    n_tr = n_traces or CFG3["n_traces"]
+    n = CFG3["n_samples"]
+    ctx = A.GpuContext(1, device=local)
+    host_t = torch.empty((n_tr, n), dtype=torch.float64)
+    try:
+        host_t = host_t.pin_memory()
+    except Exception:
+        pass
+    host = host_t.numpy()
+    gen_traces(n_tr, n, CFG3["seed0"], first=rank * n_tr, out=host)
+    dev = torch.empty((n_tr, n), dtype=torch.float64, device=f"cuda:{local}")
+    dev.copy_(host_t)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.sync()
+
+    for _ in range(args.warmup):
+        act, ess = ctx.ess_batch_device(dev.data_ptr(), n_tr, n, n)
+    sampler = ClockSampler(local, period_s=0.05)
+    per = []
+    barrier()
+    l0 = ctx.launch_count()
+    sampler.start()
+    for _ in range(args.steps):  # 8 GB of traces per step: inputs larger than L2, no flush needed
+        barrier()
+        ctx.timer_mark(0)
+        act, ess = ctx.ess_batch_device(dev.data_ptr(), n_tr, n, n)
+        ctx.timer_mark(1)
+        per.append(ctx.timer_elapsed_ms(0, 1))
+    clocks = sampler.stop()
+    launches = (ctx.launch_count() - l0) // max(args.steps, 1)
+    ms = float(np.mean(per))
+    if world > 1:
+        t = torch.tensor([ms], device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        g = [torch.zeros(n_tr, dtype=torch.float64, device=f"cuda:{local}") for _ in range(world)]
+        dist.all_gather(g, torch.from_numpy(ess).to(f"cuda:{local}"))  # ESS vector gather; min on host (Java NaN rules)
+    value = world * n_tr * n / (ms * 1e-3)
+    ctx.profile_enable(True)
+    ctx.profile_reset()
+    ctx.ess_batch_device(dev.data_ptr(), n_tr, n, n)
+    k_ms, k_n = ctx.profile_get(L.K_ESS_LAG)
+    f_ms, _ = ctx.profile_get(L.K_ESS_FINISH)
+    ctx.profile_enable(False)
+    lmax = min(n, 2000)
+    flops = 2.0 * (lmax * n - lmax * (lmax - 1) / 2) * n_tr
+    roof = {"bound": "hbm", "achieved": 8.0 * n_tr * n / (k_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": 8.0 * n_tr * n / (k_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None, "kernel": "ess_lag_kernel",
+            "kernel_ms": k_ms, "finish_ms": f_ms,
+            "note": "FP64-pipe bound (~500 flop/byte), not HBM bound: see fp64",
+            "fp64": {"achieved_tflops": flops / (k_ms * 1e-3) / 1e12, "unit": "TFLOP/s (separate DMUL+DADD, no FMA)",
+                     "algorithmic": "2*(L*n - L(L-1)/2) flop per trace, L = 2000"}}
+    e2e_ms = []
+    for i in range(2):
+        barrier()
+        t0 = time.perf_counter()
+        act2, ess2 = ctx.ess_batch(host)
+        e2e_ms.append((time.perf_counter() - t0) * 1e3)
+    e_ms = float(min(e2e_ms))
+    line = {"metric": "trace-samples/sec (ESS)", "value": value, "unit": "trace-samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"cfg3: {n_tr} traces x {n} samples per GPU, AR(1) phi in {PHIS}, mu in {MUS}, max_lag 2000",
+                       "l2": "inputs (8 GB per step) larger than L2"},
+            "clocks": clocks, "gpu_launches": int(launches), "roofline": roof,
+            "e2e": {"value": world * n_tr * n / (e_ms * 1e-3), "unit": "trace-samples/s", "h2d_bytes_per_step": int(host.nbytes),
+                    "d2h_bytes_per_step": int(16 * n_tr), "ms_per_step": e_ms},
+            "min_ess": float(np.nanmin(ess)), "bit_identical_e2e_vs_resident": bool(np.array_equal(ess, ess2, equal_nan=True))}
+    return line, ctx
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="psrf", choices=["psrf", "ess", "cfg5"])
+    ap.add_argument("--method", default=os.environ.get("ASM_BENCH_METHOD", "popc"), choices=["i8", "popc"])
+    ap.add_argument("--cpu-rows", type=int, default=2048, help="row trees per chain in the CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ess", action="store_true", help="skip the secondary ESS block of the default run")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    rank, world, local, dist = dist_setup(args.gpus)
+    if args.workload == "ess":
+        line, _ = bench_ess(args, rank, world, local, dist)
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_ess(CFG3["n_samples"], CFG3["seed0"])
+    else:
+        line, ctx = bench_psrf(args, rank, world, local, dist)
+        if rank == 0 and world == 1:
+            if not args.no_cpu_baseline:
+                cfg = CFG5 if args.workload == "cfg5" else CFG2
+                line["cpu_baseline"] = cpu_baseline_psrf(cfg, cfg["n_trees"], sample_rows=args.cpu_rows)
+            if not args.no_ess and args.workload == "psrf":
+                ctx.close()
+                ess_args = argparse.Namespace(**vars(args))
+                ess_args.steps, ess_args.warmup = min(args.steps, 5), 3
+                ess_line, _ = bench_ess(ess_args, rank, world, local, dist)
+                if not args.no_cpu_baseline:
+                    ess_line["cpu_baseline"] = cpu_baseline_ess(CFG3["n_samples"], CFG3["seed0"])
+                line["ess"] = ess_line
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,218 @@
+/*
+ * asmgpu.h -- C ABI of libasmgpu.so, the B200 (sm_100a) implementation of ASM's
+ * convergence-diagnostic hot path: TreePSRF's all-pairs tree distances with their within- and
+ * between-chain reductions, and TraceESS's batched autocorrelation / effective sample size.
+ *
+ * This is the drop-in boundary.  The reference (rbouckaert/asm) is pure Java and has no FFI;
+ * these are the entry points a Panama-FFM / JNI binding inside package asm.inference would
+ * bind (see INTEGRATION.md for the stub), one per arithmetic site of the reference.  Citations
+ * are file:line relative to the reference checkout.
+ *
+ * Conventions
+ *   - plain C: pointers and sizes only; every function returns int32_t, 0 = ASM_OK, < 0 = ASM_E_*;
+ *     nothing throws or aborts.  asm_last_error(ctx) gives the message of the last failure.
+ *   - the caller owns every host buffer and may free it on return (the library copies).
+ *   - one asm_ctx = one GPU.  A context may be used from any thread, one call at a time
+ *     (the reference calls criteria from the single LogWatcherThread, AutoStopMCMC.java:214,
+ *     397-409); the library selects its device on every call.
+ *   - there is no CPU fallback: without a usable sm_100 device asm_create fails with
+ *     ASM_E_NO_DEVICE and every compute entry point fails with it as well.
+ *
+ * Tree encoding: a tree is the set of its clades, a clade is the set of
+ * leaf numbers under an internal node (CladeDifference.java:107-141, root included).  A global
+ * dictionary numbers distinct clades 0..D-1 in first-seen order; a tree is a row of D bits,
+ * stored as little-endian uint64 words, bit j of word w <-> clade id 64*w + j.  Robinson-Foulds
+ * distance = popcount(row_a XOR row_b) = |a| + |b| - 2 a.b.
+ */
+#ifndef ASMGPU_H_
+#define ASMGPU_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ASM_OK 0
+#define ASM_E_INVALID (-1)    /* bad argument (IllegalArgumentException sites of the reference) */
+#define ASM_E_NO_DEVICE (-2)  /* no CUDA device / not sm_100 / extension not usable          */
+#define ASM_E_CUDA (-3)       /* a CUDA call or kernel failed; see asm_last_error            */
+#define ASM_E_RANGE (-4)      /* index past the stored trees / samples (the Java would throw) */
+#define ASM_E_NOMEM (-5)
+#define ASM_E_UNSUPPORTED (-6)
+
+/* distance-kernel selector ("method") */
+#define ASM_RF_POPC 0 /* XOR + POPC tiles on the integer pipe, bulk-async (TMA) smem staging  */
+#define ASM_RF_I8 1   /* int8 tcgen05.mma (UTCIMMA) contraction, TMA operands, TMEM accumulators */
+
+#define ASM_MAX_CHAINS 64
+#define ASM_MAX_LAG 2000 /* TraceESS.java:21 */
+
+typedef struct asm_ctx asm_ctx;
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+
+const char* asm_version(void);
+/* Number of CUDA devices visible, 0 if none (never fails). */
+int32_t asm_device_count(void);
+/* Create a context on CUDA device `device` for `n_chains` chains (TraceInfo(chainCount),
+ * TraceInfo.java:31-41; criteria setup(nChains, traceInfo), MCMCConvergenceCriterion.java:20). */
+int32_t asm_create(asm_ctx** out, int32_t device, int32_t n_chains);
+int32_t asm_destroy(asm_ctx* ctx);
+/* Message of the last failure on this context ("" if none).  ctx may be NULL: then the message
+ * of the last failed asm_create on this thread. */
+const char* asm_last_error(const asm_ctx* ctx);
+
+/* ---- trees: replaces traceInfo.trees[chain] (TraceInfo.java:27, AutoStopMCMC.java:536) ------- */
+
+/* Replace chain `chain`'s trees by n_trees bit rows, row-major [n_trees][words_per_tree]. */
+int32_t asm_trees_set(asm_ctx* ctx, int32_t chain, int64_t n_trees, int32_t words_per_tree, const uint64_t* bits);
+/* Append n_new rows (the streaming runner adds one tree per chain per check).  words_per_tree
+ * may exceed the stored width when the dictionary grew: older rows are zero-extended. */
+int32_t asm_trees_append(asm_ctx* ctx, int32_t chain, int64_t n_new, int32_t words_per_tree, const uint64_t* bits);
+int32_t asm_trees_count(const asm_ctx* ctx, int32_t chain, int64_t* n_trees, int32_t* words_per_tree);
+/* Same as asm_trees_set, but `d_bits` is a device pointer on the context's GPU (used by the
+ * benchmark's "inputs already resident in HBM" leg and by multi-GPU replicas). */
+int32_t asm_trees_set_device(asm_ctx* ctx, int32_t chain, int64_t n_trees, int32_t words_per_tree,
+                             const uint64_t* d_bits);
+
+/* ---- parity probes ---------------------------------------------------------------------------- */
+
+/* out[(r-r0)*(c1-c0) + (c-c0)] = RF(tree[chainA][r], tree[chainB][c]) for r in [r0,r1),
+ * c in [c0,c1): the value `m.distance(tree1, tree2)` supplies at TreeESS.java:179-180 (RF in
+ * place of RNNIMetric).  `out` is a host buffer. */
+int32_t asm_rf_block(asm_ctx* ctx, int32_t chainA, int64_t r0, int64_t r1, int32_t chainB, int64_t c0, int64_t c1,
+                     int32_t method, uint16_t* out);
+/* out[id] = number of trees in [from,to) of `chain` that contain clade id, id < 64*words:
+ * the per-chain clade counts of CladeDifference.process (CladeDifference.java:147-159). */
+int32_t asm_clade_counts(asm_ctx* ctx, int32_t chain, int64_t from, int64_t to, int32_t* out);
+
+/* ---- PSRF: replaces calcPSRF + the row loops of converged2sided ------------------------------- */
+
+/* Work split for multi-GPU runs: this context evaluates tiles t with t % shard_count ==
+ * shard_index of the (symmetric) pair matrix; the partial S tables of all shards add up (exact
+ * int64) to the full table.  {0, 1} = everything. */
+typedef struct {
+  int32_t shard_index;
+  int32_t shard_count;
+} asm_shard;
+
+/* S[((a*n_rows) + r)*C + c] = sum over columns i of chain c, i = start(burnin[c]), +delta, ...
+ * < end (burn-in rounded up to a multiple of delta, TreePSRF.java:296-301), of
+ * distancePlusOne(a, x_r, c, i)^2 with x_r = row_start + r*delta, n_rows = ceil((end -
+ * row_start)/delta): varIn (c == a) and varBetween (c != a) of calcPSRF (TreePSRF.java:275-286)
+ * for every chain pair.  Exact integers.  S is a host buffer [C][n_rows][C]. */
+int32_t asm_psrf_sums(asm_ctx* ctx, const int32_t* burnin, int32_t row_start, int32_t end, int32_t delta,
+                      int32_t method, asm_shard shard, int64_t* S);
+/* Same, S left on the device (d_S is a device pointer to [C][n_rows][C] int64) so that partial
+ * tables can be combined with an NCCL all-reduce without a host round trip. */
+int32_t asm_psrf_sums_device(asm_ctx* ctx, const int32_t* burnin, int32_t row_start, int32_t end, int32_t delta,
+                             int32_t method, asm_shard shard, int64_t* d_S);
+/* From a complete S table on the device: psrf_rows[((a*n_rows)+r)*C + b] = S[a,r][a] != 0 ?
+ * sqrt(S[a,r][b] / S[a,r][a]) : sqrt(S[a,r][b]) (TreePSRF.java:287-292) and psrf_mean[a*C + b] =
+ * (sequential sum over r ascending) / n_rows (TreePSRF.java:264-271).  psrf_rows may be NULL.
+ * Both outputs are host buffers. */
+int32_t asm_psrf_finish_device(asm_ctx* ctx, const int64_t* d_S, int32_t n_rows, double* psrf_rows,
+                               double* psrf_mean);
+/* asm_psrf_sums + asm_psrf_finish in one call on one GPU: everything converged2sided
+ * (TreePSRF.java:141-158) needs from the device.  psrf_mean[0*C+1] is psrf1mean and
+ * psrf_mean[1*C+0] is psrf2mean of the two-chain reference. */
+int32_t asm_psrf_eval(asm_ctx* ctx, const int32_t* burnin, int32_t row_start, int32_t end, int32_t delta,
+                      int32_t method, double* psrf_rows, double* psrf_mean);
+
+/* ---- ESS: replaces TraceESS.ACT / calcESS ------------------------------------------------------ */
+
+/* For each of n_traces independent traces (row t at traces + t*stride, n_samples doubles):
+ * act_out[t] = ACT(trace, 0, n_samples) (TraceESS.java:130-179, max_lag = MAX_LAG = 2000) and
+ * ess_out[t] = n_samples / act_out[t] (TraceESS.java:126-128).  Either output may be NULL.
+ * All pointers are host pointers. */
+int32_t asm_ess_batch(asm_ctx* ctx, int32_t n_traces, int64_t n_samples, int64_t stride, const double* traces,
+                      int32_t max_lag, double* act_out, double* ess_out);
+/* Same with `d_traces` on the device; outputs are host buffers. */
+int32_t asm_ess_batch_device(asm_ctx* ctx, int32_t n_traces, int64_t n_samples, int64_t stride,
+                             const double* d_traces, int32_t max_lag, double* act_out, double* ess_out);
+/* Streaming form.  Append n_new log lines of n_cols columns for `chain`, row-major
+ * [n_new][n_cols] (readLogLines, AutoStopMCMC.java:459-466). */
+int32_t asm_traces_append(asm_ctx* ctx, int32_t chain, int32_t n_cols, int64_t n_new, const double* values);
+int32_t asm_traces_count(const asm_ctx* ctx, int32_t chain, int64_t* n_samples, int32_t* n_cols);
+/* ess_out[j] = ESS of the concatenation over chains i of column cols[j], samples
+ * [burnin[i], end) (TraceESS.java:53-62).  The min with Java NaN semantics (:63) and the
+ * threshold (:68) stay with the caller. */
+int32_t asm_ess_eval(asm_ctx* ctx, const int32_t* burnin, int32_t end, const int32_t* cols, int32_t n_cols,
+                     double* ess_out);
+
+/* ---- measurement hooks -------------------------------------------------------------------------- */
+
+/* CUDA-event timing on the context's own stream (torch.cuda.Event only sees torch's stream).
+ * asm_timer_mark records event `slot` (0..15); asm_timer_elapsed_ms synchronises on `to`. */
+int32_t asm_timer_mark(asm_ctx* ctx, int32_t slot);
+int32_t asm_timer_elapsed_ms(asm_ctx* ctx, int32_t from, int32_t to, float* ms);
+/* Accumulated device time and launch count of the library's kernels since the last reset,
+ * per kernel family (ASM_K_*), measured with events around every launch when profiling is on. */
+#define ASM_K_GATHER 0
+#define ASM_K_RF_POPC 1
+#define ASM_K_RF_I8 2
+#define ASM_K_PSRF_FINISH 3
+#define ASM_K_CLADE_COUNTS 4
+#define ASM_K_ESS_LAG 5
+#define ASM_K_ESS_FINISH 6
+#define ASM_K_MISC 7
+#define ASM_K_COUNT 8
+int32_t asm_profile_enable(asm_ctx* ctx, int32_t on);
+int32_t asm_profile_reset(asm_ctx* ctx);
+int32_t asm_profile_get(asm_ctx* ctx, int32_t family, double* total_ms, int64_t* launches);
+/* Total kernel launches issued by this context since creation (always counted). */
+int64_t asm_launch_count(const asm_ctx* ctx);
+int32_t asm_sync(asm_ctx* ctx);
+/* Write `bytes` of a device scratch buffer (> L2) to evict the L2 between timed iterations. */
+int32_t asm_flush_l2(asm_ctx* ctx);
+/* Layout facts of the last PSRF evaluation: padded row count, dictionary width in bits (padded),
+ * tiles evaluated by this shard, tiles in the full problem. */
+int32_t asm_psrf_last_layout(const asm_ctx* ctx, int64_t* padded_rows, int64_t* padded_bits, int64_t* tiles_done,
+                             int64_t* tiles_total);
+
+/* ---- host encoder (the step before the path): trees -> clades -> dictionary -> bit rows -------- */
+/* CPU only; usable without a GPU.  Follows CladeDifference.traverse (CladeDifference.java:107-144)
+ * for clade identity and the NEXUS/Newick conventions of readTreeLogLine (AutoStopMCMC.java:486-538). */
+
+typedef struct asm_encoder asm_encoder;
+
+int32_t asm_encoder_create(asm_encoder** out, int32_t n_taxa);
+int32_t asm_encoder_destroy(asm_encoder* enc);
+/* Trees as child arrays: left/right are [n_trees][2*n_taxa-1] (-1 for the leaves 0..n_taxa-1),
+ * root is [n_trees].  clade_ids_out is [n_trees][n_taxa-1]: dictionary ids in post-order (children
+ * before parent, left before right), new clades numbered in first-seen order. */
+int32_t asm_encoder_add_topologies(asm_encoder* enc, int64_t n_trees, const int32_t* left, const int32_t* right,
+                                   const int32_t* root, int32_t* clade_ids_out);
+/* One Newick string whose leaf labels are integers (the NEXUS translate index); label_offset is
+ * subtracted from each label (parser.offsetInput = 1, AutoStopMCMC.java:527).  Branch lengths and
+ * [&...] annotations are skipped. */
+int32_t asm_encoder_add_newick(asm_encoder* enc, const char* newick, int32_t label_offset, int32_t* clade_ids_out);
+int64_t asm_encoder_num_clades(const asm_encoder* enc);
+/* Sorted leaf numbers of clade `id`; returns the clade size or ASM_E_*. */
+int32_t asm_encoder_clade_leaves(const asm_encoder* enc, int64_t id, int32_t* leaves_out, int32_t cap);
+/* Words per bit row for the current dictionary: ceil(D/64) rounded up to a multiple of 4 (256 bits). */
+int32_t asm_encoder_words(const asm_encoder* enc);
+/* bits_out[n_trees][words_per_tree] from clade_ids[n_trees][ids_per_tree]. */
+int32_t asm_encode_bits(const int32_t* clade_ids, int64_t n_trees, int32_t ids_per_tree, int32_t words_per_tree,
+                        uint64_t* bits_out);
+
+/* ---- synthetic inputs of the named shapes (BASELINE.json configs) ---------------- */
+
+/* One chain of n_trees rooted binary trees on n_taxa leaves: all chains share the start tree
+ * (random-join shape from start_seed); each sample applies `moves_per_sample` Metropolis steps of
+ * a random rooted NNI with target exp(-beta * #clades not in the start tree), seeded by
+ * chain_seed.  left/right/root as in asm_encoder_add_topologies (any may be NULL);
+ * if enc != NULL, clade_ids_out [n_trees][n_taxa-1] receives dictionary ids (ids of clades new to
+ * the dictionary are handed out in the order the walk creates them). */
+int32_t asm_synth_tree_chain(int32_t n_taxa, int64_t n_trees, uint64_t start_seed, uint64_t chain_seed,
+                             int32_t moves_per_sample, double beta, int32_t* left, int32_t* right, int32_t* root,
+                             asm_encoder* enc, int32_t* clade_ids_out);
+/* AR(1) trace x_t = mu + phi (x_{t-1} - mu) + eps_t, eps ~ N(0,1) from a counter-based generator
+ * keyed by seed; x_0 drawn from the stationary law. */
+int32_t asm_synth_ar1(double* out, int64_t n, double mu, double phi, uint64_t seed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASMGPU_H_ */

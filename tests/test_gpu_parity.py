@@ -1,0 +1,250 @@
+"""GPU parity: every C-ABI compute entry point against the CPU oracle on the same seeded inputs.
+Integer results (RF, clade counts, S) must be identical; PSRF/ESS doubles must be bit-identical
+(which is stricter than the 1e-12 relative tolerance the north star states)."""
+import numpy as np
+import pytest
+
+import oracle as O
+from conftest import SynthChains, bits_equal
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-12  # north-star tolerance for PSRF / ESS doubles; the tests below demand bit equality
+
+METHODS = [0, 1]  # ASM_RF_POPC, ASM_RF_I8
+
+
+def _ctx(gpu, chains):
+    ctx = gpu.GpuContext(chains.n_chains)
+    chains.upload(ctx)
+    return ctx
+
+
+# ---------------------------------------------------------------- RF distances (TreeESS.java:179-180)
+@pytest.mark.parametrize("method", METHODS)
+def test_rf_block_bit_exact(gpu, multi_chains, method):
+    ch = multi_chains
+    with _ctx(gpu, ch) as ctx:
+        for (a, r0, r1, b, c0, c1) in [(0, 0, 300, 0, 0, 300), (0, 17, 200, 3, 5, 411), (2, 650, 700, 1, 0, 700)]:
+            got = ctx.rf_block(a, r0, r1, b, c0, c1, method)
+            want = ch.ts.rf_block(a, r0, r1, b, c0, c1)
+            assert got.dtype == np.uint16 and np.array_equal(got, want)
+        assert ctx.rf_block(0, 5, 5, 1, 0, 10, method).shape == (0, 10)  # empty range
+
+
+def test_rf_known_answers(gpu):
+    # two fixed 4-taxon trees ((0,1),(2,3)) and ((0,2),(1,3)): clades {01,23,0123} vs {02,13,0123} -> RF 4;
+    # caterpillars (((0,1),2),3) vs (((0,2),1),3): {01,012,0123} vs {02,012,0123} -> RF 2
+    import asm_b200 as A
+    enc = A.Encoder(4)
+    t = [enc.add_newick(s, 1) for s in ("((1,2),(3,4));", "((1,3),(2,4));", "(((1,2),3),4);", "(((1,3),2),4);",
+                                        "((1:0.1,2:0.2)[&x=1]:0.3,(3:1e-2,4:1):0.5):0.0;")]
+    bits = enc.bits(np.stack(t))
+    with gpu.GpuContext(1) as ctx:
+        ctx.trees_set(0, bits)
+        d = ctx.rf_block(0, 0, 5, 0, 0, 5)
+    assert d[0, 1] == 4 and d[2, 3] == 2 and d[0, 4] == 0 and np.array_equal(d, d.T) and not d.diagonal().any()
+
+
+# ---------------------------------------------------------------- clade counts (CladeDifference.java:147-159)
+def test_clade_counts_bit_exact(gpu, multi_chains):
+    ch = multi_chains
+    D = ch.ts.num_clades
+    assert D == ch.enc.num_clades
+    with _ctx(gpu, ch) as ctx:
+        for c, (lo, hi) in enumerate([(0, 700), (100, 101), (3, 699), (0, 0)]):
+            got = ctx.clade_counts(c, lo, hi)
+            want = ch.ts.clade_counts(c, lo, hi)
+            assert np.array_equal(got[:D], want) and not got[D:].any()
+    # identity of the dictionary: same clade <-> same id on both sides
+    for cid in [0, 1, D // 2, D - 1]:
+        assert ch.ts.clade_key(cid) == "".join(f"{x}," for x in ch.enc.clade_leaves(cid))
+
+
+# ---------------------------------------------------------------- S sums (TreePSRF.java:275-286)
+PSRF_CASES = [
+    # burnin, row_start, end, delta
+    ([0, 0], 0, 300, 1),
+    ([30, 30], 0, 300, 1),        # columns trimmed, rows not (TreePSRF.java:141-144 vs :276-277)
+    ([31, 17], 30, 299, 1),       # ragged burn-in, smoothing < 1
+    ([0, 0], 0, 300, 2),          # thinning
+    ([33, 10], 28, 296, 4),       # burn-in rounded up to a multiple of delta (:296-301)
+    ([300, 0], 0, 300, 1),        # chain 0 has no columns: varIn == 0 branch (:287-292)
+    ([0, 0], 0, 1, 1),            # a single tree
+]
+
+
+@pytest.mark.parametrize("method", METHODS)
+@pytest.mark.parametrize("burnin,row_start,end,delta", PSRF_CASES)
+def test_psrf_sums_two_chains(gpu, small_chains, method, burnin, row_start, end, delta):
+    ch = small_chains
+    want = ch.ts.psrf_sums(burnin, row_start, end, delta)
+    with _ctx(gpu, ch) as ctx:
+        got = ctx.psrf_sums(burnin, row_start, end, delta, method)
+    assert got.dtype == np.int64 and got.shape == want.shape
+    assert np.array_equal(got.astype(np.float64), want)  # exact integers < 2^53
+
+
+@pytest.mark.parametrize("method", METHODS)
+def test_psrf_eval_two_chains_matches_reference_rows(gpu, small_chains, method):
+    """psrf_mean[0][1] / [1][0] are psrf1mean / psrf2mean of converged2sided (TreePSRF.java:145,157)."""
+    ch = small_chains
+    for burnin, row_start, end, delta in PSRF_CASES:
+        with _ctx(gpu, ch) as ctx:
+            rows, mean = ctx.psrf_eval(burnin, row_start, end, delta, method, want_rows=True)
+        for (a, b) in [(0, 1), (1, 0)]:
+            if (end - row_start) % delta:  # the Java only ever calls with both divisible by delta
+                continue
+            m, r = ch.ts.psrf_rows_mean(a, b, row_start, burnin, end, delta, want_rows=True)
+            assert bits_equal(rows[a, :, b], r), (burnin, row_start, end, delta, a, b)
+            assert bits_equal(np.array([mean[a, b]]), np.array([m]))
+            if np.isfinite(m) and m != 0:
+                assert abs(mean[a, b] - m) <= REL_TOL * abs(m)
+
+
+@pytest.mark.parametrize("method", METHODS)
+def test_psrf_multi_chain(gpu, multi_chains, method):
+    ch = multi_chains
+    cases = [([0, 0, 0, 0], 0, 700, 1), ([70, 10, 0, 33], 70, 700, 1), ([5, 9, 300, 2], 0, 696, 8)]
+    for burnin, row_start, end, delta in cases:
+        want = ch.ts.psrf_sums(burnin, row_start, end, delta)
+        with _ctx(gpu, ch) as ctx:
+            got = ctx.psrf_sums(burnin, row_start, end, delta, method)
+            rows, mean = ctx.psrf_eval(burnin, row_start, end, delta, method, want_rows=True)
+        assert np.array_equal(got.astype(np.float64), want)
+        for a in range(4):
+            for b in range(4):
+                if a == b:
+                    continue
+                m, r = ch.ts.psrf_rows_mean(a, b, row_start, burnin, end, delta, want_rows=True)
+                assert bits_equal(rows[a, :, b], r) and bits_equal(np.array([mean[a, b]]), np.array([m]))
+
+
+@pytest.mark.parametrize("method", METHODS)
+def test_psrf_ragged_and_empty(gpu, ragged_chains, method):
+    ch = ragged_chains
+    with _ctx(gpu, ch) as ctx:
+        want = ch.ts.psrf_sums([3, 0, 60], 0, 64, 1)
+        assert np.array_equal(ctx.psrf_sums([3, 0, 60], 0, 64, 1, method).astype(np.float64), want)
+        # end == 0: no rows, mean = 0/0 = NaN (AutoStopMCMC calls with end = 0 first)
+        mean = ctx.psrf_eval([0, 0, 0], 0, 0, 1, method)
+        assert np.isnan(mean).all()
+        # end past the shortest chain: the Java throws inside converged2sided; here ASM_E_RANGE
+        with pytest.raises(gpu.AsmGpuError) as e:
+            ctx.psrf_eval([0, 0, 0], 0, 65, 1, method)
+        assert e.value.code == gpu.ASM_E_RANGE
+        with pytest.raises(gpu.AsmGpuError) as e:
+            ctx.psrf_eval([0, 0, 0], 3, 64, 2, method)  # row_start not a multiple of delta
+        assert e.value.code == gpu.ASM_E_INVALID
+
+
+@pytest.mark.parametrize("method", METHODS)
+def test_psrf_shards_add_up(gpu, multi_chains, method):
+    """Multi-GPU split: partial S tables of the shards sum (exact int64) to the full table."""
+    ch = multi_chains
+    burnin, row_start, end, delta = [70, 10, 0, 33], 70, 700, 1
+    with _ctx(gpu, ch) as ctx:
+        full = ctx.psrf_sums(burnin, row_start, end, delta, method)
+        for n in (2, 3, 8):
+            parts = [ctx.psrf_sums(burnin, row_start, end, delta, method, shard=(i, n)) for i in range(n)]
+            assert np.array_equal(sum(parts), full)
+            assert any(p.any() for p in parts[1:])
+
+
+def test_identical_trees_known_answer(gpu):
+    """All trees identical: every (d+1)^2 = 1, so psrf = sqrt(m2/m1) (known answers)."""
+    ch = SynthChains(12, 50, 2, beta=50.0, moves=0)
+    with _ctx(gpu, ch) as ctx:
+        S = ctx.psrf_sums([10, 0], 0, 50, 1)
+        assert (S[:, :, 0] == 40).all() and (S[:, :, 1] == 50).all()
+        mean = ctx.psrf_eval([10, 0], 0, 50, 1)
+    assert mean[0, 1] == np.sqrt(50.0 / 40.0) and mean[1, 0] == np.sqrt(40.0 / 50.0)
+
+
+def test_streaming_append_and_dictionary_growth(gpu, small_chains):
+    """One tree per chain per check (AutoStopMCMC.java:355-375), dictionary width growing on the way."""
+    ch = small_chains
+    import asm_b200 as A
+    enc = A.Encoder(ch.n_taxa)
+    with gpu.GpuContext(2) as ctx:
+        for i in range(0, 120):
+            for c in range(2):
+                l, r, root = ch.topo[c]
+                ids = enc.add_topologies(l[i:i + 1], r[i:i + 1], root[i:i + 1])
+                ctx.trees_append(c, enc.bits(ids))  # enc.words grows in steps of 4 words
+            if i in (0, 1, 7, 63, 119):
+                end = i + 1
+                want = ch.ts.psrf_sums([0, 0], 0, end, 1)
+                got = ctx.psrf_sums([0, 0], 0, end, 1)
+                assert np.array_equal(got.astype(np.float64), want)
+        assert ctx.trees_count(0)[0] == 120
+
+
+# ---------------------------------------------------------------- ESS (TraceESS.java:126-179)
+def _traces(n_tr, n, seed=777):
+    from asm_b200 import _lib as L
+    phis, mus = [0.0, 0.5, 0.9, 0.99], [0.0, 1.0, -1e4]
+    x = np.empty((n_tr, n))
+    for j in range(n_tr):
+        L.synth_ar1(n, mus[j % 3], phis[j % 4], seed + j, out=x[j])
+    return x
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 8, 9, 50, 300, 777, 1023, 1024, 1025, 1999, 2000, 2001, 2003, 4100, 10007])
+def test_ess_batch_bit_exact(gpu, n):
+    x = _traces(6, n)
+    want_act, want_ess = O.ess_batch(x)
+    with gpu.GpuContext(1) as ctx:
+        act, ess = ctx.ess_batch(x)
+    assert bits_equal(act, want_act) and bits_equal(ess, want_ess)
+    if n <= 2003:  # the literal O(n*2000) Java loop, not just its closed form
+        lit = np.array([O.act_literal(x[j]) for j in range(6)])
+        assert bits_equal(act, lit)
+
+
+def test_ess_edge_cases(gpu):
+    with gpu.GpuContext(1) as ctx:
+        act, ess = ctx.ess_batch(np.full((2, 100), 3.25))  # constant trace: ac[0] = 0 -> NaN
+        assert np.isnan(act).all() and np.isnan(ess).all()
+        act, ess = ctx.ess_batch(np.zeros((3, 0)))  # n = 0: 0/0
+        assert np.isnan(act).all() and np.isnan(ess).all()
+        x = _traces(4, 50000)  # iid / AR(1): ACT ~ (1+phi)/(1-phi)
+        act, _ = ctx.ess_batch(x)
+        for j, phi in enumerate([0.0, 0.5, 0.9, 0.99]):
+            assert abs(act[j] / ((1 + phi) / (1 - phi)) - 1) < 0.35
+        # strided input (row stride > n)
+        big = _traces(3, 1000)
+        act2, _ = ctx.ess_batch(big[:, :600])
+        assert bits_equal(act2, O.ess_batch(np.ascontiguousarray(big[:, :600]))[0])
+        with pytest.raises(gpu.AsmGpuError):
+            ctx.ess_batch(x, max_lag=0)
+
+
+def test_ess_eval_streaming_concat(gpu):
+    """Chain concatenation of TraceESS.converged (TraceESS.java:53-62) done on the device."""
+    n_chains, n_cols, n = 3, 5, 900
+    rng = np.random.default_rng(5)
+    logs = [np.cumsum(rng.normal(size=(n_cols, n)), axis=1) * 0.1 + rng.normal(size=(n_cols, n)) for _ in range(n_chains)]
+    with gpu.GpuContext(n_chains) as ctx:
+        for i in range(0, n, 100):  # appended in blocks of log lines [n_new][n_cols]
+            for c in range(n_chains):
+                ctx.traces_append(c, np.ascontiguousarray(logs[c][:, i:i + 100].T))
+        for burnin, end, cols in [([0, 0, 0], 900, [1, 2, 3]), ([90, 10, 450], 700, [4, 0]), ([5, 5, 5], 5, [1])]:
+            got = ctx.ess_eval(burnin, end, cols)
+            conv, want, mn = O.trace_ess_converged(logs, burnin, end, cols, targetESS=100)
+            assert bits_equal(got, want)
+        with pytest.raises(gpu.AsmGpuError) as e:
+            ctx.ess_eval([0, 0, 0], 901, [1])
+        assert e.value.code == gpu.ASM_E_RANGE
+
+
+def test_errors_are_codes_not_crashes(gpu, small_chains):
+    with gpu.GpuContext(2) as ctx:
+        with pytest.raises(gpu.AsmGpuError) as e:
+            ctx.trees_set(5, small_chains.bits[0])
+        assert e.value.code == gpu.ASM_E_INVALID
+        with pytest.raises(gpu.AsmGpuError) as e:
+            ctx.rf_block(0, 0, 10, 1, 0, 10)  # nothing stored yet
+        assert e.value.code == gpu.ASM_E_RANGE
+    with pytest.raises(gpu.AsmGpuError):
+        gpu.GpuContext(0)
