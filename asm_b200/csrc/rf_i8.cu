@@ -1,7 +1,478 @@
-// rf_i8.cu -- K2 placeholder (replaced by the tcgen05 kernel).
+// rf_i8.cu -- K2: Robinson-Foulds distances as a dense int8 contraction on the 5th-generation tensor
+// cores.  On 0/1 clade indicator rows RF(a,b) = |a| + |b| - 2 a.b, so the all-pairs matrix is
+// A * A^T with K = D (the clade dictionary width), followed by an integer epilogue that turns the
+// dot products into (d+1)^2 and folds them into the within-/between-chain sums of calcPSRF
+// (TreePSRF.java:274-286).
+//
+// One persistent CTA per SM, 384 threads, warp-specialised:
+//   warp 0      TMA producer: cp.async.bulk.tensor (UTMALDG) of a 128x128-byte A box and two
+//               128x128-byte B boxes per K block into a 4-stage, 128B-swizzled shared-memory ring
+//   warp 1      MMA issuer: one thread issues tcgen05.mma.cta_group::1.kind::i8 (UTCIMMA), M=128,
+//               N=256, K=32 per instruction, accumulating s32 in TMEM; tcgen05.commit releases the
+//               smem stage / publishes the accumulator
+//   warp 2      TMEM allocator (512 columns = two 128x256 s32 accumulators, double-buffered)
+//   warps 4-11  epilogue: tcgen05.ld (LDTM) 32 columns at a time, d = |a|+|b|-2 dot, v = (d+1)^2,
+//               row sums stay in the thread (one thread = one row), column sums are warp-reduced with
+//               REDUX, partials are added to S with 64-bit integer atomics
+// The tile-pair matrix is walked over its upper triangle in 256-row blocks (two 128x256 tiles per
+// block pair); an off-diagonal tile contributes row sums and column sums (symmetry), a diagonal block
+// is evaluated in full and contributes row sums only.  Tiles are dealt round-robin to CTAs and,
+// across GPUs, to shards.
+//
+// Bound: tensor pipe.  Algorithmic work D*T*(T-1) int8 flop (unordered pairs); see DESIGN.md.
+#include <cuda.h>
+
+#include <algorithm>
+#include <mutex>
+
 #include "asm_internal.h"
 
-int32_t rf_i8_sums(asm_ctx* ctx, asm_shard) { return asm_fail(ctx, ASM_E_UNSUPPORTED, "ASM_RF_I8 not built yet"); }
-int32_t rf_i8_block(asm_ctx* ctx, int32_t, int64_t, int64_t, int32_t, int64_t, int64_t, uint16_t*) {
-  return asm_fail(ctx, ASM_E_UNSUPPORTED, "ASM_RF_I8 not built yet");
+namespace {
+
+constexpr int kStages = 4;
+constexpr int kBlockK = 128;                       // bytes (= int8 elements) per K block, one swizzle atom wide
+constexpr int kTileN = 256;                        // columns per tile
+constexpr int kABytes = kTileRows * kBlockK;       // 16 KB
+constexpr int kBBytes = kTileN * kBlockK;          // 32 KB
+constexpr int kStageBytes = kABytes + kBBytes;     // 48 KB
+constexpr int kThreads = 384;
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kAccCols = 256;                      // TMEM columns per accumulator
+constexpr int kTmemCols = 512;
+constexpr size_t kAuxBytes = 128 /*barriers + tmem ptr*/ + 2 * kTileN * 4 /*nb+1, double buffered*/ + 4 * kTileN * 4 /*col partials*/;
+constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + kAuxBytes;
+
+// instruction descriptor for kind::i8 (cute::UMMA::InstrDescriptor): c_format S32 = 2 @ [4,6),
+// a/b_format S8 = 1 @ [7,10)/[10,13), K-major A and B (bits 15,16 = 0), N>>3 @ [17,23), M>>4 @ [24,29)
+constexpr uint32_t kIdesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(kTileRows >> 4) << 24);
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol error traps (the launch fails with an error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 28)) __trap();
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// shared-memory matrix descriptor, K-major, 128B swizzle: start>>4 @ [0,14), LBO>>4 @ [16,30) (unused
+// for swizzled K-major), SBO>>4 = 1024>>4 @ [32,46) (8 rows x 128 B per swizzle atom), version 1 @ [46,48),
+// layout SWIZZLE_128B = 2 @ [61,64)  (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__device__ __forceinline__ void umma_i8(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_c),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
+
+struct TileInfo {
+  int row_tile;   // 128-row tile index of the A operand
+  int col_block;  // 256-row block index of the B operand
+  bool do_row, do_col;
+  int chain_rows, chain_cols;  // chain of the A rows / of the B rows
+};
+
+// PSRF mode: tile t of the upper triangle over 256-row blocks; dump mode: rectangular enumeration.
+template <bool kDump>
+__device__ __forceinline__ bool decode_tile(long long t, int n_row_tiles, const int2* __restrict__ meta, TileInfo& ti) {
+  if (kDump) {
+    ti.row_tile = (int)(t % n_row_tiles);
+    ti.col_block = (int)(t / n_row_tiles);
+    ti.do_row = ti.do_col = false;
+    ti.chain_rows = ti.chain_cols = 0;
+    return true;
+  }
+  const long long bp = t >> 1;
+  const int half = (int)(t & 1);
+  long long jb = (long long)((sqrt(8.0 * (double)bp + 1.0) - 1.0) * 0.5);
+  while (jb * (jb + 1) / 2 > bp) jb--;
+  while ((jb + 1) * (jb + 2) / 2 <= bp) jb++;
+  const int ib = (int)(bp - jb * (jb + 1) / 2);
+  ti.row_tile = 2 * ib + half;
+  ti.col_block = (int)jb;
+  const int2 mi = meta[ti.row_tile], mj0 = meta[2 * jb], mj1 = meta[2 * jb + 1];
+  const bool diag = ib == (int)jb;
+  ti.do_row = (mi.y & kFlagRows) && (mj0.y & kFlagCol);
+  ti.do_col = !diag && (mi.y & kFlagCol) && ((mj0.y | mj1.y) & kFlagRows);
+  ti.chain_rows = mi.x;
+  ti.chain_cols = mj0.x;
+  return ti.do_row || ti.do_col;
+}
+
+template <bool kDump>
+__global__ void __launch_bounds__(kThreads, 1)
+rf_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int nkb,
+             const int* __restrict__ nbitsA, const int* __restrict__ nbitsB, const int2* __restrict__ tile_meta,
+             long long n_tiles, int n_row_tiles, int shard_index, int shard_count, unsigned long long* __restrict__ S,
+             int C, uint16_t* __restrict__ dump, long long dump_ld) {
+  extern __shared__ __align__(1024) unsigned char smem[];  // 128B-swizzle atoms need 1024-byte alignment
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  unsigned char* aux = smem + (size_t)kStages * kStageBytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(aux);      // [kStages]
+  uint64_t* empty = full + kStages;                       // [kStages]
+  uint64_t* tfull = empty + kStages;                      // [2]
+  uint64_t* tempty = tfull + 2;                           // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+  int* nb_s = reinterpret_cast<int*>(aux + 128);          // [2][256]  |b| + 1 of the tile's columns
+  uint32_t* colpart = reinterpret_cast<uint32_t*>(aux + 128 + 2 * kTileN * 4);  // [4][256]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; s++) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; a++) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], kEpiWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const long long first = blockIdx.x, stride = gridDim.x;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long k = first;; k += stride) {
+        const long long t = k * shard_count + shard_index;
+        if (t >= n_tiles) break;
+        TileInfo ti;
+        if (!decode_tile<kDump>(t, n_row_tiles, tile_meta, ti)) continue;
+        for (int kb = 0; kb < nkb; kb++) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          unsigned char* st = smem + (size_t)stage * kStageBytes;
+          mbar_expect_tx(&full[stage], kStageBytes);
+          tma_load_2d(st, &tmA, kb * kBlockK, ti.row_tile * kTileRows, &full[stage]);
+          tma_load_2d(st + kABytes, &tmB, kb * kBlockK, ti.col_block * kTileN, &full[stage]);
+          tma_load_2d(st + kABytes + kABytes, &tmB, kb * kBlockK, ti.col_block * kTileN + kTileRows, &full[stage]);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (long long k = first;; k += stride) {
+        const long long t = k * shard_count + shard_index;
+        if (t >= n_tiles) break;
+        TileInfo ti;
+        if (!decode_tile<kDump>(t, n_row_tiles, tile_meta, ti)) continue;
+        mbar_wait(&tempty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_c = tmem_base + (uint32_t)(acc * kAccCols);
+        for (int kb = 0; kb < nkb; kb++) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + (size_t)stage * kStageBytes);
+          const uint64_t adesc = make_desc(a_addr), bdesc = make_desc(a_addr + kABytes);
+#pragma unroll
+          for (int kk = 0; kk < kBlockK / 32; kk++)  // UMMA_K = 32 bytes; advance the start address inside the atom
+            umma_i8(tmem_c, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), kIdesc, (uint32_t)((kb | kk) != 0));
+          umma_commit(&empty[stage]);  // smem stage is free once these MMAs have read it
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull[acc]);  // accumulator complete
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue =====
+    const int ew = warp - 4;        // 0..7
+    const int quad = warp & 3;      // TMEM lane quadrant this warp may touch
+    const int half = ew >> 2;       // which 128 of the 256 columns
+    const int et = threadIdx.x - 128;
+    int acc = 0, buf = 0;
+    uint32_t acc_phase = 0;
+    for (long long k = first;; k += stride) {
+      const long long t = k * shard_count + shard_index;
+      if (t >= n_tiles) break;
+      TileInfo ti;
+      if (!decode_tile<kDump>(t, n_row_tiles, tile_meta, ti)) continue;
+      const long long col0 = (long long)ti.col_block * kTileN;
+      const long long row = (long long)ti.row_tile * kTileRows + quad * 32 + lane;
+      nb_s[buf * kTileN + et] = nbitsB[col0 + et] + 1;
+      const int na = nbitsA[row];
+      epi_barrier();
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kAccCols + half * 128);
+      unsigned long long row_sum = 0;
+#pragma unroll 1
+      for (int cc = 0; cc < 4; cc++) {
+        uint32_t r[32];
+        tmem_ld32(taddr + cc * 32, r);
+        const int* nb = nb_s + buf * kTileN + half * 128 + cc * 32;
+        if (kDump) {
+          uint16_t* o = dump + row * dump_ld + col0 + half * 128 + cc * 32;
+#pragma unroll
+          for (int j = 0; j < 32; j++) o[j] = (uint16_t)(na + nb[j] - 1 - 2 * (int)r[j]);
+        } else {
+          uint32_t chunk = 0, mycol = 0;
+          if (ti.do_col) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+              const uint32_t e = (uint32_t)(na + nb[j] - 2 * (int)r[j]);  // d + 1
+              const uint32_t v = e * e;
+              chunk += v;
+              const uint32_t s = __reduce_add_sync(0xffffffffu, v);  // over the 32 rows of this warp
+              if (lane == j) mycol = s;
+            }
+            colpart[quad * kTileN + half * 128 + cc * 32 + lane] = mycol;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+              const uint32_t e = (uint32_t)(na + nb[j] - 2 * (int)r[j]);
+              chunk += e * e;
+            }
+          }
+          row_sum += chunk;
+        }
+      }
+      // all TMEM reads of this accumulator are complete: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (!kDump) {
+        if (ti.do_row) atomicAdd(&S[(size_t)row * C + ti.chain_cols], row_sum);
+        if (ti.do_col) {
+          epi_barrier();
+          const uint32_t v = colpart[et] + colpart[kTileN + et] + colpart[2 * kTileN + et] + colpart[3 * kTileN + et];
+          atomicAdd(&S[(size_t)(col0 + et) * C + ti.chain_rows], (unsigned long long)v);
+        }
+      }
+      buf ^= 1;
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// [rows][bytes_per_row] uint8, boxes of 128 rows x 128 bytes, 128B swizzle
+int32_t make_tmap(asm_ctx* ctx, CUtensorMap* m, const void* base, uint64_t rows, uint64_t bytes_per_row) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return asm_fail(ctx, ASM_E_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[2] = {bytes_per_row, rows};
+  cuuint64_t strides[1] = {bytes_per_row};
+  cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)kTileRows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return asm_fail(ctx, ASM_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return ASM_OK;
+}
+
+template <bool kDump>
+int32_t set_smem_attr(asm_ctx* ctx) {
+  static bool done = false;
+  if (!done) {
+    ASM_CUDA(ctx, cudaFuncSetAttribute(rf_i8_kernel<kDump>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    done = true;
+  }
+  return ASM_OK;
+}
+
+// rows of one chain -> zero-padded 0/1 byte matrix + popcounts (operands of the dump-mode probe)
+__global__ void __launch_bounds__(256) expand_rows_kernel(const uint64_t* __restrict__ src, int words, long long n_live,
+                                                           long long n_pad, int Wp, uint4* __restrict__ out,
+                                                           int* __restrict__ nbits) {
+  const int lane = threadIdx.x & 31;
+  const long long wpb = blockDim.x >> 5;
+  for (long long p = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); p < n_pad; p += (long long)gridDim.x * wpb) {
+    int cnt = 0;
+    for (int w = lane; w < Wp; w += 32) {
+      const uint64_t v = (p < n_live && w < words) ? src[(size_t)p * words + w] : 0ULL;
+      cnt += __popcll(v);
+      uint4 q[4];
+      uint32_t* o = reinterpret_cast<uint32_t*>(q);
+#pragma unroll
+      for (int k = 0; k < 16; k++) o[k] = (((uint32_t)(v >> (4 * k)) & 0xFu) * 0x00204081u) & 0x01010101u;
+#pragma unroll
+      for (int k = 0; k < 4; k++) out[((size_t)p * Wp + w) * 4 + k] = q[k];
+    }
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) nbits[p] = cnt;
+  }
+}
+
+}  // namespace
+
+int32_t rf_i8_sums(asm_ctx* ctx, asm_shard shard) {
+  PsrfLayout& L = ctx->layout;
+  const long long nb = L.Tp / kBlockRows;
+  const long long n_tiles = nb * (nb + 1);  // two 128x256 tiles per block pair of the upper triangle
+  L.tiles_total = n_tiles;
+  L.tiles_done = (n_tiles - shard.shard_index + shard.shard_count - 1) / shard.shard_count;
+  const uint64_t Dp = (uint64_t)L.Wp * 64;
+  CUtensorMap tm;
+  int32_t rc = make_tmap(ctx, &tm, ctx->opnd_i8.p, (uint64_t)L.Tp, Dp);
+  if (rc != ASM_OK) return rc;
+  if ((rc = set_smem_attr<false>(ctx)) != ASM_OK) return rc;
+  const int grid = (int)std::min<long long>(L.tiles_done, ctx->sm_count);
+  if (grid <= 0) return ASM_OK;
+  {
+    LaunchScope ls(ctx, ASM_K_RF_I8);
+    rf_i8_kernel<false><<<grid, kThreads, kSmemBytes, ctx->stream>>>(
+        tm, tm, (int)(Dp / kBlockK), (const int*)ctx->nbits.p, (const int*)ctx->nbits.p, (const int2*)ctx->blk_meta.p,
+        n_tiles, 0, shard.shard_index, shard.shard_count, (unsigned long long*)ctx->S_pad.p, L.C, nullptr, 0);
+  }
+  ASM_CUDA(ctx, cudaGetLastError());
+  return ASM_OK;
+}
+
+int32_t rf_i8_block(asm_ctx* ctx, int32_t chainA, int64_t r0, int64_t r1, int32_t chainB, int64_t c0, int64_t c1,
+                    uint16_t* out_host) {
+  const long long nr = r1 - r0, nc = c1 - c0;
+  const long long nr_pad = (nr + kTileRows - 1) / kTileRows * kTileRows;
+  const long long nc_pad = (nc + kTileN - 1) / kTileN * kTileN;
+  const int Wp = (ctx->words + 15) / 16 * 16;
+  const uint64_t Dp = (uint64_t)Wp * 64;
+  int32_t rc;
+  // scratch: A8 | B8 in opnd_i8, popcounts in nbits, distances in rf_out
+  if ((rc = asm_reserve(ctx, ctx->opnd_i8, (size_t)(nr_pad + nc_pad) * Dp)) != ASM_OK) return rc;
+  if ((rc = asm_reserve(ctx, ctx->nbits, sizeof(int) * (size_t)(nr_pad + nc_pad))) != ASM_OK) return rc;
+  if ((rc = asm_reserve(ctx, ctx->rf_out, sizeof(uint16_t) * (size_t)(nr_pad * nc_pad))) != ASM_OK) return rc;
+  unsigned char* A8 = (unsigned char*)ctx->opnd_i8.p;
+  unsigned char* B8 = A8 + (size_t)nr_pad * Dp;
+  int* nbA = (int*)ctx->nbits.p;
+  int* nbB = nbA + nr_pad;
+  {
+    LaunchScope ls(ctx, ASM_K_GATHER);
+    expand_rows_kernel<<<(unsigned)std::min<long long>((nr_pad + 7) / 8, ctx->sm_count * 8LL), 256, 0, ctx->stream>>>(
+        ctx->trees[chainA].d_bits + (size_t)r0 * ctx->words, ctx->words, nr, nr_pad, Wp, (uint4*)A8, nbA);
+  }
+  {
+    LaunchScope ls(ctx, ASM_K_GATHER);
+    expand_rows_kernel<<<(unsigned)std::min<long long>((nc_pad + 7) / 8, ctx->sm_count * 8LL), 256, 0, ctx->stream>>>(
+        ctx->trees[chainB].d_bits + (size_t)c0 * ctx->words, ctx->words, nc, nc_pad, Wp, (uint4*)B8, nbB);
+  }
+  ASM_CUDA(ctx, cudaGetLastError());
+  CUtensorMap tmA, tmB;
+  if ((rc = make_tmap(ctx, &tmA, A8, (uint64_t)nr_pad, Dp)) != ASM_OK) return rc;
+  if ((rc = make_tmap(ctx, &tmB, B8, (uint64_t)nc_pad, Dp)) != ASM_OK) return rc;
+  if ((rc = set_smem_attr<true>(ctx)) != ASM_OK) return rc;
+  const int n_row_tiles = (int)(nr_pad / kTileRows);
+  const long long n_tiles = (long long)n_row_tiles * (nc_pad / kTileN);
+  {
+    LaunchScope ls(ctx, ASM_K_RF_I8);
+    rf_i8_kernel<true><<<(int)std::min<long long>(n_tiles, ctx->sm_count), kThreads, kSmemBytes, ctx->stream>>>(
+        tmA, tmB, (int)(Dp / kBlockK), nbA, nbB, nullptr, n_tiles, n_row_tiles, 0, 1, nullptr, 0, (uint16_t*)ctx->rf_out.p,
+        nc_pad);
+  }
+  ASM_CUDA(ctx, cudaGetLastError());
+  ASM_CUDA(ctx, cudaMemcpy2DAsync(out_host, sizeof(uint16_t) * (size_t)nc, ctx->rf_out.p, sizeof(uint16_t) * (size_t)nc_pad,
+                                  sizeof(uint16_t) * (size_t)nc, (size_t)nr, cudaMemcpyDeviceToHost, ctx->stream));
+  ASM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return ASM_OK;
 }

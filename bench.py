@@ -470,7 +470,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="psrf", choices=["psrf", "ess", "cfg5"])
-    ap.add_argument("--method", default=os.environ.get("ASM_BENCH_METHOD", "popc"), choices=["i8", "popc"])
+    ap.add_argument("--method", default=os.environ.get("ASM_BENCH_METHOD", "i8"), choices=["i8", "popc"])
     ap.add_argument("--cpu-rows", type=int, default=2048, help="row trees per chain in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ess", action="store_true", help="skip the secondary ESS block of the default run")

@@ -158,7 +158,14 @@ def test_identical_trees_known_answer(gpu):
         S = ctx.psrf_sums([10, 0], 0, 50, 1)
         assert (S[:, :, 0] == 40).all() and (S[:, :, 1] == 50).all()
         mean = ctx.psrf_eval([10, 0], 0, 50, 1)
-    assert mean[0, 1] == np.sqrt(50.0 / 40.0) and mean[1, 0] == np.sqrt(40.0 / 50.0)
+    # TreePSRF.mean (TreePSRF.java:264-271) adds the 50 identical row values one by one, then divides
+    def seq_mean(v, n):
+        s = 0.0
+        for _ in range(n):
+            s += v
+        return s / n
+    assert mean[0, 1] == seq_mean(np.sqrt(50.0 / 40.0), 50) and mean[1, 0] == seq_mean(np.sqrt(40.0 / 50.0), 50)
+    assert abs(mean[0, 1] - np.sqrt(1.25)) < 1e-14
 
 
 def test_streaming_append_and_dictionary_growth(gpu, small_chains):
