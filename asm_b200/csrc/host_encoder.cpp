@@ -127,6 +127,8 @@ bool encode_tree(asm_encoder* enc, const int32_t* left, const int32_t* right, in
     merged.resize((size_t)(nl + nr));
     std::merge(base, base + nl, base + nl, base + nl + nr, merged.begin());
     std::memcpy(base, merged.data(), sizeof(int32_t) * (size_t)(nl + nr));
+    for (int32_t q = 1; q < nl + nr; q++)
+      if (base[q] == base[q - 1]) return false;  // a leaf reached twice: not a tree
     Key128 k{kl.a ^ kr.a, kl.b ^ kr.b};
     if (n_out >= n - 1) return false;
     ids_out[n_out++] = enc->get_or_add(k, base, nl + nr);

@@ -1,0 +1,54 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/asmgpu.h declares;
+compute entry points refuse to run without a device (there is no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from asm_b200 import _lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "asmgpu.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(asm_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = header_functions()
+    assert len(names) >= 35
+    raw = ctypes.CDLL(L.LIB_PATH)
+    for n in names:
+        assert hasattr(raw, n), f"libasmgpu.so does not export {n}"
+    # the binding covers the header one to one
+    assert sorted(L.SIGNATURES) == names
+    assert L.lib().asm_version().startswith(b"asm-b200")
+
+
+def test_no_torch_types_in_the_abi():
+    src = open(os.path.join(ROOT, "include", "asmgpu.h")).read()
+    code = re.sub(r"/\*.*?\*/", "", src, flags=re.S)  # declarations only, comments stripped
+    assert "torch" not in code and "at::" not in code and "std::" not in code and "#include <stdint.h>" in code
+
+
+@pytest.mark.skipif(L.lib().asm_device_count() > 0, reason="CPU-only behaviour")
+def test_no_cpu_fallback():
+    with pytest.raises(L.AsmGpuError) as e:
+        L.GpuContext(2)
+    assert e.value.code == L.ASM_E_NO_DEVICE and "no CPU fallback" in str(e.value)
+    # null context: every entry point returns ASM_E_INVALID instead of crashing
+    assert L.lib().asm_psrf_eval(None, None, 0, 0, 1, 0, None, None) == L.ASM_E_INVALID
+    assert L.lib().asm_ess_batch(None, 1, 1, 1, None, 2000, None, None) == L.ASM_E_INVALID
+
+
+def test_product_does_not_import_the_oracle():
+    """Only tests/, smoke() and bench.py's cpu_baseline may touch oracle/."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "asm_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h", ".hpp", ".cuh")) or f == "Makefile":
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle" not in txt.lower(), f"{f} mentions the oracle"

@@ -1,0 +1,72 @@
+"""Host encoder (the step before the path): Newick / child arrays -> clade ids -> bit rows."""
+import numpy as np
+import pytest
+
+import asm_b200 as A
+import oracle as O
+from asm_b200 import _lib as L
+
+
+def test_ids_follow_the_reference_traverse_order(multi_chains):
+    ch = multi_chains
+    # same post-order, same first-seen numbering as CladeDifference.traverse in the oracle
+    for c in range(ch.n_chains):
+        for i in (0, 1, 350, 699):
+            assert np.array_equal(ch.ids[c][i], ch.ts.tree_clade_ids(c, i))
+    assert ch.enc.num_clades == ch.ts.num_clades
+    for cid in range(0, ch.enc.num_clades, 37):
+        assert "".join(f"{x}," for x in ch.enc.clade_leaves(cid)) == ch.ts.clade_key(cid)
+
+
+def test_bit_rows(multi_chains):
+    ch = multi_chains
+    assert ch.words % 4 == 0 and ch.words * 64 >= ch.enc.num_clades
+    row = ch.bits[2][17]
+    ids = sorted(int(w) * 64 + b for w in range(ch.words) for b in range(64) if (int(row[w]) >> b) & 1)
+    assert ids == sorted(ch.ids[2][17].tolist())
+    with pytest.raises(L.AsmGpuError):
+        ch.enc.bits(ch.ids[3][-2:], words=1)  # dictionary does not fit
+
+
+def test_newick_reader():
+    enc = A.Encoder(5)
+    # BEAST tree log style: translate indices start at 1 (parser.offsetInput = 1, AutoStopMCMC.java:527)
+    a = enc.add_newick("((1:0.1,2:0.2):0.3,(3:0.1,(4:0.05,5:0.05):0.2):0.1):0.0;", 1)
+    b = enc.add_newick("((1[&rate=1.0]:0.1,2:0.2)[&posterior=0.9]:0.3,(3:0.1,(4:0.05,5:0.05):0.2):0.1);", 1)
+    assert np.array_equal(a, b)
+    leaves = [enc.clade_leaves(int(i)).tolist() for i in a]
+    assert leaves == [[0, 1], [3, 4], [2, 3, 4], [0, 1, 2, 3, 4]]  # post-order, left before right
+    c = enc.add_newick("((2,1),((5,4),3));", 1)                     # same clades, different child order
+    assert sorted(c.tolist()) == sorted(a.tolist())
+    for bad in ("((1,2),(3,4));", "((1,2),(3,(4,5)),6);", "((1,1),(3,(4,5)));", "((a,b),(c,(d,e)));", "((1,2,3),(4,5));"):
+        with pytest.raises(L.AsmGpuError):
+            enc.add_newick(bad, 1)
+
+
+def test_topology_validation():
+    enc = A.Encoder(4)
+    left = np.array([[-1, -1, -1, -1, 0, 2, 4]], dtype=np.int32)
+    right = np.array([[-1, -1, -1, -1, 1, 3, 5]], dtype=np.int32)
+    ids = enc.add_topologies(left, right, np.array([6], dtype=np.int32))
+    assert [enc.clade_leaves(int(i)).tolist() for i in ids[0]] == [[0, 1], [2, 3], [0, 1, 2, 3]]
+    bad = right.copy()
+    bad[0, 6] = 4  # both children the same subtree: not a tree on 4 leaves
+    with pytest.raises(L.AsmGpuError):
+        enc.add_topologies(left, bad, np.array([6], dtype=np.int32))
+
+
+def test_synthetic_generators_are_reproducible():
+    a = L.synth_tree_chain(30, 50, 1, 42, 2, 2.5)
+    b = L.synth_tree_chain(30, 50, 1, 42, 2, 2.5)
+    c = L.synth_tree_chain(30, 50, 1, 43, 2, 2.5)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and not np.array_equal(a[0], c[0])
+    # the fast path (ids straight from the walk) names the same clades as the canonical encoder
+    enc1, enc2 = A.Encoder(30), A.Encoder(30)
+    _, _, _, ids_fast = L.synth_tree_chain(30, 50, 1, 42, 2, 2.5, topologies=False, encoder=enc1)
+    ids_ref = enc2.add_topologies(*a[:3])
+    for t in (0, 10, 49):
+        fast = sorted(tuple(enc1.clade_leaves(int(i))) for i in ids_fast[t])
+        ref = sorted(tuple(enc2.clade_leaves(int(i))) for i in ids_ref[t])
+        assert fast == ref
+    x = L.synth_ar1(1000, -1e4, 0.9, 5)
+    assert np.array_equal(x, L.synth_ar1(1000, -1e4, 0.9, 5)) and abs(x.mean() + 1e4) < 5
