@@ -33,12 +33,14 @@ struct PsrfLayout {
   int32_t n_seg = 0;
   Segment seg[kMaxSegments];
   int64_t Tp = 0;                 // padded rows, multiple of 256
-  int32_t Wp = 0;                 // padded words per row, multiple of 16
+  int32_t Wp = 0;                 // padded words per row, multiple of 16 (popcount operand)
+  int32_t pitch8 = 0;             // bytes per row of the int8 operand, multiple of 128
   int64_t row_pos0[ASM_MAX_CHAINS];   // padded position of output row r of chain a:
   int64_t row_posB[ASM_MAX_CHAINS];   //   r < rowsA[a] ? row_pos0[a] + r : row_posB[a] + (r - rowsA[a])
   int32_t rowsA[ASM_MAX_CHAINS];
   int64_t padB[ASM_MAX_CHAINS];   // zero-padding rows inside the column segment of chain c
   int64_t tiles_total = 0, tiles_done = 0;
+  int64_t bits_used = 0;          // operand width (bits) of the kernel that ran last
 };
 
 struct ChainTrees {
@@ -62,6 +64,8 @@ struct asm_ctx {
   int n_chains = 0;
   int sm_count = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;  // side stream (ESS sum chain)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int32_t words = 0;  // stored row width of every chain (uint64 words)
   std::vector<ChainTrees> trees;
   std::vector<ChainTraces> traces;
@@ -69,6 +73,7 @@ struct asm_ctx {
   DevBuf opnd_bits, opnd_i8, nbits, S_pad, blk_meta, seg_dev, S_compact, psrf_rows, psrf_mean, misc, flush, ess_tr,
       ess_sls, ess_out, tile_counter, rf_out;
   PsrfLayout layout;
+  std::vector<int2> meta_host;  // staging for tile metadata
   // measurement
   cudaEvent_t timer[16] = {};
   bool profile = false;
@@ -102,7 +107,8 @@ struct LaunchScope {
 // psrf_layout.cu
 int32_t psrf_build_layout(asm_ctx* ctx, const int32_t* burnin, int32_t row_start, int32_t end, int32_t delta);
 int32_t psrf_gather_bits(asm_ctx* ctx);  // layout -> opnd_bits [Tp][Wp], nbits [Tp], blk_meta
-int32_t psrf_expand_i8(asm_ctx* ctx);    // opnd_bits -> opnd_i8 [Tp][64*Wp]
+int32_t psrf_expand_i8(asm_ctx* ctx);    // opnd_bits -> opnd_i8 [Tp][64*Wp] (unused by the default path)
+int32_t psrf_gather_i8(asm_ctx* ctx);    // layout -> opnd_i8 [Tp][pitch8] directly, nbits [Tp], blk_meta
 int32_t psrf_compact(asm_ctx* ctx, asm_shard shard, int64_t* d_S_out);  // S_pad -> [C][n_rows][C], pad-corrected
 int32_t psrf_finish(asm_ctx* ctx, const int64_t* d_S, int32_t n_rows, double* psrf_rows_host, double* psrf_mean_host);
 // rf_popc.cu

@@ -190,6 +190,9 @@ int32_t asm_create(asm_ctx** out, int32_t device, int32_t n_chains) {
     delete ctx;
     return asm_fail(nullptr, ASM_E_CUDA, "stream create: %s", cudaGetErrorString(e));
   }
+  cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
   for (auto& ev : ctx->timer) cudaEventCreate(&ev);
   cudaEventCreate(&ctx->pe0);
   cudaEventCreate(&ctx->pe1);
@@ -214,6 +217,9 @@ int32_t asm_destroy(asm_ctx* ctx) {
     if (ev) cudaEventDestroy(ev);
   if (ctx->pe0) cudaEventDestroy(ctx->pe0);
   if (ctx->pe1) cudaEventDestroy(ctx->pe1);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return ASM_OK;
@@ -275,11 +281,11 @@ static int32_t psrf_sums_impl(asm_ctx* ctx, const int32_t* burnin, int32_t row_s
   int32_t rc = psrf_build_layout(ctx, burnin, row_start, end, delta);
   if (rc != ASM_OK) return rc;
   if (ctx->layout.n_rows == 0) return ASM_OK;
-  if ((rc = psrf_gather_bits(ctx)) != ASM_OK) return rc;
   if (method == ASM_RF_I8) {
-    if ((rc = psrf_expand_i8(ctx)) != ASM_OK) return rc;
+    if ((rc = psrf_gather_i8(ctx)) != ASM_OK) return rc;
     if ((rc = rf_i8_sums(ctx, shard)) != ASM_OK) return rc;
   } else {
+    if ((rc = psrf_gather_bits(ctx)) != ASM_OK) return rc;
     if ((rc = rf_popc_sums(ctx, shard)) != ASM_OK) return rc;
   }
   return psrf_compact(ctx, shard, d_S_out);
@@ -474,7 +480,7 @@ int32_t asm_psrf_last_layout(const asm_ctx* ctx, int64_t* padded_rows, int64_t* 
                              int64_t* tiles_total) {
   if (!ctx) return ASM_E_INVALID;
   if (padded_rows) *padded_rows = ctx->layout.Tp;
-  if (padded_bits) *padded_bits = (int64_t)ctx->layout.Wp * 64;
+  if (padded_bits) *padded_bits = ctx->layout.bits_used;
   if (tiles_done) *tiles_done = ctx->layout.tiles_done;
   if (tiles_total) *tiles_total = ctx->layout.tiles_total;
   return ASM_OK;

@@ -27,8 +27,9 @@ struct SegTableDev {
 };
 
 // One warp per padded row: copy (zero-extended) or zero-fill, and count the set bits.
-__global__ void __launch_bounds__(256) gather_bits_kernel(const SegTableDev* __restrict__ tab,
+__global__ void __launch_bounds__(256) gather_bits_kernel(const __grid_constant__ SegTableDev tab_,
                                                            uint64_t* __restrict__ out, int32_t* __restrict__ nbits) {
+  const SegTableDev* tab = &tab_;
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const int64_t Tp = tab->Tp;
@@ -50,6 +51,43 @@ __global__ void __launch_bounds__(256) gather_bits_kernel(const SegTableDev* __r
       uint64_t v = (live && w < words) ? __ldg(src + w) : 0ULL;
       out[(size_t)p * Wp + w] = v;
       cnt += __popcll(v);
+    }
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) nbits[p] = cnt;
+  }
+}
+
+
+// int8 path: the same gather, written straight as 0/1 bytes (one 64-bit word -> 64 bytes, four 16-byte
+// stores per lane, a warp writes 2 KB contiguous); the bit matrix itself is never materialised.
+__global__ void __launch_bounds__(256) gather_i8_kernel(const __grid_constant__ SegTableDev tab_, uint4* __restrict__ out,
+                                                         int W8, int32_t* __restrict__ nbits) {
+  const SegTableDev* tab = &tab_;
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const int64_t Tp = tab->Tp;
+  const int words = tab->words, delta = tab->delta, n_seg = tab->n_seg;
+  for (int64_t p = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); p < Tp;
+       p += (int64_t)gridDim.x * warps_per_block) {
+    int lo = 0, hi = n_seg - 1;
+    while (lo < hi) {
+      int mid = (lo + hi + 1) >> 1;
+      if (tab->seg[mid].dst_off <= p) lo = mid; else hi = mid - 1;
+    }
+    const Segment& s = tab->seg[lo];
+    const int64_t j = p - s.dst_off;
+    const bool live = j < s.n;
+    const uint64_t* src = live ? tab->chain_bits[s.chain] + (size_t)(s.src_first + j * delta) * words : nullptr;
+    int cnt = 0;
+    for (int w = lane; w < W8; w += 32) {
+      const uint64_t v = (live && w < words) ? __ldg(src + w) : 0ULL;
+      cnt += __popcll(v);
+      uint4 q[4];
+      uint32_t* o = reinterpret_cast<uint32_t*>(q);
+#pragma unroll
+      for (int k = 0; k < 16; k++) o[k] = (((uint32_t)(v >> (4 * k)) & 0xFu) * 0x00204081u) & 0x01010101u;
+#pragma unroll
+      for (int k = 0; k < 4; k++) out[((size_t)p * W8 + w) * 4 + k] = q[k];
     }
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     if (lane == 0) nbits[p] = cnt;
@@ -80,9 +118,10 @@ struct CompactParams {
   int32_t rowsA[ASM_MAX_CHAINS];
 };
 
-__global__ void __launch_bounds__(256) compact_kernel(const CompactParams* __restrict__ prm,
+__global__ void __launch_bounds__(256) compact_kernel(const __grid_constant__ CompactParams prm_,
                                                        const long long* __restrict__ S_pad,
                                                        const int32_t* __restrict__ nbits, long long* __restrict__ out) {
+  const CompactParams* prm = &prm_;
   const int C = prm->C, n_rows = prm->n_rows;
   const int64_t total = (int64_t)C * n_rows * C;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -103,7 +142,7 @@ __global__ void __launch_bounds__(256) compact_kernel(const CompactParams* __res
 // One block per ordered chain pair (a, b).  The per-row values are produced in parallel into shared
 // memory, then thread 0 adds them in ascending row order: the sequential sum of TreePSRF.mean
 // (TreePSRF.java:264-271).  Row value: TreePSRF.java:287-292.
-constexpr int kFinishChunk = 1024;
+constexpr int kFinishChunk = 4096;
 __global__ void __launch_bounds__(256) psrf_finish_kernel(const long long* __restrict__ S, int C, int n_rows,
                                                            double* __restrict__ psrf_rows,
                                                            double* __restrict__ psrf_mean) {
@@ -127,7 +166,20 @@ __global__ void __launch_bounds__(256) psrf_finish_kernel(const long long* __res
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-      for (int k = 0; k < n; k++) sum = __dadd_rn(sum, vals[k]);
+      int k = 0;
+      for (; k + 8 <= n; k += 8) {  // loads first, then the dependent chain of 8 adds
+        const double v0 = vals[k], v1 = vals[k + 1], v2 = vals[k + 2], v3 = vals[k + 3];
+        const double v4 = vals[k + 4], v5 = vals[k + 5], v6 = vals[k + 6], v7 = vals[k + 7];
+        sum = __dadd_rn(sum, v0);
+        sum = __dadd_rn(sum, v1);
+        sum = __dadd_rn(sum, v2);
+        sum = __dadd_rn(sum, v3);
+        sum = __dadd_rn(sum, v4);
+        sum = __dadd_rn(sum, v5);
+        sum = __dadd_rn(sum, v6);
+        sum = __dadd_rn(sum, v7);
+      }
+      for (; k < n; k++) sum = __dadd_rn(sum, vals[k]);
     }
     __syncthreads();
   }
@@ -157,6 +209,7 @@ int32_t psrf_build_layout(asm_ctx* ctx, const int32_t* burnin, int32_t row_start
   L.end = end;
   L.n_rows = end > row_start ? (end - row_start + delta - 1) / delta : 0;
   L.Wp = (int32_t)round_up(ctx->words > 0 ? ctx->words : 1, kBitsPad / 64);
+  L.pitch8 = (int32_t)round_up((int64_t)(ctx->words > 0 ? ctx->words : 1) * 64, 128);  // int8 operand row pitch: whole 128-byte K blocks
   if (L.n_rows == 0) return ASM_OK;
   int64_t off = 0;
   for (int c = 0; c < C; c++) {
@@ -187,16 +240,13 @@ int32_t psrf_build_layout(asm_ctx* ctx, const int32_t* burnin, int32_t row_start
   return ASM_OK;
 }
 
-int32_t psrf_gather_bits(asm_ctx* ctx) {
+// Seg table, per-tile metadata and the zeroed S table: common to both distance kernels.
+static int32_t psrf_prepare(asm_ctx* ctx, SegTableDev& tab) {
   PsrfLayout& L = ctx->layout;
   int32_t rc;
-  if ((rc = asm_reserve(ctx, ctx->opnd_bits, sizeof(uint64_t) * (size_t)L.Tp * L.Wp)) != ASM_OK) return rc;
   if ((rc = asm_reserve(ctx, ctx->nbits, sizeof(int32_t) * (size_t)L.Tp)) != ASM_OK) return rc;
-  if ((rc = asm_reserve(ctx, ctx->seg_dev, sizeof(SegTableDev))) != ASM_OK) return rc;
   const int64_t n_tiles = L.Tp / kTileRows;
   if ((rc = asm_reserve(ctx, ctx->blk_meta, sizeof(int2) * (size_t)n_tiles)) != ASM_OK) return rc;
-
-  SegTableDev tab;
   tab.n_seg = L.n_seg;
   tab.delta = L.delta;
   tab.words = ctx->words;
@@ -204,11 +254,10 @@ int32_t psrf_gather_bits(asm_ctx* ctx) {
   tab.Tp = L.Tp;
   for (int c = 0; c < ctx->n_chains; c++) tab.chain_bits[c] = ctx->trees[c].d_bits;
   for (int s = 0; s < L.n_seg; s++) tab.seg[s] = L.seg[s];
-  // pinned-less small upload: cudaMemcpyAsync from pageable memory is synchronous w.r.t. the host copy
-  ASM_CUDA(ctx, cudaMemcpyAsync(ctx->seg_dev.p, &tab, sizeof tab, cudaMemcpyHostToDevice, ctx->stream));
 
   // per-tile metadata {chain, flags}
-  std::vector<int2> meta((size_t)n_tiles);
+  std::vector<int2>& meta = ctx->meta_host;
+  meta.resize((size_t)n_tiles);
   for (int s = 0; s < L.n_seg; s++) {
     const Segment& g = L.seg[s];
     const int64_t padded = round_up(g.n, kBlockRows);
@@ -227,19 +276,42 @@ int32_t psrf_gather_bits(asm_ctx* ctx) {
       meta[(size_t)(g.dst_off / kTileRows + t)] = make_int2(g.chain, (int)f);
     }
   }
+  // pageable source: the runtime stages the bytes before returning, so no host sync is needed here
   ASM_CUDA(ctx, cudaMemcpyAsync(ctx->blk_meta.p, meta.data(), sizeof(int2) * (size_t)n_tiles, cudaMemcpyHostToDevice,
                                 ctx->stream));
-  ASM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `tab` and `meta` live on this frame
-  {
-    LaunchScope ls(ctx, ASM_K_GATHER);
-    int blocks = (int)std::min<int64_t>((L.Tp + 7) / 8, (int64_t)ctx->sm_count * 16);
-    gather_bits_kernel<<<blocks, 256, 0, ctx->stream>>>((const SegTableDev*)ctx->seg_dev.p, (uint64_t*)ctx->opnd_bits.p,
-                                                        (int32_t*)ctx->nbits.p);
-  }
-  ASM_CUDA(ctx, cudaGetLastError());
   // S_pad starts at zero; the distance kernels accumulate into it with integer atomics
   if ((rc = asm_reserve(ctx, ctx->S_pad, sizeof(int64_t) * (size_t)L.Tp * L.C)) != ASM_OK) return rc;
   ASM_CUDA(ctx, cudaMemsetAsync(ctx->S_pad.p, 0, sizeof(int64_t) * (size_t)L.Tp * L.C, ctx->stream));
+  return ASM_OK;
+}
+
+int32_t psrf_gather_bits(asm_ctx* ctx) {
+  PsrfLayout& L = ctx->layout;
+  int32_t rc;
+  if ((rc = asm_reserve(ctx, ctx->opnd_bits, sizeof(uint64_t) * (size_t)L.Tp * L.Wp)) != ASM_OK) return rc;
+  SegTableDev tab;
+  if ((rc = psrf_prepare(ctx, tab)) != ASM_OK) return rc;
+  {
+    LaunchScope ls(ctx, ASM_K_GATHER);
+    int blocks = (int)std::min<int64_t>((L.Tp + 7) / 8, (int64_t)ctx->sm_count * 16);
+    gather_bits_kernel<<<blocks, 256, 0, ctx->stream>>>(tab, (uint64_t*)ctx->opnd_bits.p, (int32_t*)ctx->nbits.p);
+  }
+  ASM_CUDA(ctx, cudaGetLastError());
+  return ASM_OK;
+}
+
+int32_t psrf_gather_i8(asm_ctx* ctx) {
+  PsrfLayout& L = ctx->layout;
+  int32_t rc;
+  if ((rc = asm_reserve(ctx, ctx->opnd_i8, (size_t)L.Tp * L.pitch8)) != ASM_OK) return rc;
+  SegTableDev tab;
+  if ((rc = psrf_prepare(ctx, tab)) != ASM_OK) return rc;
+  {
+    LaunchScope ls(ctx, ASM_K_GATHER);
+    int blocks = (int)std::min<int64_t>((L.Tp + 7) / 8, (int64_t)ctx->sm_count * 16);
+    gather_i8_kernel<<<blocks, 256, 0, ctx->stream>>>(tab, (uint4*)ctx->opnd_i8.p, L.pitch8 / 64, (int32_t*)ctx->nbits.p);
+  }
+  ASM_CUDA(ctx, cudaGetLastError());
   return ASM_OK;
 }
 
@@ -269,15 +341,11 @@ int32_t psrf_compact(asm_ctx* ctx, asm_shard shard, int64_t* d_S_out) {
     prm.padB[c] = L.padB[c];
     prm.rowsA[c] = L.rowsA[c];
   }
-  int32_t rc = asm_reserve(ctx, ctx->misc, sizeof prm);
-  if (rc != ASM_OK) return rc;
-  ASM_CUDA(ctx, cudaMemcpyAsync(ctx->misc.p, &prm, sizeof prm, cudaMemcpyHostToDevice, ctx->stream));
-  ASM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   {
     LaunchScope ls(ctx, ASM_K_PSRF_FINISH);
     int64_t total = (int64_t)L.C * L.n_rows * L.C;
     int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)ctx->sm_count * 16);
-    compact_kernel<<<blocks, 256, 0, ctx->stream>>>((const CompactParams*)ctx->misc.p, (const long long*)ctx->S_pad.p,
+    compact_kernel<<<blocks, 256, 0, ctx->stream>>>(prm, (const long long*)ctx->S_pad.p,
                                                     (const int32_t*)ctx->nbits.p, (long long*)d_S_out);
   }
   ASM_CUDA(ctx, cudaGetLastError());

@@ -23,6 +23,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 #include "asm_internal.h"
@@ -340,6 +341,259 @@ rf_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   }
 }
 
+
+// =====================================================================================================
+// 2-CTA variant (cta_group::2): a cluster of two CTAs on one TPC computes a 256x256 block pair.  Each
+// CTA stages its own 128 A rows and its own half (128 rows) of B, so a CTA moves 32 KB per K block
+// instead of 48 KB for the same 128x256 outputs -- L2 -> SM traffic per MAC drops by a third (ncu on
+// the 1-CTA kernel: lts__throughput 76 %, the limiter).  The leader CTA issues
+// tcgen05.mma.cta_group::2 (M = 256); both CTAs' TMA loads signal the leader's `full` barrier; the
+// leader's commits are multicast to both CTAs' `empty` / `tmem_full` barriers; the peer's epilogue
+// warps arrive remotely on the leader's `tmem_empty` barrier.
+// =====================================================================================================
+constexpr int kStages2 = 6;
+constexpr int kStageBytes2 = 2 * kABytes;  // A half + B half: 32 KB
+constexpr size_t kSmemBytes2 = (size_t)kStages2 * kStageBytes2 + kAuxBytes + 64;
+constexpr uint32_t kIdesc2 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;  // shared::cluster address of the same offset in CTA 0 of the pair
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* leader_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(leader_bar) & kPeerMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_i8_2sm(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_c),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {  // arrives on `bar` in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cta0(uint64_t* bar) {  // arrive on CTA 0's copy of `bar`
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar))
+      : "memory");
+}
+
+struct PairInfo {
+  int ib, jb;
+  bool do_row, do_col;  // for THIS CTA's 128 rows
+  int chain_rows, chain_cols;
+};
+
+__device__ __forceinline__ bool decode_pair(long long bp, int rank, const int2* __restrict__ meta, PairInfo& pi) {
+  long long jb = (long long)((sqrt(8.0 * (double)bp + 1.0) - 1.0) * 0.5);
+  while (jb * (jb + 1) / 2 > bp) jb--;
+  while ((jb + 1) * (jb + 2) / 2 <= bp) jb++;
+  const int ib = (int)(bp - jb * (jb + 1) / 2);
+  pi.ib = ib;
+  pi.jb = (int)jb;
+  const int2 mi0 = meta[2 * ib], mi1 = meta[2 * ib + 1], mj0 = meta[2 * jb], mj1 = meta[2 * jb + 1];
+  const bool diag = ib == (int)jb;
+  const bool col_j = (mj0.y & kFlagCol) != 0, col_i = (mi0.y & kFlagCol) != 0;
+  const bool rows_j = ((mj0.y | mj1.y) & kFlagRows) != 0;
+  const int my = rank ? mi1.y : mi0.y;
+  pi.do_row = (my & kFlagRows) && col_j;
+  pi.do_col = !diag && col_i && rows_j;
+  pi.chain_rows = mi0.x;
+  pi.chain_cols = mj0.x;
+  return (((mi0.y | mi1.y) & kFlagRows) && col_j) || pi.do_col;  // identical in both CTAs of the pair
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+rf_i8x2_kernel(const __grid_constant__ CUtensorMap tm, int nkb, const int* __restrict__ nbits,
+               const int2* __restrict__ tile_meta, long long n_pairs, int shard_index, int shard_count,
+               unsigned long long* __restrict__ S, int C) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  unsigned char* aux = smem + (size_t)kStages2 * kStageBytes2;
+  uint64_t* full = reinterpret_cast<uint64_t*>(aux);  // [kStages2]   (used in CTA 0)
+  uint64_t* empty = full + kStages2;                  // [kStages2]   (each CTA)
+  uint64_t* tfull = empty + kStages2;                 // [2]          (each CTA)
+  uint64_t* tempty = tfull + 2;                       // [2]          (used in CTA 0)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+  int* nb_s = reinterpret_cast<int*>(aux + 192);
+  uint32_t* colpart = reinterpret_cast<uint32_t*>(aux + 192 + 2 * kTileN * 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages2; s++) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; a++) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 2 * kEpiWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  cluster_sync_all();  // the peer's barriers exist before anything can arrive on them
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const long long first = blockIdx.x >> 1, stride = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs; completion bytes go to CTA 0's full barrier) =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long k = first;; k += stride) {
+        const long long bp = k * shard_count + shard_index;
+        if (bp >= n_pairs) break;
+        PairInfo pi;
+        if (!decode_pair(bp, rank, tile_meta, pi)) continue;
+        for (int kb = 0; kb < nkb; kb++) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          unsigned char* st = smem + (size_t)stage * kStageBytes2;
+          if (rank == 0) mbar_expect_tx(&full[stage], 2 * kStageBytes2);  // bytes of both CTAs
+          tma_load_2d_2sm(st, &tm, kb * kBlockK, pi.ib * kBlockRows + rank * kTileRows, &full[stage]);
+          tma_load_2d_2sm(st + kABytes, &tm, kb * kBlockK, pi.jb * kBlockRows + rank * kTileRows, &full[stage]);
+          if (++stage == kStages2) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (leader CTA only) =====
+    if (rank == 0 && lane == 0) {
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (long long k = first;; k += stride) {
+        const long long bp = k * shard_count + shard_index;
+        if (bp >= n_pairs) break;
+        PairInfo pi;
+        if (!decode_pair(bp, rank, tile_meta, pi)) continue;
+        mbar_wait(&tempty[acc], acc_phase ^ 1);  // both CTAs' epilogues have drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_c = tmem_base + (uint32_t)(acc * kAccCols);
+        for (int kb = 0; kb < nkb; kb++) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + (size_t)stage * kStageBytes2);
+          const uint64_t adesc = make_desc(a_addr), bdesc = make_desc(a_addr + kABytes);
+#pragma unroll
+          for (int kk = 0; kk < kBlockK / 32; kk++)
+            umma_i8_2sm(tmem_c, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), kIdesc2, (uint32_t)((kb | kk) != 0));
+          umma_commit_2sm(&empty[stage]);
+          if (++stage == kStages2) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_2sm(&tfull[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue (each CTA: its 128 rows x 256 columns) =====
+    const int ew = warp - 4;
+    const int quad = warp & 3;
+    const int half = ew >> 2;
+    const int et = threadIdx.x - 128;
+    int acc = 0, buf = 0;
+    uint32_t acc_phase = 0;
+    for (long long k = first;; k += stride) {
+      const long long bp = k * shard_count + shard_index;
+      if (bp >= n_pairs) break;
+      PairInfo pi;
+      if (!decode_pair(bp, rank, tile_meta, pi)) continue;
+      const long long col0 = (long long)pi.jb * kTileN;
+      const long long row = (long long)pi.ib * kBlockRows + rank * kTileRows + quad * 32 + lane;
+      nb_s[buf * kTileN + et] = nbits[col0 + et] + 1;
+      const int na = nbits[row];
+      epi_barrier();
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kAccCols + half * 128);
+      unsigned long long row_sum = 0;
+#pragma unroll 1
+      for (int cc = 0; cc < 4; cc++) {
+        uint32_t r[32];
+        tmem_ld32(taddr + cc * 32, r);
+        const int* nb = nb_s + buf * kTileN + half * 128 + cc * 32;
+        uint32_t chunk = 0, mycol = 0;
+        if (pi.do_col) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            const uint32_t e = (uint32_t)(na + nb[j] - 2 * (int)r[j]);
+            const uint32_t v = e * e;
+            chunk += v;
+            const uint32_t s = __reduce_add_sync(0xffffffffu, v);
+            if (lane == j) mycol = s;
+          }
+          colpart[quad * kTileN + half * 128 + cc * 32 + lane] = mycol;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            const uint32_t e = (uint32_t)(na + nb[j] - 2 * (int)r[j]);
+            chunk += e * e;
+          }
+        }
+        row_sum += chunk;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0)
+          mbar_arrive(&tempty[acc]);
+        else
+          mbar_arrive_cta0(&tempty[acc]);
+      }
+      if (pi.do_row) atomicAdd(&S[(size_t)row * C + pi.chain_cols], row_sum);
+      if (pi.do_col) {
+        epi_barrier();
+        const uint32_t v = colpart[et] + colpart[kTileN + et] + colpart[2 * kTileN + et] + colpart[3 * kTileN + et];
+        atomicAdd(&S[(size_t)(col0 + et) * C + pi.chain_rows], (unsigned long long)v);
+      }
+      buf ^= 1;
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // neither CTA leaves (or frees TMEM) while the other may still signal it
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+  }
+}
+
 // ---- host side ------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -408,16 +662,46 @@ __global__ void __launch_bounds__(256) expand_rows_kernel(const uint64_t* __rest
 
 }  // namespace
 
+static bool use_two_cta() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ASM_I8_1CTA");
+    v = (e && e[0] && e[0] != '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 int32_t rf_i8_sums(asm_ctx* ctx, asm_shard shard) {
   PsrfLayout& L = ctx->layout;
   const long long nb = L.Tp / kBlockRows;
-  const long long n_tiles = nb * (nb + 1);  // two 128x256 tiles per block pair of the upper triangle
-  L.tiles_total = n_tiles;
-  L.tiles_done = (n_tiles - shard.shard_index + shard.shard_count - 1) / shard.shard_count;
-  const uint64_t Dp = (uint64_t)L.Wp * 64;
+  const uint64_t Dp = (uint64_t)L.pitch8;
+  L.bits_used = (int64_t)Dp;
   CUtensorMap tm;
   int32_t rc = make_tmap(ctx, &tm, ctx->opnd_i8.p, (uint64_t)L.Tp, Dp);
   if (rc != ASM_OK) return rc;
+  if (use_two_cta()) {
+    const long long n_pairs = nb * (nb + 1) / 2;  // 256x256 block pairs of the upper triangle, one per cluster step
+    L.tiles_total = n_pairs;
+    L.tiles_done = (n_pairs - shard.shard_index + shard.shard_count - 1) / shard.shard_count;
+    static bool attr = false;
+    if (!attr) {
+      ASM_CUDA(ctx, cudaFuncSetAttribute(rf_i8x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes2));
+      attr = true;
+    }
+    const int clusters = (int)std::min<long long>(L.tiles_done, ctx->sm_count / 2);
+    if (clusters <= 0) return ASM_OK;
+    {
+      LaunchScope ls(ctx, ASM_K_RF_I8);
+      rf_i8x2_kernel<<<2 * clusters, kThreads, kSmemBytes2, ctx->stream>>>(
+          tm, (int)(Dp / kBlockK), (const int*)ctx->nbits.p, (const int2*)ctx->blk_meta.p, n_pairs, shard.shard_index,
+          shard.shard_count, (unsigned long long*)ctx->S_pad.p, L.C);
+    }
+    ASM_CUDA(ctx, cudaGetLastError());
+    return ASM_OK;
+  }
+  const long long n_tiles = nb * (nb + 1);  // two 128x256 tiles per block pair of the upper triangle
+  L.tiles_total = n_tiles;
+  L.tiles_done = (n_tiles - shard.shard_index + shard.shard_count - 1) / shard.shard_count;
   if ((rc = set_smem_attr<false>(ctx)) != ASM_OK) return rc;
   const int grid = (int)std::min<long long>(L.tiles_done, ctx->sm_count);
   if (grid <= 0) return ASM_OK;

@@ -222,6 +222,7 @@ int32_t rf_popc_sums(asm_ctx* ctx, asm_shard shard) {
   const long long n_tiles = L.Tp / kTileRows;
   const long long n_pairs = n_tiles * (n_tiles + 1) / 2;
   L.tiles_total = n_pairs;
+  L.bits_used = (int64_t)L.Wp * 64;
   L.tiles_done = (n_pairs - shard.shard_index + shard.shard_count - 1) / shard.shard_count;
   int32_t rc = asm_reserve(ctx, ctx->tile_counter, sizeof(unsigned long long));
   if (rc != ASM_OK) return rc;
