@@ -17,8 +17,8 @@
 // values and the 8 current samples (LDS.128, XOR-swizzled 64-byte blocks so that the 8 lanes of a
 // quarter warp hit 8 different bank groups) and issues 64 DMUL + 64 DADD on a 15-value register
 // window.  Bound: FP64 pipe; arithmetic intensity ~500 flop/byte of HBM.
-// K6 ess_finish_kernel: one warp per trace: the sequential `sum`, then the autocorrelation
-// normalisation (:154-155), the pair-sum truncated integral (:161-172) and ACT/ESS (:178,:126-128).
+// ess_sum_kernel: the sequential `sum` chain, on a side stream.  K6 ess_finish_kernel: one thread per trace:
+// the autocorrelation normalisation (:154-155), the pair-sum truncated integral (:161-172) and ACT/ESS (:178,:126-128).
 #include <algorithm>
 #include <cmath>
 
@@ -129,27 +129,48 @@ __global__ void __launch_bounds__(kNT) ess_lag_kernel(const double* __restrict__
   for (int r = 0; r < kR; r++) out[r] = acc[r];
 }
 
-// One warp per trace.
-__global__ void __launch_bounds__(32) ess_finish_kernel(const double* __restrict__ traces, long long stride, long long n,
-                                                        int max_lag, int lags_stride, const double* __restrict__ sls,
-                                                        double* __restrict__ act_out, double* __restrict__ ess_out,
-                                                        int* __restrict__ lags_used) {
-  __shared__ double buf[256];
-  const int lane = threadIdx.x;
-  const long long trace = blockIdx.x;
+// The sequential `sum` chain (TraceESS.java:137): one warp per trace, 8 traces per block (few, fat blocks,
+// so that the lag kernel keeps its CTA slots).  The lanes stage 256 samples in shared memory while lane 0
+// adds the previous 256 in order.  Latency-bound (one dependent DADD per sample): it runs on a side stream
+// underneath the lag kernel.
+constexpr int kSumWarps = 8;
+__global__ void __launch_bounds__(32 * kSumWarps) ess_sum_kernel(const double* __restrict__ traces, long long stride,
+                                                                 long long n, int n_traces, double* __restrict__ sums) {
+  __shared__ double bufs[kSumWarps][2][256];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const long long trace = (long long)blockIdx.x * kSumWarps + wid;
+  if (trace >= n_traces) return;
+  double(*buf)[256] = bufs[wid];
   const double* __restrict__ x = traces + trace * stride;
   double sum = 0.0;
+  int cur = 0;
+  for (int k = lane; k < 256 && k < n; k += 32) buf[0][k] = x[k];
+  __syncwarp();
   for (long long base = 0; base < n; base += 256) {
     const int m = (int)min(256LL, n - base);
-    for (int k = lane; k < m; k += 32) buf[k] = x[base + k];
-    __syncwarp();
-    if (lane == 0) {
+    const long long nb = base + 256;
+    if (lane != 0) {  // lanes 1..31 prefetch the next block while lane 0 adds
+      for (long long k = nb + lane - 1; k < nb + 256 && k < n; k += 31) buf[cur ^ 1][k - nb] = x[k];
+    } else {
 #pragma unroll 8
-      for (int k = 0; k < m; k++) sum = __dadd_rn(sum, buf[k]);  // :137
+      for (int k = 0; k < m; k++) sum = __dadd_rn(sum, buf[cur][k]);
     }
     __syncwarp();
+    cur ^= 1;
   }
-  if (lane != 0) return;
+  if (lane == 0) sums[trace] = sum;
+}
+
+// One thread per trace: normalisation (:154-155), pair-sum truncated integral (:161-172), ACT and ESS.
+__global__ void __launch_bounds__(128) ess_finish_kernel(const double* __restrict__ traces, long long stride, long long n,
+                                                         int n_traces, int max_lag, int lags_stride,
+                                                         const double* __restrict__ sls, const double* __restrict__ sums,
+                                                         double* __restrict__ act_out, double* __restrict__ ess_out,
+                                                         int* __restrict__ lags_used) {
+  const long long trace = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (trace >= n_traces) return;
+  const double* __restrict__ x = traces + trace * stride;
+  const double sum = sums[trace];
   const long long L = n < (long long)max_lag ? n : (long long)max_lag;  // :160
   const double* s = sls + trace * (long long)lags_stride;
   double act;
@@ -223,21 +244,31 @@ int32_t ess_batch_device(asm_ctx* ctx, int32_t n_traces, int64_t n_samples, int6
   const int lags_stride = lag_blocks * kLagsPerCta;
   int32_t rc;
   if ((rc = asm_reserve(ctx, ctx->ess_sls, sizeof(double) * (size_t)n_traces * lags_stride)) != ASM_OK) return rc;
-  if ((rc = asm_reserve(ctx, ctx->ess_out, sizeof(double) * 2 * (size_t)n_traces + sizeof(int) * (size_t)n_traces)) != ASM_OK)
+  if ((rc = asm_reserve(ctx, ctx->ess_out, sizeof(double) * 3 * (size_t)n_traces + sizeof(int) * ((size_t)n_traces + 2))) != ASM_OK)
     return rc;
   double* d_act = (double*)ctx->ess_out.p;
   double* d_ess = d_act + n_traces;
   int* d_used = (int*)(d_ess + n_traces);
+  double* d_sums = (double*)(d_used + n_traces + (n_traces & 1));
+  // sum chain on the side stream, underneath the lag kernel
+  ASM_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+  ASM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+  ctx->launches++;
+  ess_sum_kernel<<<(n_traces + kSumWarps - 1) / kSumWarps, 32 * kSumWarps, 0, ctx->stream2>>>(d_traces, stride, n_samples,
+                                                                                              n_traces, d_sums);
+  ASM_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));
   if (n_samples > 0) {
     LaunchScope ls(ctx, ASM_K_ESS_LAG);
     ess_lag_kernel<<<n_traces * lag_blocks, kNT, 0, ctx->stream>>>(d_traces, stride, n_samples, lag_blocks,
                                                                    (double*)ctx->ess_sls.p);
   }
   ASM_CUDA(ctx, cudaGetLastError());
+  ASM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
   {
     LaunchScope ls(ctx, ASM_K_ESS_FINISH);
-    ess_finish_kernel<<<n_traces, 32, 0, ctx->stream>>>(d_traces, stride, n_samples, max_lag, lags_stride,
-                                                        (const double*)ctx->ess_sls.p, d_act, d_ess, d_used);
+    ess_finish_kernel<<<(n_traces + 127) / 128, 128, 0, ctx->stream>>>(d_traces, stride, n_samples, n_traces, max_lag,
+                                                                       lags_stride, (const double*)ctx->ess_sls.p, d_sums,
+                                                                       d_act, d_ess, d_used);
   }
   ASM_CUDA(ctx, cudaGetLastError());
   if (act_out_host)

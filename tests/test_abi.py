@@ -12,10 +12,10 @@ from asm_b200 import _lib as L
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def header_functions():
-    src = open(os.path.join(ROOT, "include", "asmgpu.h")).read()
+def header_functions(name="asmgpu.h", prefix="asm_"):
+    src = open(os.path.join(ROOT, "include", name)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(asm_[a-z0-9_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(%s[a-z0-9_]+)\s*\(" % prefix, src)))
 
 
 def test_library_exports_every_declared_symbol():
@@ -27,6 +27,12 @@ def test_library_exports_every_declared_symbol():
     # the binding covers the header one to one
     assert sorted(L.SIGNATURES) == names
     assert L.lib().asm_version().startswith(b"asm-b200")
+    # host wrapper (criteria mirror): include/asmgpu_host.h
+    from asm_b200 import criteria
+    host = header_functions("asmgpu_host.h", "asmh_")
+    assert len(host) >= 20 and sorted(criteria.HOST_SIGNATURES) == host
+    for n in host:
+        assert hasattr(raw, n), f"libasmgpu.so does not export {n}"
 
 
 def test_no_torch_types_in_the_abi():
@@ -43,6 +49,27 @@ def test_no_cpu_fallback():
     # null context: every entry point returns ASM_E_INVALID instead of crashing
     assert L.lib().asm_psrf_eval(None, None, 0, 0, 1, 0, None, None) == L.ASM_E_INVALID
     assert L.lib().asm_ess_batch(None, 1, 1, 1, None, 2000, None, None) == L.ASM_E_INVALID
+    from asm_b200 import criteria
+    with pytest.raises(L.AsmGpuError) as e:
+        criteria.TraceInfo(2)  # TraceInfo owns a GPU context
+    assert e.value.code == L.ASM_E_NO_DEVICE
+
+
+def test_criteria_validation_matches_the_reference():
+    """initAndValidate sites (TreePSRF.java:54-84; TreeESS.java:45-76) -- host logic, no GPU needed."""
+    from asm_b200 import criteria as K
+    K.TreePSRF()  # defaults are valid
+    K.TreePSRF(smoothing=0.0), K.TreePSRF(smoothing=0.9, cacheLimit=200)
+    for kw in (dict(smoothing=1.5), dict(smoothing=-0.1), dict(smoothing=float("nan")), dict(targetESS=0),
+               dict(cacheLimit=0), dict(cacheLimit=100, targetESS=100), dict(sampleSize=0),
+               dict(sampleSize=100, targetESS=100)):
+        with pytest.raises(K.IllegalArgumentException):
+            K.TreePSRF(**kw)
+    # TreeESS.initAndValidate as written throws for every smoothing >= 0, its own default included (TreeESS.java:47)
+    with pytest.raises(K.IllegalArgumentException):
+        K.TreeESS()
+    K.TreeESS(smoothing=-0.5)
+    assert K.TraceESS().header() == "TraceESS" and K.TreePSRF().header() == "TreePSRF"
 
 
 def test_product_does_not_import_the_oracle():
