@@ -104,14 +104,24 @@ class ClockSampler:
 
 # --------------------------------------------------------------------------------------------------
 def gen_psrf_input(cfg, n_trees, want_topologies=False):
-    """Synthetic chains -> (encoder, [bits per chain], [topologies per chain] or None)."""
+    """Synthetic chains -> (encoder, [bits per chain], [topologies per chain] or None).
+
+    Chains longer than cfg["n_trees"] (the weak-scaling runs at N > 1 GPUs) keep the first cfg["n_trees"]
+    generated trees and append a seeded resample of them, so the clade dictionary -- the K dimension of the
+    contraction, i.e. the work per tree pair -- is the same at every N."""
     import asm_b200 as A
     from asm_b200 import _lib as L
     enc = A.Encoder(cfg["n_taxa"])
+    n_base = min(n_trees, cfg["n_trees"])
     ids, topo = [], []
     for c in range(cfg["n_chains"]):
-        l, r, root, i = L.synth_tree_chain(cfg["n_taxa"], n_trees, cfg["start_seed"], cfg["seed0"] + c, cfg["moves"],
+        l, r, root, i = L.synth_tree_chain(cfg["n_taxa"], n_base, cfg["start_seed"], cfg["seed0"] + c, cfg["moves"],
                                            cfg["beta"], topologies=want_topologies, encoder=enc)
+        if n_trees > n_base:
+            pick = np.random.default_rng(cfg["seed0"] + 1000 + c).integers(0, n_base, n_trees - n_base)
+            i = np.concatenate([i, i[pick]])
+            if want_topologies:
+                l, r, root = np.concatenate([l, l[pick]]), np.concatenate([r, r[pick]]), np.concatenate([root, root[pick]])
         ids.append(i)
         topo.append((l, r, root))
     words = enc.words
@@ -376,6 +386,8 @@ def bench_psrf(args, rank, world, local, dist):
                        "l2": "L2 flushed (256 MiB write) between timed steps, outside the timed bracket",
                        "timing": "CUDA events on the library stream per step" if world == 1 else "host bracket after device sync, max over ranks",
                        "generator": {k: cfg[k] for k in ("beta", "moves", "start_seed", "seed0")},
+                       "weak_scaling": "trees per chain = 10000*sqrt(N); trees beyond the first 10000 are a seeded resample "
+                                       "of them, so D (work per pair) is the same at every N",
                        "psrf_mean_01": float(mean[0, 1]), "psrf_mean_10": float(mean[1, 0])},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
             "step_breakdown_ms": fam_ms}
