@@ -62,6 +62,8 @@ SIGNATURES = {
     "asm_launch_count": (_i64, [_p]),
     "asm_sync": (_i32, [_p]),
     "asm_flush_l2": (_i32, [_p]),
+    "asm_ess_last_lag_count": (_i64, [_p]),
+    "asm_ess_set_adaptive": (_i32, [_p, _i32]),
     "asm_psrf_last_layout": (_i32, [_p, _i64p, _i64p, _i64p, _i64p]),
     "asm_encoder_create": (_i32, [C.POINTER(_p), _i32]),
     "asm_encoder_destroy": (_i32, [_p]),
@@ -355,6 +357,12 @@ class GpuContext:
 
     def flush_l2(self):
         self._check(lib().asm_flush_l2(self._h))
+
+    def ess_set_adaptive(self, on: bool):
+        self._check(lib().asm_ess_set_adaptive(self._h, int(on)))
+
+    def ess_last_lag_count(self) -> int:
+        return int(lib().asm_ess_last_lag_count(self._h))
 
     def last_layout(self):
         a, b, c, d = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()

@@ -65,6 +65,7 @@ struct asm_ctx {
   int sm_count = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;  // side stream (ESS sum chain)
+  cudaStream_t stream_copy = nullptr;  // H2D copies overlapped with compute (asm_ess_batch)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int32_t words = 0;  // stored row width of every chain (uint64 words)
   std::vector<ChainTrees> trees;
@@ -81,6 +82,8 @@ struct asm_ctx {
   double prof_ms[ASM_K_COUNT] = {};
   int64_t prof_n[ASM_K_COUNT] = {};
   int64_t launches = 0;
+  bool ess_adaptive = true;     // staged lag evaluation (ess.cu)
+  long long ess_lag_slots = 0;  // (trace, lag) chains evaluated by the last ESS call
   std::string err;
 };
 

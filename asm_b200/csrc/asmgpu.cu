@@ -1,8 +1,11 @@
 // asmgpu.cu -- context, tree / trace storage and the C-ABI glue of libasmgpu.so.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <new>
+#include <vector>
 
 #include "asm_internal.h"
 
@@ -186,11 +189,16 @@ int32_t asm_create(asm_ctx** out, int32_t device, int32_t n_chains) {
   ctx->sm_count = prop.multiProcessorCount;
   ctx->trees.resize((size_t)n_chains);
   ctx->traces.resize((size_t)n_chains);
+  {
+    const char* e = getenv("ASM_ESS_ADAPTIVE");
+    ctx->ess_adaptive = !(e && e[0] == '0');
+  }
   if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
     delete ctx;
     return asm_fail(nullptr, ASM_E_CUDA, "stream create: %s", cudaGetErrorString(e));
   }
   cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&ctx->stream_copy, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
   for (auto& ev : ctx->timer) cudaEventCreate(&ev);
@@ -220,6 +228,7 @@ int32_t asm_destroy(asm_ctx* ctx) {
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+  if (ctx->stream_copy) cudaStreamDestroy(ctx->stream_copy);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return ASM_OK;
@@ -360,11 +369,36 @@ int32_t asm_ess_batch(asm_ctx* ctx, int32_t n_traces, int64_t n_samples, int64_t
   if (n_pad == 0) n_pad = 2;
   int32_t rc = asm_reserve(ctx, ctx->ess_tr, sizeof(double) * (size_t)n_traces * (size_t)n_pad);
   if (rc != ASM_OK) return rc;
-  if (n_samples > 0)
-    ASM_CUDA(ctx, cudaMemcpy2DAsync(ctx->ess_tr.p, sizeof(double) * (size_t)n_pad, traces, sizeof(double) * (size_t)stride,
-                                    sizeof(double) * (size_t)n_samples, (size_t)n_traces, cudaMemcpyHostToDevice,
-                                    ctx->stream));
-  return ess_batch_device(ctx, n_traces, n_samples, n_pad, (const double*)ctx->ess_tr.p, max_lag, act_out, ess_out);
+  double* d_tr = (double*)ctx->ess_tr.p;
+  // Chunked upload on the copy stream, each chunk evaluated as soon as it has landed: with page-locked host
+  // memory the H2D copy of chunk k+1 runs underneath the kernels of chunk k.
+  const int64_t chunk_bytes = 256LL << 20;
+  int32_t chunk = (int32_t)std::max<int64_t>(1, std::min<int64_t>(n_traces, chunk_bytes / (n_pad * 8)));
+  if ((int64_t)n_traces * n_pad * 8 <= 2 * chunk_bytes) chunk = n_traces;
+  const int n_chunks = (n_traces + chunk - 1) / chunk;
+  std::vector<cudaEvent_t> ev((size_t)n_chunks, nullptr);
+  for (int k = 0; k < n_chunks; k++) {
+    const int32_t t0 = k * chunk, nt = std::min(chunk, n_traces - t0);
+    ASM_CUDA(ctx, cudaEventCreateWithFlags(&ev[(size_t)k], cudaEventDisableTiming));
+    if (n_samples > 0)
+      ASM_CUDA(ctx, cudaMemcpy2DAsync(d_tr + (size_t)t0 * n_pad, sizeof(double) * (size_t)n_pad, traces + (size_t)t0 * stride,
+                                      sizeof(double) * (size_t)stride, sizeof(double) * (size_t)n_samples, (size_t)nt,
+                                      cudaMemcpyHostToDevice, ctx->stream_copy));
+    ASM_CUDA(ctx, cudaEventRecord(ev[(size_t)k], ctx->stream_copy));
+  }
+  long long slots = 0;
+  for (int k = 0; k < n_chunks && rc == ASM_OK; k++) {
+    const int32_t t0 = k * chunk, nt = std::min(chunk, n_traces - t0);
+    cudaStreamWaitEvent(ctx->stream, ev[(size_t)k], 0);
+    rc = ess_batch_device(ctx, nt, n_samples, n_pad, d_tr + (size_t)t0 * n_pad, max_lag, act_out ? act_out + t0 : nullptr,
+                          ess_out ? ess_out + t0 : nullptr);
+    slots += ctx->ess_lag_slots;
+  }
+  ctx->ess_lag_slots = slots;
+  cudaStreamSynchronize(ctx->stream_copy);
+  for (cudaEvent_t e : ev)
+    if (e) cudaEventDestroy(e);
+  return rc;
 }
 
 int32_t asm_traces_append(asm_ctx* ctx, int32_t chain, int32_t n_cols, int64_t n_new, const double* values) {
@@ -473,6 +507,13 @@ int32_t asm_flush_l2(asm_ctx* ctx) {
     flush_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>((uint4*)ctx->flush.p, bytes / 16, ++v);
   }
   ASM_CUDA(ctx, cudaGetLastError());
+  return ASM_OK;
+}
+
+int64_t asm_ess_last_lag_count(const asm_ctx* ctx) { return ctx ? ctx->ess_lag_slots : 0; }
+int32_t asm_ess_set_adaptive(asm_ctx* ctx, int32_t on) {
+  if (!ctx) return ASM_E_INVALID;
+  ctx->ess_adaptive = on != 0;
   return ASM_OK;
 }
 

@@ -11,26 +11,30 @@
 // Java order -- one accumulator per (trace, lag), samples visited in ascending i, a separate
 // multiply and add per step (DMUL + DADD, never DFMA) -- and spreads the chains over threads.
 //
-// K5 ess_lag_kernel: one CTA = 128 threads x 8 lags = 1024 consecutive lags of one trace.  The
-// trace streams through a 4096-sample shared-memory ring (cp.async, one chunk of 512 samples in
-// flight while the previous one is consumed).  Per group of 8 samples a thread reads 8 new window
-// values and the 8 current samples (LDS.128, XOR-swizzled 64-byte blocks so that the 8 lanes of a
-// quarter warp hit 8 different bank groups) and issues 64 DMUL + 64 DADD on a 15-value register
-// window.  Bound: FP64 pipe; arithmetic intensity ~500 flop/byte of HBM.
-// ess_sum_kernel: the sequential `sum` chain, on a side stream.  K6 ess_finish_kernel: one thread per trace:
-// the autocorrelation normalisation (:154-155), the pair-sum truncated integral (:161-172) and ACT/ESS (:178,:126-128).
+// K5 ess_lag_kernel<R>: one CTA = blockDim.x threads x R consecutive lags of one trace.  The trace
+// streams through a 4096-sample shared-memory ring (cp.async, one chunk of 512 samples in flight while
+// the previous one is consumed).  Per group of R samples a thread reads R new window values and the R
+// current samples (LDS.128, XOR-swizzled 64-byte blocks so that the 8 lanes of a quarter warp hit 8
+// different bank groups) and issues R*R DMUL + R*R DADD on a (2R-1)-value register window.
+// Bound: FP64 pipe; arithmetic intensity ~500 flop/byte of HBM.
+//
+// Staged evaluation: the integral of TraceESS.java:161-172 stops at the first even lag whose pair sum
+// autoCorrelation[lag-1] + autoCorrelation[lag] is not positive, so lags beyond that point cannot change
+// the result.  Lags are therefore evaluated in stages [0,256), [256,1024), [1024,2048); after each stage
+// K6 ess_scan_kernel advances every still-open trace's integral and retires the traces whose loop has
+// stopped (or has reached min(n, 2000) lags).  The output is bit-identical to evaluating all lags
+// (asm_ess_set_adaptive(ctx, 0) / ASM_ESS_ADAPTIVE=0 does exactly that, in one stage).
+// ess_sum_kernel: the sequential `sum` chain, on a side stream underneath the first stage.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "asm_internal.h"
 
 namespace {
 
-constexpr int kNT = 128;             // threads per CTA
-constexpr int kR = 8;                // lags per thread
-constexpr int kLagsPerCta = kNT * kR;  // 1024
-constexpr int kChunk = 512;          // samples per cp.async group
-constexpr int kRing = 4096;          // ring size in samples (>= max lag + 8 + 2*kChunk)
+constexpr int kChunk = 512;  // samples per cp.async group
+constexpr int kRing = 4096;  // ring size in samples (>= max lag + 8 + 2*kChunk)
 
 // logical ring index -> physical: 64-byte blocks, the four 16-byte sub-blocks XOR-swizzled
 __device__ __forceinline__ int ring_phys(int e) {
@@ -49,38 +53,42 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// read the aligned 8-sample block that starts at logical index e0 (multiple of 8)
-__device__ __forceinline__ void load_block8(const double* ring, int e0, double (&v)[8]) {
-  const int g = (e0 & (kRing - 1)) >> 3;
+// read the aligned R-sample block that starts at logical index e0 (multiple of R), R = 4 or 8
+template <int R>
+__device__ __forceinline__ void load_block(const double* ring, int e0, double (&v)[R]) {
+  const int e = e0 & (kRing - 1);
+  const int g = e >> 3;
   const int sw = (g >> 1) & 3;
+  const int first = (R == 8) ? 0 : ((e >> 2) & 1) * 2;  // first 16-byte sub-block of the group
   const double2* base = reinterpret_cast<const double2*>(ring + (g << 3));
 #pragma unroll
-  for (int s = 0; s < 4; s++) {
-    double2 d = base[s ^ sw];
+  for (int s = 0; s < R / 2; s++) {
+    double2 d = base[(first + s) ^ sw];
     v[2 * s] = d.x;
     v[2 * s + 1] = d.y;
   }
 }
 
-__global__ void __launch_bounds__(kNT) ess_lag_kernel(const double* __restrict__ traces, long long stride, long long n,
-                                                      int lag_blocks, double* __restrict__ sls) {
+// grid: x = trace (index into trace_ids if given), y = lag block of this stage
+template <int R>
+__global__ void __launch_bounds__(256) ess_lag_kernel(const double* __restrict__ traces, long long stride, long long n,
+                                                      int lag_begin, const int* __restrict__ trace_ids, int lags_stride,
+                                                      double* __restrict__ sls) {
   __shared__ __align__(16) double ring[kRing];
-  const int tid = threadIdx.x;
-  const long long trace = blockIdx.x / lag_blocks;
-  const int lb = blockIdx.x % lag_blocks;
+  const int tid = threadIdx.x, NT = blockDim.x;
+  const long long trace = trace_ids ? trace_ids[blockIdx.x] : blockIdx.x;
   const double* __restrict__ x = traces + trace * stride;
-  const int l0 = lb * kLagsPerCta + tid * kR;
+  const int l0 = lag_begin + (int)blockIdx.y * NT * R + tid * R;
 
-  for (int e = tid; e < kRing; e += kNT) ring[e] = 0.0;  // x[i] = 0 for i < 0
+  for (int e = tid; e < kRing; e += NT) ring[e] = 0.0;  // x[i] = 0 for i < 0
   __syncthreads();
 
-  const long long n8 = (n + 7) & ~7LL;
-  const long long n_chunks = (n8 + kChunk - 1) / kChunk;
+  const long long nR = (n + R - 1) / R * R;
+  const long long n_chunks = (nR + kChunk - 1) / kChunk;
 
   auto load_chunk = [&](long long c) {
     const long long base = c * kChunk;
-#pragma unroll
-    for (int e = tid; e < kChunk; e += kNT) {
+    for (int e = tid; e < kChunk; e += NT) {
       const long long i = base + e;
       double* dst = ring + ring_phys((int)(i & (kRing - 1)));
       if (i < n)
@@ -91,12 +99,12 @@ __global__ void __launch_bounds__(kNT) ess_lag_kernel(const double* __restrict__
     cp_async_commit();
   };
 
-  double acc[kR];
-  double w[2 * kR - 1];
+  double acc[R];
+  double w[2 * R - 1];
 #pragma unroll
-  for (int r = 0; r < kR; r++) acc[r] = 0.0;
+  for (int r = 0; r < R; r++) acc[r] = 0.0;
 #pragma unroll
-  for (int k = 0; k < 2 * kR - 1; k++) w[k] = 0.0;
+  for (int k = 0; k < 2 * R - 1; k++) w[k] = 0.0;
 
   if (n_chunks > 0) load_chunk(0);
   for (long long c = 0; c < n_chunks; c++) {
@@ -108,31 +116,32 @@ __global__ void __launch_bounds__(kNT) ess_lag_kernel(const double* __restrict__
     }
     __syncthreads();
     const long long i_begin = c * kChunk;
-    const long long i_end = min(i_begin + (long long)kChunk, n8);
-    for (long long i = i_begin; i < i_end; i += 8) {
-      double xi[8], wn[8];
-      load_block8(ring, (int)(i & (kRing - 1)), xi);
-      load_block8(ring, (int)((i - l0) & (kRing - 1)), wn);
+    const long long i_end = min(i_begin + (long long)kChunk, nR);
+    for (long long i = i_begin; i < i_end; i += R) {
+      double xi[R], wn[R];
+      load_block<R>(ring, (int)(i & (kRing - 1)), xi);
+      load_block<R>(ring, (int)((i - l0) & (kRing - 1)), wn);
 #pragma unroll
-      for (int k = 0; k < 8; k++) w[kR - 1 + k] = wn[k];
-      // w[k] = x[i - l0 - 7 + k]; lag l0+r pairs x[i+di] with x[i+di-l0-r] = w[7 + di - r]
+      for (int k = 0; k < R; k++) w[R - 1 + k] = wn[k];
+      // w[k] = x[i - l0 - (R-1) + k]; lag l0+r pairs x[i+di] with x[i+di-l0-r] = w[R-1 + di - r]
 #pragma unroll
-      for (int di = 0; di < 8; di++)
+      for (int di = 0; di < R; di++)
 #pragma unroll
-        for (int r = 0; r < kR; r++) acc[r] = __dadd_rn(acc[r], __dmul_rn(w[kR - 1 + di - r], xi[di]));
+        for (int r = 0; r < R; r++) acc[r] = __dadd_rn(acc[r], __dmul_rn(w[R - 1 + di - r], xi[di]));
 #pragma unroll
-      for (int k = 0; k < kR - 1; k++) w[k] = w[k + 8];
+      for (int k = 0; k < R - 1; k++) w[k] = w[k + R];
     }
   }
-  double* out = sls + (trace * lag_blocks + lb) * (long long)kLagsPerCta + tid * kR;
+  if (l0 + R <= lags_stride) {
+    double* out = sls + trace * (long long)lags_stride + l0;
 #pragma unroll
-  for (int r = 0; r < kR; r++) out[r] = acc[r];
+    for (int r = 0; r < R; r++) out[r] = acc[r];
+  }
 }
 
 // The sequential `sum` chain (TraceESS.java:137): one warp per trace, 8 traces per block (few, fat blocks,
 // so that the lag kernel keeps its CTA slots).  The lanes stage 256 samples in shared memory while lane 0
-// adds the previous 256 in order.  Latency-bound (one dependent DADD per sample): it runs on a side stream
-// underneath the lag kernel.
+// adds the previous 256 in order.  Latency-bound (one dependent DADD per sample).
 constexpr int kSumWarps = 8;
 __global__ void __launch_bounds__(32 * kSumWarps) ess_sum_kernel(const double* __restrict__ traces, long long stride,
                                                                  long long n, int n_traces, double* __restrict__ sums) {
@@ -161,53 +170,81 @@ __global__ void __launch_bounds__(32 * kSumWarps) ess_sum_kernel(const double* _
   if (lane == 0) sums[trace] = sum;
 }
 
-// One thread per trace: normalisation (:154-155), pair-sum truncated integral (:161-172), ACT and ESS.
-__global__ void __launch_bounds__(128) ess_finish_kernel(const double* __restrict__ traces, long long stride, long long n,
-                                                         int n_traces, int max_lag, int lags_stride,
-                                                         const double* __restrict__ sls, const double* __restrict__ sums,
-                                                         double* __restrict__ act_out, double* __restrict__ ess_out,
-                                                         int* __restrict__ lags_used) {
-  const long long trace = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (trace >= n_traces) return;
+// per-trace state of the integral loop carried from stage to stage
+struct EssState {
+  double integral, prev, sum1, sum2, ac0;
+  int next_lag;
+};
+
+// K6: one thread per open trace: advance the loop of TraceESS.java:161-172 over the lags [next_lag, stage_end)
+// whose sums are now available; retire the trace (write ACT, ESS) when the loop stops or all L lags are used,
+// otherwise append it to the next stage's work list.
+__global__ void __launch_bounds__(128) ess_scan_kernel(const double* __restrict__ traces, long long stride, long long n,
+                                                       int n_open, const int* __restrict__ ids_in, int max_lag, int stage_end,
+                                                       int lags_stride, const double* __restrict__ sls,
+                                                       const double* __restrict__ sums, EssState* __restrict__ state,
+                                                       double* __restrict__ act_out, double* __restrict__ ess_out,
+                                                       int* __restrict__ lags_used, int* __restrict__ ids_out,
+                                                       int* __restrict__ n_out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_open) return;
+  const long long trace = ids_in ? ids_in[k] : k;
   const double* __restrict__ x = traces + trace * stride;
   const double sum = sums[trace];
   const long long L = n < (long long)max_lag ? n : (long long)max_lag;  // :160
   const double* s = sls + trace * (long long)lags_stride;
-  double act;
-  int used = 0;
+  EssState st = state[trace];
+  bool finished = false;
   if (L == 0) {
-    act = __longlong_as_double(0x7ff8000000000000LL);  // 0.0 / 0.0
+    st.integral = 0.0;
+    st.ac0 = 0.0;  // 0.0 / 0.0 = NaN below
+    finished = true;
   } else {
     const double mean = __ddiv_rn(sum, (double)n);  // :139 at i = n-1
     const double mm = __dmul_rn(mean, mean);
-    double sum1 = sum, sum2 = sum;
-    double integral = 0.0, ac0 = 0.0, prev = 0.0;
-    for (long long lag = 0; lag < L; lag++) {
+    if (st.next_lag == 0) {
+      st.sum1 = sum;
+      st.sum2 = sum;
+      st.integral = 0.0;
+      st.prev = 0.0;
+      st.ac0 = 0.0;
+    }
+    const long long end = L < (long long)stage_end ? L : (long long)stage_end;
+    long long lag = st.next_lag;
+    for (; lag < end; lag++) {
       // :154-155  ((SLS - (sum1+sum2)*mean) + (mean*mean)*(n-lag)) / (n+start-lag), start = 0
-      double a = __dsub_rn(s[lag], __dmul_rn(__dadd_rn(sum1, sum2), mean));
+      double a = __dsub_rn(s[lag], __dmul_rn(__dadd_rn(st.sum1, st.sum2), mean));
       a = __dadd_rn(a, __dmul_rn(mm, (double)(n - lag)));
       a = __ddiv_rn(a, (double)(n - lag));
       if (lag == 0) {  // :163-164
-        integral = a;
-        ac0 = a;
-        used = 1;
+        st.integral = a;
+        st.ac0 = a;
       } else if ((lag & 1) == 0) {  // :165-171
-        used = (int)lag + 1;
-        const double pair = __dadd_rn(prev, a);
-        if (pair > 0)
-          integral = __dadd_rn(integral, __dmul_rn(2.0, pair));
-        else
+        const double pair = __dadd_rn(st.prev, a);
+        if (pair > 0) {
+          st.integral = __dadd_rn(st.integral, __dmul_rn(2.0, pair));
+        } else {
+          finished = true;  // break
+          lag++;
           break;
+        }
       }
-      prev = a;
-      sum1 = __dsub_rn(sum1, x[n - 1 - lag]);  // :156
-      sum2 = __dsub_rn(sum2, x[lag]);          // :157
+      st.prev = a;
+      st.sum1 = __dsub_rn(st.sum1, x[n - 1 - lag]);  // :156
+      st.sum2 = __dsub_rn(st.sum2, x[lag]);          // :157
     }
-    act = __ddiv_rn(integral, ac0);  // :178
+    st.next_lag = (int)lag;
+    if (lag >= L) finished = true;
   }
-  if (act_out) act_out[trace] = act;
-  if (ess_out) ess_out[trace] = __ddiv_rn((double)n, act);  // :126-128
-  if (lags_used) lags_used[trace] = used;
+  if (finished) {
+    const double act = __ddiv_rn(st.integral, st.ac0);  // :178
+    if (act_out) act_out[trace] = act;
+    if (ess_out) ess_out[trace] = __ddiv_rn((double)n, act);  // :126-128
+    if (lags_used) lags_used[trace] = st.next_lag;
+  } else {
+    state[trace] = st;
+    ids_out[atomicAdd(n_out, 1)] = (int)trace;
+  }
 }
 
 struct ConcatParams {
@@ -221,7 +258,8 @@ struct ConcatParams {
 };
 
 // trace[j][offset[i] + (x - burnin[i])] = logLines[i][cols[j]].get(x)   (TraceESS.java:55-60)
-__global__ void __launch_bounds__(256) concat_kernel(const ConcatParams* __restrict__ prm, double* __restrict__ out) {
+__global__ void __launch_bounds__(256) concat_kernel(const __grid_constant__ ConcatParams prm_, double* __restrict__ out) {
+  const ConcatParams* prm = &prm_;
   const long long total = prm->total;
   const long long all = total * prm->n_cols;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < all;
@@ -235,46 +273,88 @@ __global__ void __launch_bounds__(256) concat_kernel(const ConcatParams* __restr
   }
 }
 
+
 }  // namespace
 
 int32_t ess_batch_device(asm_ctx* ctx, int32_t n_traces, int64_t n_samples, int64_t stride, const double* d_traces,
                          int32_t max_lag, double* act_out_host, double* ess_out_host) {
   const long long L = std::min<long long>(n_samples, max_lag);
-  const int lag_blocks = (int)std::max<long long>(1, (L + kLagsPerCta - 1) / kLagsPerCta);
-  const int lags_stride = lag_blocks * kLagsPerCta;
+  const int lags_stride = 2048;  // >= ASM_MAX_LAG rounded up to the widest stage
   int32_t rc;
   if ((rc = asm_reserve(ctx, ctx->ess_sls, sizeof(double) * (size_t)n_traces * lags_stride)) != ASM_OK) return rc;
-  if ((rc = asm_reserve(ctx, ctx->ess_out, sizeof(double) * 3 * (size_t)n_traces + sizeof(int) * ((size_t)n_traces + 2))) != ASM_OK)
-    return rc;
+  // [act n][ess n][sums n][state n][used n (int)][ids_a n (int)][ids_b n (int)][counter (int)]
+  const size_t nd = (size_t)n_traces;
+  const size_t bytes = sizeof(double) * 3 * nd + sizeof(EssState) * nd + sizeof(int) * (3 * nd + 4);
+  if ((rc = asm_reserve(ctx, ctx->ess_out, bytes)) != ASM_OK) return rc;
   double* d_act = (double*)ctx->ess_out.p;
-  double* d_ess = d_act + n_traces;
-  int* d_used = (int*)(d_ess + n_traces);
-  double* d_sums = (double*)(d_used + n_traces + (n_traces & 1));
-  // sum chain on the side stream, underneath the lag kernel
+  double* d_ess = d_act + nd;
+  double* d_sums = d_ess + nd;
+  EssState* d_state = (EssState*)(d_sums + nd);
+  int* d_used = (int*)(d_state + nd);
+  int* d_ids[2] = {d_used + nd, d_used + 2 * nd};
+  int* d_counter = d_used + 3 * nd;
+  ASM_CUDA(ctx, cudaMemsetAsync(d_state, 0, sizeof(EssState) * nd, ctx->stream));
+
+  // sum chain on the side stream, underneath the first stage
   ASM_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
   ASM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
   ctx->launches++;
   ess_sum_kernel<<<(n_traces + kSumWarps - 1) / kSumWarps, 32 * kSumWarps, 0, ctx->stream2>>>(d_traces, stride, n_samples,
                                                                                               n_traces, d_sums);
   ASM_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));
-  if (n_samples > 0) {
-    LaunchScope ls(ctx, ASM_K_ESS_LAG);
-    ess_lag_kernel<<<n_traces * lag_blocks, kNT, 0, ctx->stream>>>(d_traces, stride, n_samples, lag_blocks,
-                                                                   (double*)ctx->ess_sls.p);
+
+  int bounds[4];
+  int n_stage;
+  if (ctx->ess_adaptive) {
+    bounds[0] = 0, bounds[1] = 256, bounds[2] = 1024, bounds[3] = 2048, n_stage = 3;
+  } else {
+    bounds[0] = 0, bounds[1] = 2048, n_stage = 1;
   }
-  ASM_CUDA(ctx, cudaGetLastError());
-  ASM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
-  {
-    LaunchScope ls(ctx, ASM_K_ESS_FINISH);
-    ess_finish_kernel<<<(n_traces + 127) / 128, 128, 0, ctx->stream>>>(d_traces, stride, n_samples, n_traces, max_lag,
-                                                                       lags_stride, (const double*)ctx->ess_sls.p, d_sums,
-                                                                       d_act, d_ess, d_used);
+  int n_open = n_traces;
+  const int* ids_in = nullptr;
+  ctx->ess_lag_slots = 0;
+  for (int s = 0; s < n_stage && n_open > 0; s++) {
+    const int b = bounds[s], e = bounds[s + 1];
+    if (s > 0 && b >= L) break;  // (stage 0 always runs its scan, also for n = 0)
+    const int lags = e - b;
+    if (n_samples > 0) {
+      // enough CTAs x warps to fill 148 SMs: narrow threads (R = 4) when few (trace, lag) chains are open
+      const bool wide = (long long)n_open * lags >= 512LL * 1024;
+      const int R = wide ? 8 : 4;
+      const int nt = std::min(lags / R, wide ? 128 : 256);
+      const int blocks_y = (lags + nt * R - 1) / (nt * R);
+      dim3 grid((unsigned)n_open, (unsigned)blocks_y);
+      LaunchScope ls(ctx, ASM_K_ESS_LAG);
+      if (R == 8)
+        ess_lag_kernel<8><<<grid, nt, 0, ctx->stream>>>(d_traces, stride, n_samples, b, ids_in, lags_stride,
+                                                        (double*)ctx->ess_sls.p);
+      else
+        ess_lag_kernel<4><<<grid, nt, 0, ctx->stream>>>(d_traces, stride, n_samples, b, ids_in, lags_stride,
+                                                        (double*)ctx->ess_sls.p);
+      ctx->ess_lag_slots += (long long)n_open * lags;
+    }
+    ASM_CUDA(ctx, cudaGetLastError());
+    if (s == 0) ASM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    ASM_CUDA(ctx, cudaMemsetAsync(d_counter, 0, sizeof(int), ctx->stream));
+    {
+      LaunchScope ls(ctx, ASM_K_ESS_FINISH);
+      ess_scan_kernel<<<(n_open + 127) / 128, 128, 0, ctx->stream>>>(
+          d_traces, stride, n_samples, n_open, ids_in, max_lag, e, lags_stride, (const double*)ctx->ess_sls.p, d_sums,
+          d_state, d_act, d_ess, d_used, d_ids[s & 1], d_counter);
+    }
+    ASM_CUDA(ctx, cudaGetLastError());
+    if (s + 1 < n_stage) {
+      int cnt = 0;
+      ASM_CUDA(ctx, cudaMemcpyAsync(&cnt, d_counter, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      ASM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      n_open = cnt;
+      ids_in = d_ids[s & 1];
+    }
   }
-  ASM_CUDA(ctx, cudaGetLastError());
   if (act_out_host)
-    ASM_CUDA(ctx, cudaMemcpyAsync(act_out_host, d_act, sizeof(double) * (size_t)n_traces, cudaMemcpyDeviceToHost, ctx->stream));
+    ASM_CUDA(ctx, cudaMemcpyAsync(act_out_host, d_act, sizeof(double) * nd, cudaMemcpyDeviceToHost, ctx->stream));
   if (ess_out_host)
-    ASM_CUDA(ctx, cudaMemcpyAsync(ess_out_host, d_ess, sizeof(double) * (size_t)n_traces, cudaMemcpyDeviceToHost, ctx->stream));
+    ASM_CUDA(ctx, cudaMemcpyAsync(ess_out_host, d_ess, sizeof(double) * nd, cudaMemcpyDeviceToHost, ctx->stream));
   ASM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return ASM_OK;
 }
@@ -299,13 +379,10 @@ int32_t ess_eval_stream(asm_ctx* ctx, const int32_t* burnin, int32_t end, const 
   prm.stride = std::max<int64_t>(2, (total + 1) & ~int64_t(1));
   int32_t rc;
   if ((rc = asm_reserve(ctx, ctx->ess_tr, sizeof(double) * (size_t)n_cols * (size_t)prm.stride)) != ASM_OK) return rc;
-  if ((rc = asm_reserve(ctx, ctx->misc, sizeof prm)) != ASM_OK) return rc;
-  ASM_CUDA(ctx, cudaMemcpyAsync(ctx->misc.p, &prm, sizeof prm, cudaMemcpyHostToDevice, ctx->stream));
-  ASM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (total > 0) {
     LaunchScope ls(ctx, ASM_K_MISC);
     int blocks = (int)std::min<int64_t>((total * n_cols + 255) / 256, (int64_t)ctx->sm_count * 8);
-    concat_kernel<<<blocks, 256, 0, ctx->stream>>>((const ConcatParams*)ctx->misc.p, (double*)ctx->ess_tr.p);
+    concat_kernel<<<blocks, 256, 0, ctx->stream>>>(prm, (double*)ctx->ess_tr.p);
   }
   ASM_CUDA(ctx, cudaGetLastError());
   return ess_batch_device(ctx, n_cols, total, prm.stride, (const double*)ctx->ess_tr.p, ASM_MAX_LAG, nullptr, ess_out_host);

@@ -128,6 +128,23 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
 
+
+// Linear work index -> block pair (ib <= jb) of the upper triangle, walked in G x G supertiles so that the
+// 2G operand blocks a wave of CTAs touches stay resident in L2 (a plain column-major walk streams one
+// operand from HBM with no reuse: 55 TB at cfg5).  Slots that fall outside the triangle are invalid.
+__device__ __forceinline__ bool pair_from_slot(long long slot, int nb, int G, int& ib, int& jb) {
+  const long long g2 = (long long)G * G;
+  const long long st = slot / g2;
+  const int local = (int)(slot - st * g2);
+  long long sj = (long long)((sqrt(8.0 * (double)st + 1.0) - 1.0) * 0.5);
+  while (sj * (sj + 1) / 2 > st) sj--;
+  while ((sj + 1) * (sj + 2) / 2 <= st) sj++;
+  const long long si = st - sj * (sj + 1) / 2;
+  ib = (int)(si * G) + local / G;
+  jb = (int)(sj * G) + local % G;
+  return ib <= jb && jb < nb;
+}
+
 struct TileInfo {
   int row_tile;   // 128-row tile index of the A operand
   int col_block;  // 256-row block index of the B operand
@@ -137,7 +154,7 @@ struct TileInfo {
 
 // PSRF mode: tile t of the upper triangle over 256-row blocks; dump mode: rectangular enumeration.
 template <bool kDump>
-__device__ __forceinline__ bool decode_tile(long long t, int n_row_tiles, const int2* __restrict__ meta, TileInfo& ti) {
+__device__ __forceinline__ bool decode_tile(long long t, int n_row_tiles, int nb, int G, const int2* __restrict__ meta, TileInfo& ti) {
   if (kDump) {
     ti.row_tile = (int)(t % n_row_tiles);
     ti.col_block = (int)(t / n_row_tiles);
@@ -145,16 +162,13 @@ __device__ __forceinline__ bool decode_tile(long long t, int n_row_tiles, const 
     ti.chain_rows = ti.chain_cols = 0;
     return true;
   }
-  const long long bp = t >> 1;
   const int half = (int)(t & 1);
-  long long jb = (long long)((sqrt(8.0 * (double)bp + 1.0) - 1.0) * 0.5);
-  while (jb * (jb + 1) / 2 > bp) jb--;
-  while ((jb + 1) * (jb + 2) / 2 <= bp) jb++;
-  const int ib = (int)(bp - jb * (jb + 1) / 2);
+  int ib, jb;
+  if (!pair_from_slot(t >> 1, nb, G, ib, jb)) return false;
   ti.row_tile = 2 * ib + half;
-  ti.col_block = (int)jb;
+  ti.col_block = jb;
   const int2 mi = meta[ti.row_tile], mj0 = meta[2 * jb], mj1 = meta[2 * jb + 1];
-  const bool diag = ib == (int)jb;
+  const bool diag = ib == jb;
   ti.do_row = (mi.y & kFlagRows) && (mj0.y & kFlagCol);
   ti.do_col = !diag && (mi.y & kFlagCol) && ((mj0.y | mj1.y) & kFlagRows);
   ti.chain_rows = mi.x;
@@ -166,8 +180,8 @@ template <bool kDump>
 __global__ void __launch_bounds__(kThreads, 1)
 rf_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int nkb,
              const int* __restrict__ nbitsA, const int* __restrict__ nbitsB, const int2* __restrict__ tile_meta,
-             long long n_tiles, int n_row_tiles, int shard_index, int shard_count, unsigned long long* __restrict__ S,
-             int C, uint16_t* __restrict__ dump, long long dump_ld) {
+             long long n_tiles, int n_row_tiles, int nb, int G, int shard_index, int shard_count,
+             unsigned long long* __restrict__ S, int C, uint16_t* __restrict__ dump, long long dump_ld) {
   extern __shared__ __align__(1024) unsigned char smem[];  // 128B-swizzle atoms need 1024-byte alignment
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   unsigned char* aux = smem + (size_t)kStages * kStageBytes;
@@ -212,7 +226,7 @@ rf_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const long long t = k * shard_count + shard_index;
         if (t >= n_tiles) break;
         TileInfo ti;
-        if (!decode_tile<kDump>(t, n_row_tiles, tile_meta, ti)) continue;
+        if (!decode_tile<kDump>(t, n_row_tiles, nb, G, tile_meta, ti)) continue;
         for (int kb = 0; kb < nkb; kb++) {
           mbar_wait(&empty[stage], phase ^ 1);
           unsigned char* st = smem + (size_t)stage * kStageBytes;
@@ -236,7 +250,7 @@ rf_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const long long t = k * shard_count + shard_index;
         if (t >= n_tiles) break;
         TileInfo ti;
-        if (!decode_tile<kDump>(t, n_row_tiles, tile_meta, ti)) continue;
+        if (!decode_tile<kDump>(t, n_row_tiles, nb, G, tile_meta, ti)) continue;
         mbar_wait(&tempty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_c = tmem_base + (uint32_t)(acc * kAccCols);
@@ -273,7 +287,7 @@ rf_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const long long t = k * shard_count + shard_index;
       if (t >= n_tiles) break;
       TileInfo ti;
-      if (!decode_tile<kDump>(t, n_row_tiles, tile_meta, ti)) continue;
+      if (!decode_tile<kDump>(t, n_row_tiles, nb, G, tile_meta, ti)) continue;
       const long long col0 = (long long)ti.col_block * kTileN;
       const long long row = (long long)ti.row_tile * kTileRows + quad * 32 + lane;
       nb_s[buf * kTileN + et] = nbitsB[col0 + et] + 1;
@@ -400,15 +414,14 @@ struct PairInfo {
   int chain_rows, chain_cols;
 };
 
-__device__ __forceinline__ bool decode_pair(long long bp, int rank, const int2* __restrict__ meta, PairInfo& pi) {
-  long long jb = (long long)((sqrt(8.0 * (double)bp + 1.0) - 1.0) * 0.5);
-  while (jb * (jb + 1) / 2 > bp) jb--;
-  while ((jb + 1) * (jb + 2) / 2 <= bp) jb++;
-  const int ib = (int)(bp - jb * (jb + 1) / 2);
+__device__ __forceinline__ bool decode_pair(long long slot, int rank, int nb, int G, const int2* __restrict__ meta,
+                                            PairInfo& pi) {
+  int ib, jb;
+  if (!pair_from_slot(slot, nb, G, ib, jb)) return false;
   pi.ib = ib;
-  pi.jb = (int)jb;
+  pi.jb = jb;
   const int2 mi0 = meta[2 * ib], mi1 = meta[2 * ib + 1], mj0 = meta[2 * jb], mj1 = meta[2 * jb + 1];
-  const bool diag = ib == (int)jb;
+  const bool diag = ib == jb;
   const bool col_j = (mj0.y & kFlagCol) != 0, col_i = (mi0.y & kFlagCol) != 0;
   const bool rows_j = ((mj0.y | mj1.y) & kFlagRows) != 0;
   const int my = rank ? mi1.y : mi0.y;
@@ -421,7 +434,7 @@ __device__ __forceinline__ bool decode_pair(long long bp, int rank, const int2* 
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 rf_i8x2_kernel(const __grid_constant__ CUtensorMap tm, int nkb, const int* __restrict__ nbits,
-               const int2* __restrict__ tile_meta, long long n_pairs, int shard_index, int shard_count,
+               const int2* __restrict__ tile_meta, long long n_pairs, int nb, int G, int shard_index, int shard_count,
                unsigned long long* __restrict__ S, int C) {
   extern __shared__ __align__(1024) unsigned char smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -469,7 +482,7 @@ rf_i8x2_kernel(const __grid_constant__ CUtensorMap tm, int nkb, const int* __res
         const long long bp = k * shard_count + shard_index;
         if (bp >= n_pairs) break;
         PairInfo pi;
-        if (!decode_pair(bp, rank, tile_meta, pi)) continue;
+        if (!decode_pair(bp, rank, nb, G, tile_meta, pi)) continue;
         for (int kb = 0; kb < nkb; kb++) {
           mbar_wait(&empty[stage], phase ^ 1);
           unsigned char* st = smem + (size_t)stage * kStageBytes2;
@@ -492,7 +505,7 @@ rf_i8x2_kernel(const __grid_constant__ CUtensorMap tm, int nkb, const int* __res
         const long long bp = k * shard_count + shard_index;
         if (bp >= n_pairs) break;
         PairInfo pi;
-        if (!decode_pair(bp, rank, tile_meta, pi)) continue;
+        if (!decode_pair(bp, rank, nb, G, tile_meta, pi)) continue;
         mbar_wait(&tempty[acc], acc_phase ^ 1);  // both CTAs' epilogues have drained this accumulator
         tc_fence_after();
         const uint32_t tmem_c = tmem_base + (uint32_t)(acc * kAccCols);
@@ -529,7 +542,7 @@ rf_i8x2_kernel(const __grid_constant__ CUtensorMap tm, int nkb, const int* __res
       const long long bp = k * shard_count + shard_index;
       if (bp >= n_pairs) break;
       PairInfo pi;
-      if (!decode_pair(bp, rank, tile_meta, pi)) continue;
+      if (!decode_pair(bp, rank, nb, G, tile_meta, pi)) continue;
       const long long col0 = (long long)pi.jb * kTileN;
       const long long row = (long long)pi.ib * kBlockRows + rank * kTileRows + quad * 32 + lane;
       nb_s[buf * kTileN + et] = nbits[col0 + et] + 1;
@@ -679,9 +692,14 @@ int32_t rf_i8_sums(asm_ctx* ctx, asm_shard shard) {
   CUtensorMap tm;
   int32_t rc = make_tmap(ctx, &tm, ctx->opnd_i8.p, (uint64_t)L.Tp, Dp);
   if (rc != ASM_OK) return rc;
+  // supertile edge: 2G operand blocks (256 rows x Dp bytes each) should sit in about half of the 126 MB L2
+  const long long block_bytes = (long long)kBlockRows * (long long)Dp;
+  const int G = (int)std::max<long long>(1, std::min<long long>(32, (64LL << 20) / (2 * block_bytes)));
+  const long long nst = (nb + G - 1) / G;
+  const long long n_slots = nst * (nst + 1) / 2 * G * G;  // work slots incl. the invalid ones outside the triangle
+  const long long n_pairs = nb * (nb + 1) / 2;
   if (use_two_cta()) {
-    const long long n_pairs = nb * (nb + 1) / 2;  // 256x256 block pairs of the upper triangle, one per cluster step
-    L.tiles_total = n_pairs;
+    L.tiles_total = n_pairs;  // 256x256 block pairs of the upper triangle, one per cluster step
     L.tiles_done = (n_pairs - shard.shard_index + shard.shard_count - 1) / shard.shard_count;
     static bool attr = false;
     if (!attr) {
@@ -693,15 +711,14 @@ int32_t rf_i8_sums(asm_ctx* ctx, asm_shard shard) {
     {
       LaunchScope ls(ctx, ASM_K_RF_I8);
       rf_i8x2_kernel<<<2 * clusters, kThreads, kSmemBytes2, ctx->stream>>>(
-          tm, (int)(Dp / kBlockK), (const int*)ctx->nbits.p, (const int2*)ctx->blk_meta.p, n_pairs, shard.shard_index,
-          shard.shard_count, (unsigned long long*)ctx->S_pad.p, L.C);
+          tm, (int)(Dp / kBlockK), (const int*)ctx->nbits.p, (const int2*)ctx->blk_meta.p, n_slots, (int)nb, G,
+          shard.shard_index, shard.shard_count, (unsigned long long*)ctx->S_pad.p, L.C);
     }
     ASM_CUDA(ctx, cudaGetLastError());
     return ASM_OK;
   }
-  const long long n_tiles = nb * (nb + 1);  // two 128x256 tiles per block pair of the upper triangle
-  L.tiles_total = n_tiles;
-  L.tiles_done = (n_tiles - shard.shard_index + shard.shard_count - 1) / shard.shard_count;
+  L.tiles_total = 2 * n_pairs;  // two 128x256 tiles per block pair of the upper triangle
+  L.tiles_done = (2 * n_pairs - shard.shard_index + shard.shard_count - 1) / shard.shard_count;
   if ((rc = set_smem_attr<false>(ctx)) != ASM_OK) return rc;
   const int grid = (int)std::min<long long>(L.tiles_done, ctx->sm_count);
   if (grid <= 0) return ASM_OK;
@@ -709,7 +726,8 @@ int32_t rf_i8_sums(asm_ctx* ctx, asm_shard shard) {
     LaunchScope ls(ctx, ASM_K_RF_I8);
     rf_i8_kernel<false><<<grid, kThreads, kSmemBytes, ctx->stream>>>(
         tm, tm, (int)(Dp / kBlockK), (const int*)ctx->nbits.p, (const int*)ctx->nbits.p, (const int2*)ctx->blk_meta.p,
-        n_tiles, 0, shard.shard_index, shard.shard_count, (unsigned long long*)ctx->S_pad.p, L.C, nullptr, 0);
+        2 * n_slots, 0, (int)nb, G, shard.shard_index, shard.shard_count, (unsigned long long*)ctx->S_pad.p, L.C, nullptr,
+        0);
   }
   ASM_CUDA(ctx, cudaGetLastError());
   return ASM_OK;
@@ -751,7 +769,7 @@ int32_t rf_i8_block(asm_ctx* ctx, int32_t chainA, int64_t r0, int64_t r1, int32_
   {
     LaunchScope ls(ctx, ASM_K_RF_I8);
     rf_i8_kernel<true><<<(int)std::min<long long>(n_tiles, ctx->sm_count), kThreads, kSmemBytes, ctx->stream>>>(
-        tmA, tmB, (int)(Dp / kBlockK), nbA, nbB, nullptr, n_tiles, n_row_tiles, 0, 1, nullptr, 0, (uint16_t*)ctx->rf_out.p,
+        tmA, tmB, (int)(Dp / kBlockK), nbA, nbB, nullptr, n_tiles, n_row_tiles, 0, 1, 0, 1, nullptr, 0, (uint16_t*)ctx->rf_out.p,
         nc_pad);
   }
   ASM_CUDA(ctx, cudaGetLastError());

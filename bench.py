@@ -37,7 +37,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 CFG2 = dict(n_chains=4, n_trees=10000, n_taxa=100, beta=3.3, moves=2, start_seed=1, seed0=20240001)
-CFG5 = dict(n_chains=32, n_trees=50000, n_taxa=500, beta=4.3, moves=2, start_seed=1, seed0=20240100)
+CFG5 = dict(n_chains=32, n_trees=50000, n_taxa=500, beta=3.9, moves=2, start_seed=1, seed0=20240100)
 CFG3 = dict(n_traces=1000, n_samples=1_000_000, seed0=777)
 PHIS, MUS = [0.0, 0.5, 0.9, 0.99], [0.0, 1.0, -1e4]
 
@@ -324,7 +324,7 @@ def bench_psrf(args, rank, world, local, dist):
     # ---- kernel-only time for the roofline (CUDA events around the dominant kernel, same stream) ------
     ctx.profile_enable(True)
     ctx.profile_reset()
-    for _ in range(max(3, min(args.steps, 10))):
+    for _ in range(1 if args.workload == "cfg5" else max(3, min(args.steps, 10))):
         ctx.flush_l2()
         step_resident()
     fam = L.K_RF_I8 if method == L.ASM_RF_I8 else L.K_RF_POPC
@@ -359,14 +359,15 @@ def bench_psrf(args, rank, world, local, dist):
 
     # ---- e2e: host buffers through the C ABI, H2D + D2H inside the timed region ------------------------
     e2e_steps = []
-    for i in range(args.warmup + args.steps):
+    e2e_warm = 0 if args.workload == "cfg5" else args.warmup
+    for i in range(e2e_warm + (1 if args.workload == "cfg5" else args.steps)):
         ctx.flush_l2()
         barrier()
         t0 = time.perf_counter()
         upload()
         mean_e = step_resident()
         dt = (time.perf_counter() - t0) * 1e3
-        if i >= args.warmup:
+        if i >= e2e_warm:
             e2e_steps.append(dt)
     e_ms = float(np.mean(e2e_steps))
     if world > 1:
@@ -442,20 +443,39 @@ def bench_ess(args, rank, world, local, dist, n_traces=None):
         g = [torch.zeros(n_tr, dtype=torch.float64, device=f"cuda:{local}") for _ in range(world)]
         dist.all_gather(g, torch.from_numpy(ess).to(f"cuda:{local}"))  # ESS vector gather; min on host (Java NaN rules)
     value = world * n_tr * n / (ms * 1e-3)
-    ctx.profile_enable(True)
-    ctx.profile_reset()
-    ctx.ess_batch_device(dev.data_ptr(), n_tr, n, n)
-    k_ms, k_n = ctx.profile_get(L.K_ESS_LAG)
-    f_ms, _ = ctx.profile_get(L.K_ESS_FINISH)
-    ctx.profile_enable(False)
+
+    def profiled():
+        ctx.profile_enable(True)
+        ctx.profile_reset()
+        ctx.ess_batch_device(dev.data_ptr(), n_tr, n, n)
+        k, kn = ctx.profile_get(L.K_ESS_LAG)
+        f, _ = ctx.profile_get(L.K_ESS_FINISH)
+        ctx.profile_enable(False)
+        return k, f, ctx.ess_last_lag_count()
+
+    k_ms, f_ms, slots = profiled()          # as shipped: staged lag evaluation
+    ctx.ess_set_adaptive(False)
+    ctx.timer_mark(2)
+    act_full, ess_full = ctx.ess_batch_device(dev.data_ptr(), n_tr, n, n)
+    ctx.timer_mark(3)
+    full_step_ms = ctx.timer_elapsed_ms(2, 3)
+    kf_ms, ff_ms, slots_full = profiled()   # every lag of every trace (what the reference evaluates)
+    ctx.ess_set_adaptive(True)
     lmax = min(n, 2000)
-    flops = 2.0 * (lmax * n - lmax * (lmax - 1) / 2) * n_tr
+    flops_full = 2.0 * (lmax * n - lmax * (lmax - 1) / 2) * n_tr
+    flops = 2.0 * slots * n  # (trace, lag) chains evaluated x n mul+add pairs (upper bound: ignores the i < lag head)
     roof = {"bound": "hbm", "achieved": 8.0 * n_tr * n / (k_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
             "frac": 8.0 * n_tr * n / (k_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None, "kernel": "ess_lag_kernel",
             "kernel_ms": k_ms, "finish_ms": f_ms,
             "note": "FP64-pipe bound (~500 flop/byte), not HBM bound: see fp64",
             "fp64": {"achieved_tflops": flops / (k_ms * 1e-3) / 1e12, "unit": "TFLOP/s (separate DMUL+DADD, no FMA)",
-                     "algorithmic": "2*(L*n - L(L-1)/2) flop per trace, L = 2000"}}
+                     "lag_chains_evaluated": int(slots), "lag_chains_all": int(n_tr) * 2048,
+                     "algorithmic": "2 * n flop per evaluated (trace, lag) chain; staged evaluation stops a trace once the "
+                                    "integral loop of TraceESS.java:161-172 has stopped"},
+            "all_lags": {"step_ms": full_step_ms, "kernel_ms": kf_ms, "achieved_tflops": flops_full / (kf_ms * 1e-3) / 1e12,
+                         "value": world * n_tr * n / (full_step_ms * 1e-3),
+                         "bit_identical_to_staged": bool(np.array_equal(ess, ess_full, equal_nan=True)),
+                         "algorithmic": "2*(L*n - L(L-1)/2) flop per trace, L = 2000"}}
     e2e_ms = []
     for i in range(2):
         barrier()
@@ -500,9 +520,8 @@ def main():
     else:
         line, ctx = bench_psrf(args, rank, world, local, dist)
         if rank == 0 and world == 1:
-            if not args.no_cpu_baseline:
-                cfg = CFG5 if args.workload == "cfg5" else CFG2
-                line["cpu_baseline"] = cpu_baseline_psrf(cfg, cfg["n_trees"], sample_rows=args.cpu_rows)
+            if not args.no_cpu_baseline and args.workload != "cfg5":  # cfg5's CPU sample: tools/cfg5_check.py
+                line["cpu_baseline"] = cpu_baseline_psrf(CFG2, CFG2["n_trees"], sample_rows=args.cpu_rows)
             if not args.no_ess and args.workload == "psrf":
                 ctx.close()
                 ess_args = argparse.Namespace(**vars(args))

@@ -166,6 +166,11 @@ int64_t asm_launch_count(const asm_ctx* ctx);
 int32_t asm_sync(asm_ctx* ctx);
 /* Write `bytes` of a device scratch buffer (> L2) to evict the L2 between timed iterations. */
 int32_t asm_flush_l2(asm_ctx* ctx);
+/* Number of (trace, lag) chains the last ESS call evaluated: n_traces * 2048 when every lag is computed, fewer
+ * when the staged evaluation retired traces early (the integral loop of TraceESS.java:161-172 had stopped). */
+int64_t asm_ess_last_lag_count(const asm_ctx* ctx);
+/* on = 1 (default): staged lag evaluation; on = 0: every lag of every trace.  The results are bit-identical. */
+int32_t asm_ess_set_adaptive(asm_ctx* ctx, int32_t on);
 /* Layout facts of the last PSRF evaluation: padded row count, dictionary width in bits (padded),
  * tiles evaluated by this shard, tiles in the full problem. */
 int32_t asm_psrf_last_layout(const asm_ctx* ctx, int64_t* padded_rows, int64_t* padded_bits, int64_t* tiles_done,

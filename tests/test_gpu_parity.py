@@ -209,6 +209,26 @@ def test_ess_batch_bit_exact(gpu, n):
         assert bits_equal(act, lit)
 
 
+def test_ess_staged_equals_all_lags_and_wide_path(gpu):
+    """Staged (adaptive) lag evaluation must be bit-identical to evaluating every lag, on both thread shapes
+    (R = 4 for few open chains, R = 8 for many)."""
+    from asm_b200 import _lib as L
+    n_tr, n = 2200, 2600
+    x = np.empty((n_tr, n))
+    for j in range(n_tr):
+        L.synth_ar1(n, [0.0, -1e4][j % 2], [0.0, 0.9, 0.99, 0.999][j % 4], 4000 + j, out=x[j])
+    want_act, want_ess = O.ess_batch(x)
+    with gpu.GpuContext(1) as ctx:
+        act_a, ess_a = ctx.ess_batch(x)
+        slots_a = ctx.ess_last_lag_count()
+        ctx.ess_set_adaptive(False)
+        act_f, ess_f = ctx.ess_batch(x)
+        slots_f = ctx.ess_last_lag_count()
+    assert bits_equal(act_a, want_act) and bits_equal(ess_a, want_ess)
+    assert bits_equal(act_f, want_act) and bits_equal(ess_f, want_ess)
+    assert slots_f == n_tr * 2048 and n_tr * 256 <= slots_a < slots_f
+
+
 def test_ess_edge_cases(gpu):
     with gpu.GpuContext(1) as ctx:
         act, ess = ctx.ess_batch(np.full((2, 100), 3.25))  # constant trace: ac[0] = 0 -> NaN
