@@ -372,9 +372,10 @@ int32_t asm_ess_batch(asm_ctx* ctx, int32_t n_traces, int64_t n_samples, int64_t
   double* d_tr = (double*)ctx->ess_tr.p;
   // Chunked upload on the copy stream, each chunk evaluated as soon as it has landed: with page-locked host
   // memory the H2D copy of chunk k+1 runs underneath the kernels of chunk k.
-  const int64_t chunk_bytes = 256LL << 20;
-  int32_t chunk = (int32_t)std::max<int64_t>(1, std::min<int64_t>(n_traces, chunk_bytes / (n_pad * 8)));
-  if ((int64_t)n_traces * n_pad * 8 <= 2 * chunk_bytes) chunk = n_traces;
+  // Chunks must stay large: a stage of the lag kernel cannot finish faster than one warp streams one trace, so
+  // a small chunk leaves the SMs idle.  Four chunks when there are at least 512 traces and 1 GB, else one.
+  int32_t chunk = n_traces;
+  if (n_traces >= 512 && (int64_t)n_traces * n_pad * 8 >= (1LL << 30)) chunk = (n_traces + 3) / 4;
   const int n_chunks = (n_traces + chunk - 1) / chunk;
   std::vector<cudaEvent_t> ev((size_t)n_chunks, nullptr);
   for (int k = 0; k < n_chunks; k++) {

@@ -117,10 +117,16 @@ __global__ void __launch_bounds__(256) ess_lag_kernel(const double* __restrict__
     __syncthreads();
     const long long i_begin = c * kChunk;
     const long long i_end = min(i_begin + (long long)kChunk, nR);
+    // software pipeline: the loads of group g+1 are issued before the arithmetic of group g, so that a warp
+    // that has an SMSP almost to itself (few open traces) does not stall on shared-memory latency
+    double xi[R], wn[R], xi_n[R], wn_n[R];
+    load_block<R>(ring, (int)(i_begin & (kRing - 1)), xi);
+    load_block<R>(ring, (int)((i_begin - l0) & (kRing - 1)), wn);
+#pragma unroll 2
     for (long long i = i_begin; i < i_end; i += R) {
-      double xi[R], wn[R];
-      load_block<R>(ring, (int)(i & (kRing - 1)), xi);
-      load_block<R>(ring, (int)((i - l0) & (kRing - 1)), wn);
+      const long long in = (i + R < i_end) ? i + R : i;
+      load_block<R>(ring, (int)(in & (kRing - 1)), xi_n);
+      load_block<R>(ring, (int)((in - l0) & (kRing - 1)), wn_n);
 #pragma unroll
       for (int k = 0; k < R; k++) w[R - 1 + k] = wn[k];
       // w[k] = x[i - l0 - (R-1) + k]; lag l0+r pairs x[i+di] with x[i+di-l0-r] = w[R-1 + di - r]
@@ -130,6 +136,11 @@ __global__ void __launch_bounds__(256) ess_lag_kernel(const double* __restrict__
         for (int r = 0; r < R; r++) acc[r] = __dadd_rn(acc[r], __dmul_rn(w[R - 1 + di - r], xi[di]));
 #pragma unroll
       for (int k = 0; k < R - 1; k++) w[k] = w[k + R];
+#pragma unroll
+      for (int k = 0; k < R; k++) {
+        xi[k] = xi_n[k];
+        wn[k] = wn_n[k];
+      }
     }
   }
   if (l0 + R <= lags_stride) {
@@ -318,8 +329,11 @@ int32_t ess_batch_device(asm_ctx* ctx, int32_t n_traces, int64_t n_samples, int6
     if (s > 0 && b >= L) break;  // (stage 0 always runs its scan, also for n = 0)
     const int lags = e - b;
     if (n_samples > 0) {
-      // enough CTAs x warps to fill 148 SMs: narrow threads (R = 4) when few (trace, lag) chains are open
-      const bool wide = (long long)n_open * lags >= 512LL * 1024;
+      // Thread shape.  8 lags per thread (R = 8) halves the shared-memory traffic per flop and runs at the FP64
+      // issue rate; it needs at least one warp per SM sub-partition (4 x 148) to fill the machine.  With fewer
+      // open chains, 4 lags per thread doubles the number of warps.
+      const long long warps8 = (long long)n_open * std::max(1, lags / 256);
+      const bool wide = warps8 >= 4LL * ctx->sm_count;
       const int R = wide ? 8 : 4;
       const int nt = std::min(lags / R, wide ? 128 : 256);
       const int blocks_y = (lags + nt * R - 1) / (nt * R);

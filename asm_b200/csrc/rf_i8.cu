@@ -133,6 +133,14 @@ __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" :
 // 2G operand blocks a wave of CTAs touches stay resident in L2 (a plain column-major walk streams one
 // operand from HBM with no reuse: 55 TB at cfg5).  Slots that fall outside the triangle are invalid.
 __device__ __forceinline__ bool pair_from_slot(long long slot, int nb, int G, int& ib, int& jb) {
+  if (G == 0) {  // plain column-major walk of the triangle
+    long long j = (long long)((sqrt(8.0 * (double)slot + 1.0) - 1.0) * 0.5);
+    while (j * (j + 1) / 2 > slot) j--;
+    while ((j + 1) * (j + 2) / 2 <= slot) j++;
+    jb = (int)j;
+    ib = (int)(slot - j * (j + 1) / 2);
+    return jb < nb;
+  }
   const long long g2 = (long long)G * G;
   const long long st = slot / g2;
   const int local = (int)(slot - st * g2);
@@ -364,6 +372,12 @@ rf_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 // tcgen05.mma.cta_group::2 (M = 256); both CTAs' TMA loads signal the leader's `full` barrier; the
 // leader's commits are multicast to both CTAs' `empty` / `tmem_full` barriers; the peer's epilogue
 // warps arrive remotely on the leader's `tmem_empty` barrier.
+// Work distribution is dynamic: warp 3 of the leader draws the next block pair from a global counter and
+// publishes it through a 4-deep shared-memory queue to every role of both CTAs (remote store + remote
+// mbarrier arrive for the peer).  The pairs in flight across the GPU are therefore always ~74 consecutive
+// points of a Morton (Z-order) walk over the triangle, i.e. a compact 2-D patch: operand blocks are shared
+// through L2 by CTAs that use them at the same time (static striding let the clusters drift apart: ncu on
+// a cfg5-shaped run showed 49 % L2 hit rate and 5.9 TB/s of DRAM reads).
 // =====================================================================================================
 constexpr int kStages2 = 6;
 constexpr int kStageBytes2 = 2 * kABytes;  // A half + B half: 32 KB
@@ -414,10 +428,9 @@ struct PairInfo {
   int chain_rows, chain_cols;
 };
 
-__device__ __forceinline__ bool decode_pair(long long slot, int rank, int nb, int G, const int2* __restrict__ meta,
-                                            PairInfo& pi) {
-  int ib, jb;
-  if (!pair_from_slot(slot, nb, G, ib, jb)) return false;
+// Work flags of block pair (ib <= jb) for the CTA of rank `rank`; the return value (any work at all) is the
+// same in both CTAs of the pair.
+__device__ __forceinline__ bool pair_flags(int ib, int jb, int rank, const int2* __restrict__ meta, PairInfo& pi) {
   pi.ib = ib;
   pi.jb = jb;
   const int2 mi0 = meta[2 * ib], mi1 = meta[2 * ib + 1], mj0 = meta[2 * jb], mj1 = meta[2 * jb + 1];
@@ -429,13 +442,90 @@ __device__ __forceinline__ bool decode_pair(long long slot, int rank, int nb, in
   pi.do_col = !diag && col_i && rows_j;
   pi.chain_rows = mi0.x;
   pi.chain_cols = mj0.x;
-  return (((mi0.y | mi1.y) & kFlagRows) && col_j) || pi.do_col;  // identical in both CTAs of the pair
+  return (((mi0.y | mi1.y) & kFlagRows) && col_j) || pi.do_col;
 }
+
+// even bits of v, compacted (Morton decode)
+__device__ __forceinline__ uint32_t compact_bits(unsigned long long v) {
+  v &= 0x5555555555555555ULL;
+  v = (v | (v >> 1)) & 0x3333333333333333ULL;
+  v = (v | (v >> 2)) & 0x0F0F0F0F0F0F0F0FULL;
+  v = (v | (v >> 4)) & 0x00FF00FF00FF00FFULL;
+  v = (v | (v >> 8)) & 0x0000FFFF0000FFFFULL;
+  v = (v | (v >> 16)) & 0x00000000FFFFFFFFULL;
+  return (uint32_t)v;
+}
+
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (++spins > (1u << 28)) __trap();
+  }
+}
+__device__ __forceinline__ void mbar_arrive_rank(uint64_t* bar, uint32_t rank) {  // arrive on CTA `rank`'s copy of `bar`
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
+      "r"(rank)
+      : "memory");
+}
+__device__ __forceinline__ void st_int2_rank(int2* p, uint32_t rank, int a, int b) {  // store into CTA `rank`'s copy of *p
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "st.shared::cluster.v2.s32 [ra], {%2, %3};\n\t}" ::"r"(smem_u32(p)),
+      "r"(rank), "r"(a), "r"(b)
+      : "memory");
+}
+
+constexpr int kQ = 4;  // depth of the in-kernel work queue
+constexpr int kSchedConsumers = 2 + kEpiWarps + 1 + kEpiWarps;  // leader: TMA, MMA, 8 epilogue warps; peer: TMA, 8 epilogue warps
+constexpr size_t kAuxBytes2 = 256 /*barriers, tmem ptr, work queue*/ + 2 * kTileN * 4 + 4 * kTileN * 4;
+constexpr size_t kSmemBytes2x = (size_t)kStages2 * kStageBytes2 + kAuxBytes2;
+
+// A role's view of the work queue: wait for entry q, read it, hand the entry back to the scheduler.
+struct WorkQueue {
+  uint64_t* sfull;
+  uint64_t* sempty;
+  const int2* slots;
+  int q = 0;
+  uint32_t ph = 0;
+  int rank;
+  // whole-warp call (every lane returns the entry; lane 0 releases it) or single-thread call (`solo`)
+  __device__ __forceinline__ int2 next(bool solo) {
+    mbar_wait_cluster(&sfull[q], ph);
+    const int2 e = slots[q];
+    if (!solo) __syncwarp();
+    if (solo || (threadIdx.x & 31) == 0) {
+      if (rank == 0)
+        mbar_arrive(&sempty[q]);
+      else
+        mbar_arrive_rank(&sempty[q], 0);
+    }
+    if (++q == kQ) {
+      q = 0;
+      ph ^= 1;
+    }
+    return e;
+  }
+};
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 rf_i8x2_kernel(const __grid_constant__ CUtensorMap tm, int nkb, const int* __restrict__ nbits,
-               const int2* __restrict__ tile_meta, long long n_pairs, int nb, int G, int shard_index, int shard_count,
-               unsigned long long* __restrict__ S, int C) {
+               const int2* __restrict__ tile_meta, long long n_slots, int nb, int shard_index, int shard_count,
+               unsigned long long* __restrict__ slot_counter, unsigned long long* __restrict__ S, int C) {
   extern __shared__ __align__(1024) unsigned char smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   unsigned char* aux = smem + (size_t)kStages2 * kStageBytes2;
@@ -443,9 +533,12 @@ rf_i8x2_kernel(const __grid_constant__ CUtensorMap tm, int nkb, const int* __res
   uint64_t* empty = full + kStages2;                  // [kStages2]   (each CTA)
   uint64_t* tfull = empty + kStages2;                 // [2]          (each CTA)
   uint64_t* tempty = tfull + 2;                       // [2]          (used in CTA 0)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
-  int* nb_s = reinterpret_cast<int*>(aux + 192);
-  uint32_t* colpart = reinterpret_cast<uint32_t*>(aux + 192 + 2 * kTileN * 4);
+  uint64_t* sfull = tempty + 2;                       // [kQ]         (each CTA)
+  uint64_t* sempty = sfull + kQ;                      // [kQ]         (used in CTA 0)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sempty + kQ);
+  int2* slots = reinterpret_cast<int2*>(aux + 208);   // [kQ] work queue entries {ib, jb}, {-1,-1} = stop
+  int* nb_s = reinterpret_cast<int*>(aux + 256);
+  uint32_t* colpart = reinterpret_cast<uint32_t*>(aux + 256 + 2 * kTileN * 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = (int)cluster_ctarank();
@@ -459,6 +552,10 @@ rf_i8x2_kernel(const __grid_constant__ CUtensorMap tm, int nkb, const int* __res
       mbar_init(&tfull[a], 1);
       mbar_init(&tempty[a], 2 * kEpiWarps);
     }
+    for (int q = 0; q < kQ; q++) {
+      mbar_init(&sfull[q], 1);
+      mbar_init(&sempty[q], kSchedConsumers);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   cluster_sync_all();  // the peer's barriers exist before anything can arrive on them
@@ -471,24 +568,56 @@ rf_i8x2_kernel(const __grid_constant__ CUtensorMap tm, int nkb, const int* __res
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  const long long first = blockIdx.x >> 1, stride = gridDim.x >> 1;
+  WorkQueue wq;
+  wq.sfull = sfull;
+  wq.sempty = sempty;
+  wq.slots = slots;
+  wq.rank = rank;
 
-  if (warp == 0) {
+  if (warp == 3) {
+    // ===== scheduler (leader CTA): draws the next block pair of the Morton walk for the whole cluster =====
+    if (rank == 0 && lane == 0) {
+      int q = 0;
+      uint32_t ph = 0;
+      for (;;) {
+        mbar_wait_cluster(&sempty[q], ph ^ 1);
+        int ib = -1, jb = -1;
+        for (;;) {
+          const long long t = (long long)atomicAdd(slot_counter, 1ULL) * shard_count + shard_index;
+          if (t >= n_slots) {
+            ib = jb = -1;
+            break;
+          }
+          ib = (int)compact_bits((unsigned long long)t);
+          jb = (int)compact_bits((unsigned long long)t >> 1);
+          PairInfo tmp;
+          if (ib <= jb && jb < nb && pair_flags(ib, jb, 0, tile_meta, tmp)) break;
+        }
+        slots[q] = make_int2(ib, jb);
+        st_int2_rank(&slots[q], 1, ib, jb);
+        mbar_arrive_rank(&sfull[q], 0);
+        mbar_arrive_rank(&sfull[q], 1);
+        if (ib < 0) break;
+        if (++q == kQ) {
+          q = 0;
+          ph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 0) {
     // ===== TMA producer (both CTAs; completion bytes go to CTA 0's full barrier) =====
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (long long k = first;; k += stride) {
-        const long long bp = k * shard_count + shard_index;
-        if (bp >= n_pairs) break;
-        PairInfo pi;
-        if (!decode_pair(bp, rank, nb, G, tile_meta, pi)) continue;
+      for (;;) {
+        const int2 e = wq.next(true);
+        if (e.x < 0) break;
         for (int kb = 0; kb < nkb; kb++) {
           mbar_wait(&empty[stage], phase ^ 1);
           unsigned char* st = smem + (size_t)stage * kStageBytes2;
           if (rank == 0) mbar_expect_tx(&full[stage], 2 * kStageBytes2);  // bytes of both CTAs
-          tma_load_2d_2sm(st, &tm, kb * kBlockK, pi.ib * kBlockRows + rank * kTileRows, &full[stage]);
-          tma_load_2d_2sm(st + kABytes, &tm, kb * kBlockK, pi.jb * kBlockRows + rank * kTileRows, &full[stage]);
+          tma_load_2d_2sm(st, &tm, kb * kBlockK, e.x * kBlockRows + rank * kTileRows, &full[stage]);
+          tma_load_2d_2sm(st + kABytes, &tm, kb * kBlockK, e.y * kBlockRows + rank * kTileRows, &full[stage]);
           if (++stage == kStages2) {
             stage = 0;
             phase ^= 1;
@@ -501,12 +630,10 @@ rf_i8x2_kernel(const __grid_constant__ CUtensorMap tm, int nkb, const int* __res
     if (rank == 0 && lane == 0) {
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (long long k = first;; k += stride) {
-        const long long bp = k * shard_count + shard_index;
-        if (bp >= n_pairs) break;
-        PairInfo pi;
-        if (!decode_pair(bp, rank, nb, G, tile_meta, pi)) continue;
-        mbar_wait(&tempty[acc], acc_phase ^ 1);  // both CTAs' epilogues have drained this accumulator
+      for (;;) {
+        const int2 e = wq.next(true);
+        if (e.x < 0) break;
+        mbar_wait_cluster(&tempty[acc], acc_phase ^ 1);  // both CTAs' epilogues have drained this accumulator
         tc_fence_after();
         const uint32_t tmem_c = tmem_base + (uint32_t)(acc * kAccCols);
         for (int kb = 0; kb < nkb; kb++) {
@@ -538,11 +665,11 @@ rf_i8x2_kernel(const __grid_constant__ CUtensorMap tm, int nkb, const int* __res
     const int et = threadIdx.x - 128;
     int acc = 0, buf = 0;
     uint32_t acc_phase = 0;
-    for (long long k = first;; k += stride) {
-      const long long bp = k * shard_count + shard_index;
-      if (bp >= n_pairs) break;
+    for (;;) {
+      const int2 e = wq.next(false);
+      if (e.x < 0) break;
       PairInfo pi;
-      if (!decode_pair(bp, rank, nb, G, tile_meta, pi)) continue;
+      pair_flags(e.x, e.y, rank, tile_meta, pi);
       const long long col0 = (long long)pi.jb * kTileN;
       const long long row = (long long)pi.ib * kBlockRows + rank * kTileRows + quad * 32 + lane;
       nb_s[buf * kTileN + et] = nbits[col0 + et] + 1;
@@ -561,18 +688,18 @@ rf_i8x2_kernel(const __grid_constant__ CUtensorMap tm, int nkb, const int* __res
         if (pi.do_col) {
 #pragma unroll
           for (int j = 0; j < 32; j++) {
-            const uint32_t e = (uint32_t)(na + nb[j] - 2 * (int)r[j]);
-            const uint32_t v = e * e;
+            const uint32_t e2 = (uint32_t)(na + nb[j] - 2 * (int)r[j]);
+            const uint32_t v = e2 * e2;
             chunk += v;
-            const uint32_t s = __reduce_add_sync(0xffffffffu, v);
-            if (lane == j) mycol = s;
+            const uint32_t sred = __reduce_add_sync(0xffffffffu, v);
+            if (lane == j) mycol = sred;
           }
           colpart[quad * kTileN + half * 128 + cc * 32 + lane] = mycol;
         } else {
 #pragma unroll
           for (int j = 0; j < 32; j++) {
-            const uint32_t e = (uint32_t)(na + nb[j] - 2 * (int)r[j]);
-            chunk += e * e;
+            const uint32_t e2 = (uint32_t)(na + nb[j] - 2 * (int)r[j]);
+            chunk += e2 * e2;
           }
         }
         row_sum += chunk;
@@ -583,7 +710,7 @@ rf_i8x2_kernel(const __grid_constant__ CUtensorMap tm, int nkb, const int* __res
         if (rank == 0)
           mbar_arrive(&tempty[acc]);
         else
-          mbar_arrive_cta0(&tempty[acc]);
+          mbar_arrive_rank(&tempty[acc], 0);
       }
       if (pi.do_row) atomicAdd(&S[(size_t)row * C + pi.chain_cols], row_sum);
       if (pi.do_col) {
@@ -692,27 +819,36 @@ int32_t rf_i8_sums(asm_ctx* ctx, asm_shard shard) {
   CUtensorMap tm;
   int32_t rc = make_tmap(ctx, &tm, ctx->opnd_i8.p, (uint64_t)L.Tp, Dp);
   if (rc != ASM_OK) return rc;
-  // supertile edge: 2G operand blocks (256 rows x Dp bytes each) should sit in about half of the 126 MB L2
-  const long long block_bytes = (long long)kBlockRows * (long long)Dp;
-  const int G = (int)std::max<long long>(1, std::min<long long>(32, (64LL << 20) / (2 * block_bytes)));
-  const long long nst = (nb + G - 1) / G;
-  const long long n_slots = nst * (nst + 1) / 2 * G * G;  // work slots incl. the invalid ones outside the triangle
+  // Supertile edge.  Measured (tools/psrf_probe.py, profiles/): G = 2..8 is best at every size (T = 40k: 1.47 ms vs
+  // 1.46 column-major; T = 400k, D = 5116: 228 ms vs 285 ms); larger G loses more to the idle slots of the
+  // diagonal supertiles than it gains in L2 reuse.
+  int G = 4;
+  if (const char* e = getenv("ASM_I8_SUPERTILE")) G = atoi(e);  // 0 = plain column-major walk (tuning knob)
   const long long n_pairs = nb * (nb + 1) / 2;
+  const long long nst = G > 0 ? (nb + G - 1) / G : 0;
+  const long long n_slots = G > 0 ? nst * (nst + 1) / 2 * G * G : n_pairs;  // incl. invalid slots outside the triangle
   if (use_two_cta()) {
-    L.tiles_total = n_pairs;  // 256x256 block pairs of the upper triangle, one per cluster step
+    L.tiles_total = n_pairs;  // 256x256 block pairs of the upper triangle
     L.tiles_done = (n_pairs - shard.shard_index + shard.shard_count - 1) / shard.shard_count;
     static bool attr = false;
     if (!attr) {
-      ASM_CUDA(ctx, cudaFuncSetAttribute(rf_i8x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes2));
+      ASM_CUDA(ctx, cudaFuncSetAttribute(rf_i8x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes2x));
       attr = true;
     }
+    // Morton walk over the P x P square that covers the triangle, P = next power of two >= nb
+    long long P = 1;
+    while (P < nb) P <<= 1;
+    const long long n_morton = P * P;
+    if ((rc = asm_reserve(ctx, ctx->tile_counter, sizeof(unsigned long long))) != ASM_OK) return rc;
+    ASM_CUDA(ctx, cudaMemsetAsync(ctx->tile_counter.p, 0, sizeof(unsigned long long), ctx->stream));
     const int clusters = (int)std::min<long long>(L.tiles_done, ctx->sm_count / 2);
     if (clusters <= 0) return ASM_OK;
     {
       LaunchScope ls(ctx, ASM_K_RF_I8);
-      rf_i8x2_kernel<<<2 * clusters, kThreads, kSmemBytes2, ctx->stream>>>(
-          tm, (int)(Dp / kBlockK), (const int*)ctx->nbits.p, (const int2*)ctx->blk_meta.p, n_slots, (int)nb, G,
-          shard.shard_index, shard.shard_count, (unsigned long long*)ctx->S_pad.p, L.C);
+      rf_i8x2_kernel<<<2 * clusters, kThreads, kSmemBytes2x, ctx->stream>>>(
+          tm, (int)(Dp / kBlockK), (const int*)ctx->nbits.p, (const int2*)ctx->blk_meta.p, n_morton, (int)nb,
+          shard.shard_index, shard.shard_count, (unsigned long long*)ctx->tile_counter.p,
+          (unsigned long long*)ctx->S_pad.p, L.C);
     }
     ASM_CUDA(ctx, cudaGetLastError());
     return ASM_OK;
