@@ -20,7 +20,7 @@
 //
 // Staged evaluation: the integral of TraceESS.java:161-172 stops at the first even lag whose pair sum
 // autoCorrelation[lag-1] + autoCorrelation[lag] is not positive, so lags beyond that point cannot change
-// the result.  Lags are therefore evaluated in stages [0,256), [256,1024), [1024,2048); after each stage
+// the result.  Lags are therefore evaluated in stages [0,256), [256,768), [768,1792), [1792,2048); after each stage
 // K6 ess_scan_kernel advances every still-open trace's integral and retires the traces whose loop has
 // stopped (or has reached min(n, 2000) lags).  The output is bit-identical to evaluating all lags
 // (asm_ess_set_adaptive(ctx, 0) / ASM_ESS_ADAPTIVE=0 does exactly that, in one stage).
@@ -34,7 +34,7 @@
 namespace {
 
 constexpr int kChunk = 512;  // samples per cp.async group
-constexpr int kRing = 4096;  // ring size in samples (>= max lag + 8 + 2*kChunk)
+constexpr int kRingMax = 4096;  // ring size in samples must be >= max lag of the CTA + 8 + 2*kChunk
 
 // logical ring index -> physical: 64-byte blocks, the four 16-byte sub-blocks XOR-swizzled
 __device__ __forceinline__ int ring_phys(int e) {
@@ -55,8 +55,8 @@ __device__ __forceinline__ void cp_async_wait() {
 
 // read the aligned R-sample block that starts at logical index e0 (multiple of R), R = 4 or 8
 template <int R>
-__device__ __forceinline__ void load_block(const double* ring, int e0, double (&v)[R]) {
-  const int e = e0 & (kRing - 1);
+__device__ __forceinline__ void load_block(const double* ring, int mask, int e0, double (&v)[R]) {
+  const int e = e0 & mask;
   const int g = e >> 3;
   const int sw = (g >> 1) & 3;
   const int first = (R == 8) ? 0 : ((e >> 2) & 1) * 2;  // first 16-byte sub-block of the group
@@ -69,19 +69,33 @@ __device__ __forceinline__ void load_block(const double* ring, int e0, double (&
   }
 }
 
-// grid: x = trace (index into trace_ids if given), y = lag block of this stage
+// A CTA is always 4 (or 8) warps so that all four SM sub-partitions issue FP64 work; it is cut into groups of
+// `gthreads` threads, one group = gthreads*R consecutive lags of one trace with its own ring in shared memory.
+// grid: x = ceil(n_open / groups per CTA), y = lag block of this stage.
 template <int R>
 __global__ void __launch_bounds__(256) ess_lag_kernel(const double* __restrict__ traces, long long stride, long long n,
-                                                      int lag_begin, const int* __restrict__ trace_ids, int lags_stride,
-                                                      double* __restrict__ sls) {
-  __shared__ __align__(16) double ring[kRing];
-  const int tid = threadIdx.x, NT = blockDim.x;
-  const long long trace = trace_ids ? trace_ids[blockIdx.x] : blockIdx.x;
+                                                      int lag_begin, const int* __restrict__ trace_ids, int n_open,
+                                                      int lags_stride, double* __restrict__ sls, int gthreads,
+                                                      int ring_size) {
+  extern __shared__ __align__(16) double ring_all[];
+  const int group = threadIdx.x / gthreads, tid = threadIdx.x - group * gthreads, NT = gthreads;
+  const int groups = blockDim.x / gthreads;
+  const int idx = blockIdx.x * groups + group;
+  if (idx >= n_open) return;  // whole group idle; groups synchronise among themselves only
+  double* ring = ring_all + (size_t)group * ring_size;
+  const int mask = ring_size - 1;
+  const long long trace = trace_ids ? trace_ids[idx] : idx;
   const double* __restrict__ x = traces + trace * stride;
   const int l0 = lag_begin + (int)blockIdx.y * NT * R + tid * R;
+  auto group_sync = [&]() {
+    if (NT == 32)
+      __syncwarp();
+    else
+      asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(NT) : "memory");
+  };
 
-  for (int e = tid; e < kRing; e += NT) ring[e] = 0.0;  // x[i] = 0 for i < 0
-  __syncthreads();
+  for (int e = tid; e < ring_size; e += NT) ring[e] = 0.0;  // x[i] = 0 for i < 0
+  group_sync();
 
   const long long nR = (n + R - 1) / R * R;
   const long long n_chunks = (nR + kChunk - 1) / kChunk;
@@ -90,7 +104,7 @@ __global__ void __launch_bounds__(256) ess_lag_kernel(const double* __restrict__
     const long long base = c * kChunk;
     for (int e = tid; e < kChunk; e += NT) {
       const long long i = base + e;
-      double* dst = ring + ring_phys((int)(i & (kRing - 1)));
+      double* dst = ring + ring_phys((int)(i & mask));
       if (i < n)
         cp_async8(dst, x + i);
       else
@@ -114,19 +128,19 @@ __global__ void __launch_bounds__(256) ess_lag_kernel(const double* __restrict__
     } else {
       cp_async_wait<0>();
     }
-    __syncthreads();
+    group_sync();
     const long long i_begin = c * kChunk;
     const long long i_end = min(i_begin + (long long)kChunk, nR);
     // software pipeline: the loads of group g+1 are issued before the arithmetic of group g, so that a warp
-    // that has an SMSP almost to itself (few open traces) does not stall on shared-memory latency
+    // that has an SM sub-partition almost to itself does not stall on shared-memory latency
     double xi[R], wn[R], xi_n[R], wn_n[R];
-    load_block<R>(ring, (int)(i_begin & (kRing - 1)), xi);
-    load_block<R>(ring, (int)((i_begin - l0) & (kRing - 1)), wn);
+    load_block<R>(ring, mask, (int)(i_begin & mask), xi);
+    load_block<R>(ring, mask, (int)((i_begin - l0) & mask), wn);
 #pragma unroll 2
     for (long long i = i_begin; i < i_end; i += R) {
       const long long in = (i + R < i_end) ? i + R : i;
-      load_block<R>(ring, (int)(in & (kRing - 1)), xi_n);
-      load_block<R>(ring, (int)((in - l0) & (kRing - 1)), wn_n);
+      load_block<R>(ring, mask, (int)(in & mask), xi_n);
+      load_block<R>(ring, mask, (int)((in - l0) & mask), wn_n);
 #pragma unroll
       for (int k = 0; k < R; k++) w[R - 1 + k] = wn[k];
       // w[k] = x[i - l0 - (R-1) + k]; lag l0+r pairs x[i+di] with x[i+di-l0-r] = w[R-1 + di - r]
@@ -314,10 +328,16 @@ int32_t ess_batch_device(asm_ctx* ctx, int32_t n_traces, int64_t n_samples, int6
                                                                                               n_traces, d_sums);
   ASM_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));
 
-  int bounds[4];
+  static bool attr_set = false;
+  if (!attr_set) {
+    ASM_CUDA(ctx, cudaFuncSetAttribute(ess_lag_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kRingMax * 8));
+    ASM_CUDA(ctx, cudaFuncSetAttribute(ess_lag_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kRingMax * 8));
+    attr_set = true;
+  }
+  int bounds[5];
   int n_stage;
   if (ctx->ess_adaptive) {
-    bounds[0] = 0, bounds[1] = 256, bounds[2] = 1024, bounds[3] = 2048, n_stage = 3;
+    bounds[0] = 0, bounds[1] = 256, bounds[2] = 768, bounds[3] = 1792, bounds[4] = 2048, n_stage = 4;
   } else {
     bounds[0] = 0, bounds[1] = 2048, n_stage = 1;
   }
@@ -331,20 +351,22 @@ int32_t ess_batch_device(asm_ctx* ctx, int32_t n_traces, int64_t n_samples, int6
     if (n_samples > 0) {
       // Thread shape.  8 lags per thread (R = 8) halves the shared-memory traffic per flop and runs at the FP64
       // issue rate; it needs at least one warp per SM sub-partition (4 x 148) to fill the machine.  With fewer
-      // open chains, 4 lags per thread doubles the number of warps.
-      const long long warps8 = (long long)n_open * std::max(1, lags / 256);
-      const bool wide = warps8 >= 4LL * ctx->sm_count;
-      const int R = wide ? 8 : 4;
-      const int nt = std::min(lags / R, wide ? 128 : 256);
-      const int blocks_y = (lags + nt * R - 1) / (nt * R);
-      dim3 grid((unsigned)n_open, (unsigned)blocks_y);
+      // open chains, 4 lags per thread doubles the number of warps.  A CTA always has a multiple of 4 warps.
+      const long long warps8 = (long long)n_open * (lags / 256);
+      const int R = (warps8 >= 4LL * ctx->sm_count) ? 8 : 4;
+      const int gthreads = std::min(lags / R, R == 8 ? 128 : 256);  // threads of one (trace, lag block) group
+      const int blocks_y = lags / (gthreads * R);
+      const int groups = std::max(1, 128 / gthreads);               // traces per CTA
+      const int ring = (e + R + 2 * kChunk <= 2048) ? 2048 : kRingMax;
+      const size_t smem = (size_t)groups * ring * sizeof(double);
+      dim3 grid((unsigned)((n_open + groups - 1) / groups), (unsigned)blocks_y);
       LaunchScope ls(ctx, ASM_K_ESS_LAG);
       if (R == 8)
-        ess_lag_kernel<8><<<grid, nt, 0, ctx->stream>>>(d_traces, stride, n_samples, b, ids_in, lags_stride,
-                                                        (double*)ctx->ess_sls.p);
+        ess_lag_kernel<8><<<grid, groups * gthreads, smem, ctx->stream>>>(d_traces, stride, n_samples, b, ids_in, n_open,
+                                                                          lags_stride, (double*)ctx->ess_sls.p, gthreads, ring);
       else
-        ess_lag_kernel<4><<<grid, nt, 0, ctx->stream>>>(d_traces, stride, n_samples, b, ids_in, lags_stride,
-                                                        (double*)ctx->ess_sls.p);
+        ess_lag_kernel<4><<<grid, groups * gthreads, smem, ctx->stream>>>(d_traces, stride, n_samples, b, ids_in, n_open,
+                                                                          lags_stride, (double*)ctx->ess_sls.p, gthreads, ring);
       ctx->ess_lag_slots += (long long)n_open * lags;
     }
     ASM_CUDA(ctx, cudaGetLastError());
