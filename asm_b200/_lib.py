@@ -54,6 +54,7 @@ SIGNATURES = {
     "asm_traces_append": (_i32, [_p, _i32, _i32, _i64, _p]),
     "asm_traces_count": (_i32, [_p, _i32, _i64p, _i32p]),
     "asm_ess_eval": (_i32, [_p, _p, _i32, _p, _i32, _p]),
+    "asm_trace_moments": (_i32, [_p, _i32, _p, _p]),
     "asm_timer_mark": (_i32, [_p, _i32]),
     "asm_timer_elapsed_ms": (_i32, [_p, _i32, _i32, C.POINTER(C.c_float)]),
     "asm_profile_enable": (_i32, [_p, _i32]),
@@ -328,6 +329,13 @@ class GpuContext:
         out = np.empty(cc.shape[0], dtype=np.float64)
         self._check(lib().asm_ess_eval(self._h, _ptr(b), end, _ptr(cc), cc.shape[0], _ptr(out)))
         return out
+
+    def trace_moments(self, end: int):
+        _, n_cols = self.traces_count(0)
+        s = np.empty((self.n_chains, n_cols), dtype=np.float64)
+        q = np.empty((self.n_chains, n_cols), dtype=np.float64)
+        self._check(lib().asm_trace_moments(self._h, end, _ptr(s), _ptr(q)))
+        return s, q
 
     # ---- measurement
     def timer_mark(self, slot: int):

@@ -31,6 +31,9 @@ HOST_SIGNATURES = {
     "asmh_tree_psrf_create": (_i32, [C.POINTER(_p), _f64, _i32, _i32, _i32, _f64, _i32, _i32, _i32]),
     "asmh_tree_ess_create": (_i32, [C.POINTER(_p), _i32, _f64, _i32, _i32, _i32]),
     "asmh_trace_ess_create": (_i32, [C.POINTER(_p), _i32, C.c_char_p]),
+    "asmh_gelman_rubin_create": (_i32, [C.POINTER(_p), _f64]),
+    "asmh_clade_difference_create": (_i32, [C.POINTER(_p), _f64]),
+    "asmh_criterion_last_value": (_i32, [_p, C.POINTER(_f64)]),
     "asmh_criterion_destroy": (_i32, [_p]),
     "asmh_criterion_setup": (_i32, [_p, _i32, _p]),
     "asmh_criterion_converged": (_i32, [_p, _p, _i32, _i32p]),
@@ -203,3 +206,31 @@ class TraceESS(_Criterion):
 
     currentESSs = property(lambda self: self._cur()[0])
     minESS = property(lambda self: self._cur()[1])
+
+
+class GelmanRubin(_Criterion):
+    """asm.inference.GelmanRubin.  Input: threshold (GelmanRubin.java:14)."""
+
+    def __init__(self, threshold=1.05):
+        self._c = C.c_void_p()
+        _check(_h().asmh_gelman_rubin_create(C.byref(self._c), threshold))
+
+    @property
+    def lastValue(self) -> float:
+        v = C.c_double()
+        _check(_h().asmh_criterion_last_value(self._c, C.byref(v)))
+        return v.value
+
+
+class CladeDifference(_Criterion):
+    """asm.inference.CladeDifference.  Input: threshold (CladeDifference.java:16)."""
+
+    def __init__(self, threshold=0.25):
+        self._c = C.c_void_p()
+        _check(_h().asmh_clade_difference_create(C.byref(self._c), threshold))
+
+    @property
+    def lastValue(self) -> float:
+        v = C.c_double()
+        _check(_h().asmh_criterion_last_value(self._c, C.byref(v)))
+        return v.value

@@ -66,6 +66,9 @@ struct asm_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;  // side stream (ESS sum chain)
   cudaStream_t stream_copy = nullptr;  // H2D copies overlapped with compute (asm_ess_batch)
+  cudaStream_t group_stream[4] = {}, group_stream2[4] = {};   // ESS chunk groups
+  cudaEvent_t group_event[4] = {}, group_fork[4] = {}, group_join[4] = {};
+  void* h_pinned = nullptr;            // small page-locked scratch for asynchronous counters
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int32_t words = 0;  // stored row width of every chain (uint64 words)
   std::vector<ChainTrees> trees;
@@ -102,7 +105,8 @@ int32_t asm_reserve(asm_ctx* ctx, DevBuf& b, size_t bytes);
 struct LaunchScope {
   asm_ctx* ctx;
   int family;
-  LaunchScope(asm_ctx* c, int f);
+  cudaStream_t st;
+  LaunchScope(asm_ctx* c, int f, cudaStream_t s = nullptr);
   ~LaunchScope();
 };
 
@@ -124,8 +128,12 @@ int32_t rf_i8_block(asm_ctx* ctx, int32_t chainA, int64_t r0, int64_t r1, int32_
                     uint16_t* out_host);
 // clade.cu
 int32_t clade_counts(asm_ctx* ctx, int32_t chain, int64_t from, int64_t to, int32_t* out_host);
+// moments.cu
+int32_t trace_moments(asm_ctx* ctx, int32_t end, double* sums_host, double* sumsq_host);
 // ess.cu
 int32_t ess_batch_device(asm_ctx* ctx, int32_t n_traces, int64_t n_samples, int64_t stride, const double* d_traces,
                          int32_t max_lag, double* act_out_host, double* ess_out_host);
+int32_t ess_batch_host(asm_ctx* ctx, int32_t n_traces, int64_t n_samples, int64_t stride, const double* traces,
+                       int64_t n_pad, double* d_tr, int32_t max_lag, double* act_out_host, double* ess_out_host);
 int32_t ess_eval_stream(asm_ctx* ctx, const int32_t* burnin, int32_t end, const int32_t* cols, int32_t n_cols,
                         double* ess_out_host);

@@ -42,13 +42,13 @@ int32_t asm_reserve(asm_ctx* ctx, DevBuf& b, size_t bytes) {
   return ASM_OK;
 }
 
-LaunchScope::LaunchScope(asm_ctx* c, int f) : ctx(c), family(f) {
+LaunchScope::LaunchScope(asm_ctx* c, int f, cudaStream_t s) : ctx(c), family(f), st(s ? s : c->stream) {
   ctx->launches++;
-  if (ctx->profile) cudaEventRecord(ctx->pe0, ctx->stream);
+  if (ctx->profile) cudaEventRecord(ctx->pe0, st);
 }
 LaunchScope::~LaunchScope() {
   if (ctx->profile) {
-    cudaEventRecord(ctx->pe1, ctx->stream);
+    cudaEventRecord(ctx->pe1, st);
     cudaEventSynchronize(ctx->pe1);
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ctx->pe0, ctx->pe1);
@@ -199,6 +199,13 @@ int32_t asm_create(asm_ctx** out, int32_t device, int32_t n_chains) {
   }
   cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&ctx->stream_copy, cudaStreamNonBlocking);
+  for (int k = 0; k < 4; k++) {
+    cudaStreamCreateWithFlags(&ctx->group_stream[k], cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&ctx->group_stream2[k], cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->group_event[k], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->group_fork[k], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->group_join[k], cudaEventDisableTiming);
+  }
   cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
   for (auto& ev : ctx->timer) cudaEventCreate(&ev);
@@ -229,6 +236,14 @@ int32_t asm_destroy(asm_ctx* ctx) {
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->stream_copy) cudaStreamDestroy(ctx->stream_copy);
+  for (int k = 0; k < 4; k++) {
+    if (ctx->group_stream[k]) cudaStreamDestroy(ctx->group_stream[k]);
+    if (ctx->group_stream2[k]) cudaStreamDestroy(ctx->group_stream2[k]);
+    if (ctx->group_event[k]) cudaEventDestroy(ctx->group_event[k]);
+    if (ctx->group_fork[k]) cudaEventDestroy(ctx->group_fork[k]);
+    if (ctx->group_join[k]) cudaEventDestroy(ctx->group_join[k]);
+  }
+  if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return ASM_OK;
@@ -369,37 +384,7 @@ int32_t asm_ess_batch(asm_ctx* ctx, int32_t n_traces, int64_t n_samples, int64_t
   if (n_pad == 0) n_pad = 2;
   int32_t rc = asm_reserve(ctx, ctx->ess_tr, sizeof(double) * (size_t)n_traces * (size_t)n_pad);
   if (rc != ASM_OK) return rc;
-  double* d_tr = (double*)ctx->ess_tr.p;
-  // Chunked upload on the copy stream, each chunk evaluated as soon as it has landed: with page-locked host
-  // memory the H2D copy of chunk k+1 runs underneath the kernels of chunk k.
-  // Chunks must stay large: a stage of the lag kernel cannot finish faster than one warp streams one trace, so
-  // a small chunk leaves the SMs idle.  Four chunks when there are at least 512 traces and 1 GB, else one.
-  int32_t chunk = n_traces;
-  if (n_traces >= 512 && (int64_t)n_traces * n_pad * 8 >= (1LL << 30)) chunk = (n_traces + 3) / 4;
-  const int n_chunks = (n_traces + chunk - 1) / chunk;
-  std::vector<cudaEvent_t> ev((size_t)n_chunks, nullptr);
-  for (int k = 0; k < n_chunks; k++) {
-    const int32_t t0 = k * chunk, nt = std::min(chunk, n_traces - t0);
-    ASM_CUDA(ctx, cudaEventCreateWithFlags(&ev[(size_t)k], cudaEventDisableTiming));
-    if (n_samples > 0)
-      ASM_CUDA(ctx, cudaMemcpy2DAsync(d_tr + (size_t)t0 * n_pad, sizeof(double) * (size_t)n_pad, traces + (size_t)t0 * stride,
-                                      sizeof(double) * (size_t)stride, sizeof(double) * (size_t)n_samples, (size_t)nt,
-                                      cudaMemcpyHostToDevice, ctx->stream_copy));
-    ASM_CUDA(ctx, cudaEventRecord(ev[(size_t)k], ctx->stream_copy));
-  }
-  long long slots = 0;
-  for (int k = 0; k < n_chunks && rc == ASM_OK; k++) {
-    const int32_t t0 = k * chunk, nt = std::min(chunk, n_traces - t0);
-    cudaStreamWaitEvent(ctx->stream, ev[(size_t)k], 0);
-    rc = ess_batch_device(ctx, nt, n_samples, n_pad, d_tr + (size_t)t0 * n_pad, max_lag, act_out ? act_out + t0 : nullptr,
-                          ess_out ? ess_out + t0 : nullptr);
-    slots += ctx->ess_lag_slots;
-  }
-  ctx->ess_lag_slots = slots;
-  cudaStreamSynchronize(ctx->stream_copy);
-  for (cudaEvent_t e : ev)
-    if (e) cudaEventDestroy(e);
-  return rc;
+  return ess_batch_host(ctx, n_traces, n_samples, stride, traces, n_pad, (double*)ctx->ess_tr.p, max_lag, act_out, ess_out);
 }
 
 int32_t asm_traces_append(asm_ctx* ctx, int32_t chain, int32_t n_cols, int64_t n_new, const double* values) {
@@ -453,6 +438,19 @@ int32_t asm_ess_eval(asm_ctx* ctx, const int32_t* burnin, int32_t end, const int
   }
   if (n_cols == 0) return ASM_OK;
   return ess_eval_stream(ctx, burnin, end, cols, n_cols, ess_out);
+}
+
+int32_t asm_trace_moments(asm_ctx* ctx, int32_t end, double* sums_out, double* sumsq_out) {
+  ASM_ENTER(ctx);
+  if (!sums_out || !sumsq_out || end < 0) return asm_fail(ctx, ASM_E_INVALID, "trace_moments: bad argument");
+  const int n_cols = ctx->traces[0].n_cols;
+  for (int c = 0; c < ctx->n_chains; c++) {
+    if (ctx->traces[c].n_cols != n_cols) return asm_fail(ctx, ASM_E_INVALID, "trace_moments: chains differ in column count");
+    if (end > ctx->traces[c].n)
+      return asm_fail(ctx, ASM_E_RANGE, "trace_moments: end %d past chain %d's %lld samples", end, c, (long long)ctx->traces[c].n);
+  }
+  if (n_cols == 0) return ASM_OK;
+  return trace_moments(ctx, end, sums_out, sumsq_out);
 }
 
 int32_t asm_timer_mark(asm_ctx* ctx, int32_t slot) {

@@ -301,32 +301,100 @@ __global__ void __launch_bounds__(256) concat_kernel(const __grid_constant__ Con
 
 }  // namespace
 
-int32_t ess_batch_device(asm_ctx* ctx, int32_t n_traces, int64_t n_samples, int64_t stride, const double* d_traces,
-                         int32_t max_lag, double* act_out_host, double* ess_out_host) {
+namespace {
+
+// One group = a contiguous range of traces processed on its own stream.  Groups of one batch run concurrently:
+// while one group is in a late, thinly populated stage another one is still in its wide first stage (or still
+// being uploaded), which keeps the FP64 pipes busy.
+struct EssGroup {
+  int t0 = 0, nt = 0;
+  cudaStream_t st = nullptr, st2 = nullptr;
+  cudaEvent_t ready = nullptr;  // traces of this group are on the device (may be null)
+  cudaEvent_t fork = nullptr, join = nullptr;
+  int stage = 0, n_open = 0;
+  const int* ids_in = nullptr;
+  bool done = false;
+};
+
+struct EssScratch {
+  double *act, *ess, *sums, *sls;
+  EssState* state;
+  int *used, *ids[2], *counter;
+  int* h_counter;  // pinned
+};
+
+int32_t ess_launch_stage(asm_ctx* ctx, EssGroup& g, const EssScratch& sc, const double* d_traces, int64_t stride,
+                         int64_t n_samples, int32_t max_lag, const int* bounds, int n_stage, int lags_stride) {
+  const long long L = std::min<long long>(n_samples, max_lag);
+  const int s = g.stage;
+  const int b = bounds[s], e = bounds[s + 1];
+  const double* tr = d_traces + (size_t)g.t0 * stride;
+  double* sls = sc.sls + (size_t)g.t0 * lags_stride;
+  if (s == 0) {
+    if (g.ready) ASM_CUDA(ctx, cudaStreamWaitEvent(g.st, g.ready, 0));
+    ASM_CUDA(ctx, cudaMemsetAsync(sc.state + g.t0, 0, sizeof(EssState) * (size_t)g.nt, g.st));
+    // the sequential `sum` chain runs on the group's side stream, underneath the first lag stage
+    ASM_CUDA(ctx, cudaEventRecord(g.fork, g.st));
+    ASM_CUDA(ctx, cudaStreamWaitEvent(g.st2, g.fork, 0));
+    ctx->launches++;
+    ess_sum_kernel<<<(g.nt + kSumWarps - 1) / kSumWarps, 32 * kSumWarps, 0, g.st2>>>(tr, stride, n_samples, g.nt,
+                                                                                     sc.sums + g.t0);
+    ASM_CUDA(ctx, cudaEventRecord(g.join, g.st2));
+  }
+  (void)L;
+  const int lags = e - b;
+  if (n_samples > 0) {
+    // Thread shape.  8 lags per thread (R = 8) halves the shared-memory traffic per flop and runs at the FP64
+    // issue rate; it needs at least one warp per SM sub-partition (4 x 148) to fill the machine.  With fewer
+    // open chains, 4 lags per thread doubles the number of warps.  A CTA always has a multiple of 4 warps.
+    const long long warps8 = (long long)g.n_open * (lags / 256);
+    const int R = (warps8 >= 4LL * ctx->sm_count) ? 8 : 4;
+    const int gthreads = std::min(lags / R, R == 8 ? 128 : 256);  // threads of one (trace, lag block) group
+    const int blocks_y = lags / (gthreads * R);
+    const int groups = std::max(1, 128 / gthreads);               // traces per CTA
+    const int ring = (e + R + 2 * kChunk <= 2048) ? 2048 : kRingMax;
+    const size_t smem = (size_t)groups * ring * sizeof(double);
+    dim3 grid((unsigned)((g.n_open + groups - 1) / groups), (unsigned)blocks_y);
+    LaunchScope ls(ctx, ASM_K_ESS_LAG, g.st);
+    if (R == 8)
+      ess_lag_kernel<8><<<grid, groups * gthreads, smem, g.st>>>(tr, stride, n_samples, b, g.ids_in, g.n_open, lags_stride,
+                                                                 sls, gthreads, ring);
+    else
+      ess_lag_kernel<4><<<grid, groups * gthreads, smem, g.st>>>(tr, stride, n_samples, b, g.ids_in, g.n_open, lags_stride,
+                                                                 sls, gthreads, ring);
+    ctx->ess_lag_slots += (long long)g.n_open * lags;
+  }
+  ASM_CUDA(ctx, cudaGetLastError());
+  if (s == 0) ASM_CUDA(ctx, cudaStreamWaitEvent(g.st, g.join, 0));  // the scan needs the sums
+  return ASM_OK;
+}
+
+}  // namespace
+
+// Runs `n_groups` groups (each a trace range with its own stream) through the staged evaluation.
+static int32_t ess_run_groups(asm_ctx* ctx, EssGroup* groups, int n_groups, int32_t n_traces, int64_t n_samples,
+                              int64_t stride, const double* d_traces, int32_t max_lag, double* act_out_host,
+                              double* ess_out_host) {
   const long long L = std::min<long long>(n_samples, max_lag);
   const int lags_stride = 2048;  // >= ASM_MAX_LAG rounded up to the widest stage
   int32_t rc;
   if ((rc = asm_reserve(ctx, ctx->ess_sls, sizeof(double) * (size_t)n_traces * lags_stride)) != ASM_OK) return rc;
-  // [act n][ess n][sums n][state n][used n (int)][ids_a n (int)][ids_b n (int)][counter (int)]
+  // [act n][ess n][sums n][state n][used n (int)][ids_a n (int)][ids_b n (int)][counters 16 (int)]
   const size_t nd = (size_t)n_traces;
-  const size_t bytes = sizeof(double) * 3 * nd + sizeof(EssState) * nd + sizeof(int) * (3 * nd + 4);
+  const size_t bytes = sizeof(double) * 3 * nd + sizeof(EssState) * nd + sizeof(int) * (3 * nd + 16);
   if ((rc = asm_reserve(ctx, ctx->ess_out, bytes)) != ASM_OK) return rc;
-  double* d_act = (double*)ctx->ess_out.p;
-  double* d_ess = d_act + nd;
-  double* d_sums = d_ess + nd;
-  EssState* d_state = (EssState*)(d_sums + nd);
-  int* d_used = (int*)(d_state + nd);
-  int* d_ids[2] = {d_used + nd, d_used + 2 * nd};
-  int* d_counter = d_used + 3 * nd;
-  ASM_CUDA(ctx, cudaMemsetAsync(d_state, 0, sizeof(EssState) * nd, ctx->stream));
-
-  // sum chain on the side stream, underneath the first stage
-  ASM_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
-  ASM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
-  ctx->launches++;
-  ess_sum_kernel<<<(n_traces + kSumWarps - 1) / kSumWarps, 32 * kSumWarps, 0, ctx->stream2>>>(d_traces, stride, n_samples,
-                                                                                              n_traces, d_sums);
-  ASM_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));
+  EssScratch sc;
+  sc.act = (double*)ctx->ess_out.p;
+  sc.ess = sc.act + nd;
+  sc.sums = sc.ess + nd;
+  sc.state = (EssState*)(sc.sums + nd);
+  sc.used = (int*)(sc.state + nd);
+  sc.ids[0] = sc.used + nd;
+  sc.ids[1] = sc.used + 2 * nd;
+  sc.counter = sc.used + 3 * nd;
+  sc.sls = (double*)ctx->ess_sls.p;
+  if (!ctx->h_pinned) ASM_CUDA(ctx, cudaMallocHost(&ctx->h_pinned, 64));
+  sc.h_counter = (int*)ctx->h_pinned;
 
   static bool attr_set = false;
   if (!attr_set) {
@@ -341,58 +409,103 @@ int32_t ess_batch_device(asm_ctx* ctx, int32_t n_traces, int64_t n_samples, int6
   } else {
     bounds[0] = 0, bounds[1] = 2048, n_stage = 1;
   }
-  int n_open = n_traces;
-  const int* ids_in = nullptr;
   ctx->ess_lag_slots = 0;
-  for (int s = 0; s < n_stage && n_open > 0; s++) {
-    const int b = bounds[s], e = bounds[s + 1];
-    if (s > 0 && b >= L) break;  // (stage 0 always runs its scan, also for n = 0)
-    const int lags = e - b;
-    if (n_samples > 0) {
-      // Thread shape.  8 lags per thread (R = 8) halves the shared-memory traffic per flop and runs at the FP64
-      // issue rate; it needs at least one warp per SM sub-partition (4 x 148) to fill the machine.  With fewer
-      // open chains, 4 lags per thread doubles the number of warps.  A CTA always has a multiple of 4 warps.
-      const long long warps8 = (long long)n_open * (lags / 256);
-      const int R = (warps8 >= 4LL * ctx->sm_count) ? 8 : 4;
-      const int gthreads = std::min(lags / R, R == 8 ? 128 : 256);  // threads of one (trace, lag block) group
-      const int blocks_y = lags / (gthreads * R);
-      const int groups = std::max(1, 128 / gthreads);               // traces per CTA
-      const int ring = (e + R + 2 * kChunk <= 2048) ? 2048 : kRingMax;
-      const size_t smem = (size_t)groups * ring * sizeof(double);
-      dim3 grid((unsigned)((n_open + groups - 1) / groups), (unsigned)blocks_y);
-      LaunchScope ls(ctx, ASM_K_ESS_LAG);
-      if (R == 8)
-        ess_lag_kernel<8><<<grid, groups * gthreads, smem, ctx->stream>>>(d_traces, stride, n_samples, b, ids_in, n_open,
-                                                                          lags_stride, (double*)ctx->ess_sls.p, gthreads, ring);
-      else
-        ess_lag_kernel<4><<<grid, groups * gthreads, smem, ctx->stream>>>(d_traces, stride, n_samples, b, ids_in, n_open,
-                                                                          lags_stride, (double*)ctx->ess_sls.p, gthreads, ring);
-      ctx->ess_lag_slots += (long long)n_open * lags;
-    }
-    ASM_CUDA(ctx, cudaGetLastError());
-    if (s == 0) ASM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
-    ASM_CUDA(ctx, cudaMemsetAsync(d_counter, 0, sizeof(int), ctx->stream));
+
+  auto launch = [&](int gi) -> int32_t {
+    EssGroup& g = groups[gi];
+    int32_t r = ess_launch_stage(ctx, g, sc, d_traces, stride, n_samples, max_lag, bounds, n_stage, lags_stride);
+    if (r != ASM_OK) return r;
+    const int e = bounds[g.stage + 1];
+    ASM_CUDA(ctx, cudaMemsetAsync(sc.counter + gi, 0, sizeof(int), g.st));
     {
-      LaunchScope ls(ctx, ASM_K_ESS_FINISH);
-      ess_scan_kernel<<<(n_open + 127) / 128, 128, 0, ctx->stream>>>(
-          d_traces, stride, n_samples, n_open, ids_in, max_lag, e, lags_stride, (const double*)ctx->ess_sls.p, d_sums,
-          d_state, d_act, d_ess, d_used, d_ids[s & 1], d_counter);
+      LaunchScope ls(ctx, ASM_K_ESS_FINISH, g.st);
+      ess_scan_kernel<<<(g.n_open + 127) / 128, 128, 0, g.st>>>(
+          d_traces + (size_t)g.t0 * stride, stride, n_samples, g.n_open, g.ids_in, max_lag, e, lags_stride,
+          sc.sls + (size_t)g.t0 * lags_stride, sc.sums + g.t0, sc.state + g.t0, sc.act + g.t0, sc.ess + g.t0,
+          sc.used + g.t0, sc.ids[g.stage & 1] + g.t0, sc.counter + gi);
     }
     ASM_CUDA(ctx, cudaGetLastError());
-    if (s + 1 < n_stage) {
-      int cnt = 0;
-      ASM_CUDA(ctx, cudaMemcpyAsync(&cnt, d_counter, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-      ASM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-      n_open = cnt;
-      ids_in = d_ids[s & 1];
+    ASM_CUDA(ctx, cudaMemcpyAsync(sc.h_counter + gi, sc.counter + gi, sizeof(int), cudaMemcpyDeviceToHost, g.st));
+    return ASM_OK;
+  };
+
+  int remaining = 0;
+  for (int gi = 0; gi < n_groups; gi++) {
+    groups[gi].stage = 0;
+    groups[gi].n_open = groups[gi].nt;
+    groups[gi].ids_in = nullptr;
+    groups[gi].done = groups[gi].nt == 0;
+    if (!groups[gi].done) {
+      if ((rc = launch(gi)) != ASM_OK) return rc;
+      remaining++;
     }
   }
-  if (act_out_host)
-    ASM_CUDA(ctx, cudaMemcpyAsync(act_out_host, d_act, sizeof(double) * nd, cudaMemcpyDeviceToHost, ctx->stream));
-  if (ess_out_host)
-    ASM_CUDA(ctx, cudaMemcpyAsync(ess_out_host, d_ess, sizeof(double) * nd, cudaMemcpyDeviceToHost, ctx->stream));
-  ASM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  while (remaining > 0) {
+    for (int gi = 0; gi < n_groups; gi++) {
+      EssGroup& g = groups[gi];
+      if (g.done) continue;
+      ASM_CUDA(ctx, cudaStreamSynchronize(g.st));  // stage finished: the open count is on the host
+      const int cnt = sc.h_counter[gi];
+      const int next = g.stage + 1;
+      if (next < n_stage && cnt > 0 && bounds[next] < L) {
+        g.ids_in = sc.ids[g.stage & 1] + g.t0;
+        g.n_open = cnt;
+        g.stage = next;
+        if ((rc = launch(gi)) != ASM_OK) return rc;
+      } else {
+        g.done = true;
+        remaining--;
+        if (act_out_host)
+          ASM_CUDA(ctx, cudaMemcpyAsync(act_out_host + g.t0, sc.act + g.t0, sizeof(double) * (size_t)g.nt,
+                                        cudaMemcpyDeviceToHost, g.st));
+        if (ess_out_host)
+          ASM_CUDA(ctx, cudaMemcpyAsync(ess_out_host + g.t0, sc.ess + g.t0, sizeof(double) * (size_t)g.nt,
+                                        cudaMemcpyDeviceToHost, g.st));
+      }
+    }
+  }
+  for (int gi = 0; gi < n_groups; gi++) ASM_CUDA(ctx, cudaStreamSynchronize(groups[gi].st));
   return ASM_OK;
+}
+
+int32_t ess_batch_device(asm_ctx* ctx, int32_t n_traces, int64_t n_samples, int64_t stride, const double* d_traces,
+                         int32_t max_lag, double* act_out_host, double* ess_out_host) {
+  EssGroup g;
+  g.t0 = 0;
+  g.nt = n_traces;
+  g.st = ctx->stream;
+  g.st2 = ctx->stream2;
+  g.fork = ctx->ev_fork;
+  g.join = ctx->ev_join;
+  return ess_run_groups(ctx, &g, 1, n_traces, n_samples, stride, d_traces, max_lag, act_out_host, ess_out_host);
+}
+
+// Host-pointer entry: the traces are uploaded in up to four chunks on the copy stream, each chunk is a group on
+// its own stream that starts as soon as its upload has landed.
+int32_t ess_batch_host(asm_ctx* ctx, int32_t n_traces, int64_t n_samples, int64_t stride, const double* traces,
+                       int64_t n_pad, double* d_tr, int32_t max_lag, double* act_out_host, double* ess_out_host) {
+  int n_groups = 1;
+  if (n_traces >= 512 && (int64_t)n_traces * n_pad * 8 >= (1LL << 30)) n_groups = 4;
+  EssGroup groups[4];
+  const int chunk = (n_traces + n_groups - 1) / n_groups;
+  for (int k = 0; k < n_groups; k++) {
+    EssGroup& g = groups[k];
+    g.t0 = k * chunk;
+    g.nt = std::max(0, std::min(chunk, n_traces - g.t0));
+    g.st = ctx->group_stream[k];
+    g.st2 = ctx->group_stream2[k];
+    g.ready = ctx->group_event[k];
+    g.fork = ctx->group_fork[k];
+    g.join = ctx->group_join[k];
+    if (g.nt > 0 && n_samples > 0)
+      ASM_CUDA(ctx, cudaMemcpy2DAsync(d_tr + (size_t)g.t0 * n_pad, sizeof(double) * (size_t)n_pad, traces + (size_t)g.t0 * stride,
+                                      sizeof(double) * (size_t)stride, sizeof(double) * (size_t)n_samples, (size_t)g.nt,
+                                      cudaMemcpyHostToDevice, ctx->stream_copy));
+    ASM_CUDA(ctx, cudaEventRecord(g.ready, ctx->stream_copy));
+  }
+  int32_t rc = ess_run_groups(ctx, groups, n_groups, n_traces, n_samples, n_pad, d_tr, max_lag, act_out_host, ess_out_host);
+  cudaStreamSynchronize(ctx->stream_copy);
+  return rc;
 }
 
 int32_t ess_eval_stream(asm_ctx* ctx, const int32_t* burnin, int32_t end, const int32_t* cols, int32_t n_cols,

@@ -506,6 +506,83 @@ std::map<std::string, double> TraceESS::getLogMap() {  // :191-198
   return m;
 }
 
+// ------------------------------------------------------------------------------------------------ GelmanRubin
+bool GelmanRubin::converged(const int*, int available) {  // GelmanRubin.java:32-51
+  asm_ctx* ctx = traceInfo->ctx();
+  int32_t nItems = 0;
+  asm_traces_count(ctx, 0, nullptr, &nItems);
+  std::vector<double> sums((size_t)nChains * nItems), sumsq((size_t)nChains * nItems);
+  // the two accumulation loops of calcGRStat (:61-73) for every chain and item, in Java order, on the device;
+  // sampleCount > trace.size() is the reference's IllegalArgumentException (:56-58)
+  int32_t rc = asm_trace_moments(ctx, available, sums.data(), sumsq.data());
+  if (rc == ASM_E_RANGE) throw IllegalArgumentException("Expected traces of sufficient length");
+  if (rc != ASM_OK) gpu_fail(ctx, rc, "asm_trace_moments");
+  const int sampleCount = available;
+  lastMaxGR = 0;
+  bool result = true, decided = false;
+  for (int i = 0; i < nChains; i++)
+    for (int j = i + 1; j < nChains; j++)
+      for (int k = 0; k < nItems; k++) {
+        double mean1 = sums[(size_t)i * nItems + k], sumsq1 = sumsq[(size_t)i * nItems + k];
+        double mean2 = sums[(size_t)j * nItems + k], sumsq2 = sumsq[(size_t)j * nItems + k];
+        mean1 /= sampleCount;  // :67
+        mean2 /= sampleCount;  // :73
+        const double var1 = (sumsq1 - mean1 * mean1 * sampleCount) / (sampleCount - 1);  // :76
+        const double var2 = (sumsq2 - mean2 * mean2 * sampleCount) / (sampleCount - 1);  // :77
+        const double fW = (var1 + var2) / 2;                                             // :80
+        double GRstat;
+        if (fW == 0) {
+          GRstat = 1;  // :81-83
+        } else {
+          const double totalMean = (mean1 + mean2) / 2;            // :86
+          const double totalSq = mean1 * mean1 + mean2 * mean2;    // :87
+          const double fB = (totalSq - totalMean * totalMean * 2);  // :90
+          const double varR = ((sampleCount - 1.0) / sampleCount) + (fB / fW) * (1.0 / sampleCount);  // :93
+          GRstat = std::sqrt(varR);                                // :94
+        }
+        if (GRstat > lastMaxGR) lastMaxGR = GRstat;
+        if (!decided && GRstat > acceptedThreshold) {  // :44-46 (the Java returns here)
+          result = false;
+          decided = true;
+        }
+      }
+  return result;
+}
+
+// ------------------------------------------------------------------------------------------------ CladeDifference
+bool CladeDifference::converged(const int*, int available) {  // CladeDifference.java:41-65
+  asm_ctx* ctx = traceInfo->ctx();
+  for (int c = 0; c < nChains; c++)  // trees[j].get(i) for i < available (:48-52) throws past the end
+    if (available > traceInfo->treeCount(c)) throw std::out_of_range("CladeDifference: available past the stored trees");
+  int32_t words = 0;
+  asm_trees_count(ctx, 0, nullptr, &words);
+  const size_t D = (size_t)words * 64;
+  std::vector<std::vector<int32_t>> counts((size_t)nChains, std::vector<int32_t>(D ? D : 1, 0));
+  for (int c = 0; c < nChains && D; c++)  // the clade maps of process() (:147-159) = column sums of the bit matrix
+    GPU_CHECK(ctx, asm_clade_counts(ctx, c, 0, available, counts[(size_t)c].data()));
+  const int m_nClades = available > 0 ? traceInfo->taxonCount() : 1;  // :25, :149 (root clade length = taxa)
+  auto java_max = [](double a, double b) { return a != a ? a : (b != b ? b : (a > b ? a : b)); };
+  double fMaxCladeProbDiff = 0;
+  for (int i = 0; i < nChains; i++)
+    for (int k = 0; k < nChains; k++) {
+      double diff = 0;
+      if (i != k) {  // calcMaxCladeDifference :85-103
+        int nTotal = 0, nMax = 0;
+        for (size_t id = 0; id < D; id++) {
+          const int i1 = counts[(size_t)i][id];
+          if (i1 == 0) continue;  // map1.keySet()
+          const int i2 = counts[(size_t)k][id];
+          nTotal += i1;
+          nMax = std::max(nMax, std::abs(i1 - i2));
+        }
+        diff = nMax / (double)(nTotal / m_nClades);  // int division inside, :102
+      }
+      fMaxCladeProbDiff = java_max(fMaxCladeProbDiff, diff);  // :60
+    }
+  m_fMaxCladeProbDiffs.push_back(fMaxCladeProbDiff);  // :63
+  return fMaxCladeProbDiff < acceptedThreshold;       // :64
+}
+
 }  // namespace asmgpu
 
 // ================================================================================================
@@ -519,6 +596,8 @@ struct asmh_criterion {
   TreePSRF* psrf = nullptr;
   TraceESS* tess = nullptr;
   TreeESS* tree = nullptr;
+  GelmanRubin* gr = nullptr;
+  CladeDifference* cd = nullptr;
 };
 
 static thread_local std::string g_host_err;
@@ -648,6 +727,36 @@ int32_t asmh_trace_ess_create(asmh_criterion** out, int32_t target_ess, const ch
   h->c = p;
   h->tess = p;
   *out = h;
+  return ASM_OK;
+}
+int32_t asmh_gelman_rubin_create(asmh_criterion** out, double threshold) {
+  if (!out) return ASM_E_INVALID;
+  auto* p = new GelmanRubin();
+  p->acceptedThresholdInput = threshold;
+  p->initAndValidate();
+  auto* h = new asmh_criterion();
+  h->c = p;
+  h->gr = p;
+  *out = h;
+  return ASM_OK;
+}
+int32_t asmh_clade_difference_create(asmh_criterion** out, double threshold) {
+  if (!out) return ASM_E_INVALID;
+  auto* p = new CladeDifference();
+  p->acceptedThresholdInput = threshold;
+  p->initAndValidate();
+  auto* h = new asmh_criterion();
+  h->c = p;
+  h->cd = p;
+  *out = h;
+  return ASM_OK;
+}
+/* the value the last call logged: GelmanRubin -> largest statistic; CladeDifference -> fMaxCladeProbDiff (:63) */
+int32_t asmh_criterion_last_value(asmh_criterion* c, double* out) {
+  if (!c || !out) return ASM_E_INVALID;
+  if (c->gr) *out = c->gr->lastMaxGR;
+  else if (c->cd) *out = c->cd->m_fMaxCladeProbDiffs.empty() ? 0.0 : c->cd->m_fMaxCladeProbDiffs.back();
+  else return ASM_E_INVALID;
   return ASM_OK;
 }
 int32_t asmh_criterion_destroy(asmh_criterion* c) {

@@ -175,4 +175,41 @@ class TraceESS : public MCMCConvergenceCriterion {  // TraceESS.java
   std::vector<double> currentESSs;  // :24
 };
 
+class GelmanRubin : public MCMCConvergenceCriterion {  // GelmanRubin.java
+ public:
+  double acceptedThresholdInput = 1.05;  // "threshold" :14
+  void initAndValidate() override { acceptedThreshold = acceptedThresholdInput; }  // :27-29
+  bool converged(const int* burnin, int available) override;                       // :32-51
+  void setup(int nChains_, TraceInfo* ti) override {                               // :101-104
+    nChains = nChains_;
+    traceInfo = ti;
+  }
+  std::string header() const override { return "GelmanRubin"; }
+  double lastMaxGR = 0;  // largest statistic seen by the last call (NaNs skipped), for logging/tests
+
+ private:
+  TraceInfo* traceInfo = nullptr;
+  int nChains = 0;
+  double acceptedThreshold = 1.05;
+};
+
+class CladeDifference : public MCMCConvergenceCriterion {  // CladeDifference.java
+ public:
+  double acceptedThresholdInput = 0.25;  // "threshold" :16
+  void initAndValidate() override { acceptedThreshold = acceptedThresholdInput; }  // :32-35
+  bool converged(const int* burnin, int available) override;                       // :41-65
+  void setup(int nChains_, TraceInfo* ti) override {                               // :68-77
+    nChains = nChains_;
+    traceInfo = ti;
+    m_fMaxCladeProbDiffs.clear();
+  }
+  std::string header() const override { return "CladeDifference"; }
+  std::vector<double> m_fMaxCladeProbDiffs;  // :19
+
+ private:
+  TraceInfo* traceInfo = nullptr;
+  int nChains = 0;
+  double acceptedThreshold = 0.25;
+};
+
 }  // namespace asmgpu

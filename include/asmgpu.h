@@ -141,6 +141,11 @@ int32_t asm_traces_count(const asm_ctx* ctx, int32_t chain, int64_t* n_samples, 
 int32_t asm_ess_eval(asm_ctx* ctx, const int32_t* burnin, int32_t end, const int32_t* cols, int32_t n_cols,
                      double* ess_out);
 
+/* Per chain and column, over samples [0, end): sums_out[chain*n_cols + col] = sequential sum of d and
+ * sumsq_out[...] = sequential sum of d*d -- the accumulation loops of GelmanRubin.calcGRStat
+ * (GelmanRubin.java:61-73), in their Java order.  Host buffers of n_chains*n_cols doubles. */
+int32_t asm_trace_moments(asm_ctx* ctx, int32_t end, double* sums_out, double* sumsq_out);
+
 /* ---- measurement hooks -------------------------------------------------------------------------- */
 
 /* CUDA-event timing on the context's own stream (torch.cuda.Event only sees torch's stream).

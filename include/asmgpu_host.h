@@ -45,6 +45,10 @@ int32_t asmh_tree_psrf_create(asmh_criterion** out, double b, int32_t two_sided,
 int32_t asmh_tree_ess_create(asmh_criterion** out, int32_t target_ess, double smoothing, int32_t cache_limit,
                              int32_t sample_size, int32_t method);
 int32_t asmh_trace_ess_create(asmh_criterion** out, int32_t target_ess, const char* traces);
+/* GelmanRubin (GelmanRubin.java:14) and CladeDifference (CladeDifference.java:16): input "threshold" */
+int32_t asmh_gelman_rubin_create(asmh_criterion** out, double threshold);
+int32_t asmh_clade_difference_create(asmh_criterion** out, double threshold);
+int32_t asmh_criterion_last_value(asmh_criterion* c, double* out);
 int32_t asmh_criterion_destroy(asmh_criterion* c);
 /* setup(nChains, traceInfo) -- MCMCConvergenceCriterion.java:20 */
 int32_t asmh_criterion_setup(asmh_criterion* c, int32_t n_chains, asmh_trace_info* ti);

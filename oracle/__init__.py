@@ -84,6 +84,14 @@ def lib() -> C.CDLL:
         L.orc_burnin.argtypes = [_p, _i64, _i32, _p, _i32, _i32, _i32, _i32, _p]
         L.orc_pseudo_ess.restype = _f64
         L.orc_pseudo_ess.argtypes = [_p, _p, _p, _i32, _i32, _i32, _i32, _i32]
+        L.orc_gr_stat.restype = _f64
+        L.orc_gr_stat.argtypes = [_i32, _p, _p]
+        L.orc_gelman_rubin_converged.restype = _i32
+        L.orc_gelman_rubin_converged.argtypes = [_p, _i64, _i32, _i32, _i32, _f64, _p]
+        L.orc_max_clade_difference.restype = _f64
+        L.orc_max_clade_difference.argtypes = [_p, _i32, _i32, _i32]
+        L.orc_clade_difference_converged.restype = _i32
+        L.orc_clade_difference_converged.argtypes = [_p, _i32, _i32, _f64, C.POINTER(_f64)]
         L.orc_num_threads.restype = _i32
         _lib = L
     return _lib
@@ -263,6 +271,22 @@ def burnin(logs, cols, strategy: str, percent: int, end: int) -> np.ndarray:
     lib().orc_burnin(ptrs, stride, len(arrs), _ptr(m), len(m), 0 if strategy == "Automatic" else 1, percent, end,
                      _ptr(out))
     return out
+
+
+def gelman_rubin_converged(logs, available: int, threshold: float = 1.05):
+    """GelmanRubin.converged (GelmanRubin.java:32-51). Returns (converged, GR statistics [pairs][items])."""
+    arrs, ptrs, stride = _log_ptrs(logs)
+    n, items = len(arrs), arrs[0].shape[0]
+    gr = np.empty((n * (n - 1) // 2, items))
+    r = lib().orc_gelman_rubin_converged(ptrs, stride, n, items, available, threshold, _ptr(gr))
+    return bool(r), gr
+
+
+def clade_difference_converged(ts: "TreeSet", available: int, threshold: float = 0.25):
+    """CladeDifference.converged (CladeDifference.java:41-65). Returns (converged, fMaxCladeProbDiff)."""
+    mx = C.c_double()
+    r = lib().orc_clade_difference_converged(ts._h, ts.n_chains, available, threshold, C.byref(mx))
+    return bool(r), mx.value
 
 
 def num_threads() -> int:

@@ -806,3 +806,96 @@ int32_t orc_num_threads(void) {
   return 1;
 #endif
 }
+
+/* ------------------------------------------------------------------------------------------
+ * GelmanRubin (GelmanRubin.java) and CladeDifference (CladeDifference.java) criteria
+ * ---------------------------------------------------------------------------------------- */
+
+/* GelmanRubin.java:55-96 calcGRStat(sampleCount, trace1, trace2), literally. */
+double orc_gr_stat(int32_t sampleCount, const double *trace1, const double *trace2) {
+  double mean1 = 0, mean2 = 0, sumsq1 = 0, sumsq2 = 0;
+  for (int i = 0; i < sampleCount; i++) {
+    double d = trace1[i];
+    mean1 += d;
+    sumsq1 += d * d;
+  }
+  mean1 /= sampleCount;
+  for (int i = 0; i < sampleCount; i++) {
+    double d = trace2[i];
+    mean2 += d;
+    sumsq2 += d * d;
+  }
+  mean2 /= sampleCount;
+  double var1 = (sumsq1 - mean1 * mean1 * sampleCount) / (sampleCount - 1);
+  double var2 = (sumsq2 - mean2 * mean2 * sampleCount) / (sampleCount - 1);
+  double fW = (var1 + var2) / 2;
+  if (fW == 0) return 1;
+  double totalMean = (mean1 + mean2) / 2;
+  double totalSq = mean1 * mean1 + mean2 * mean2;
+  double fB = (totalSq - totalMean * totalMean * 2);
+  double varR = ((sampleCount - 1.0) / sampleCount) + (fB / fW) * (1.0 / sampleCount);
+  return sqrt(varR);
+}
+
+/* GelmanRubin.java:32-51 converged(burnin, available): every chain pair i<j, every item k (all columns, no
+ * burn-in), false at the first statistic above the threshold.  gr_out (optional, [pairs][nItems] in loop
+ * order) receives every statistic regardless of the early return. */
+int32_t orc_gelman_rubin_converged(const double *const *logs, int64_t log_stride, int32_t nChains, int32_t nItems,
+                                   int32_t available, double threshold, double *gr_out) {
+  int result = 1, decided = 0, p = 0;
+  for (int i = 0; i < nChains; i++)
+    for (int j = i + 1; j < nChains; j++)
+      for (int k = 0; k < nItems; k++) {
+        double g = orc_gr_stat(available, logs[i] + (size_t)k * log_stride, logs[j] + (size_t)k * log_stride);
+        if (gr_out) gr_out[p] = g;
+        p++;
+        if (!decided && g > threshold) {
+          result = 0;
+          decided = 1;
+        }
+      }
+  return result;
+}
+
+/* CladeDifference.java:85-103 calcMaxCladeDifference(iThread1, iThread2) on the clade counts of the first
+ * `available` trees of each chain (process() has been called for trees [0, available), :48-53).
+ * m_nClades is the LENGTH OF THE ROOT CLADE = number of taxa (:149), and nTotal/m_nClades is an int division. */
+double orc_max_clade_difference(const orc_treeset *ts, int32_t iThread1, int32_t iThread2, int32_t available) {
+  if (iThread1 == iThread2) return 0;
+  int64_t D = ts->dict.n;
+  int32_t *c1 = (int32_t *)calloc((size_t)(D > 0 ? D : 1), sizeof(int32_t));
+  int32_t *c2 = (int32_t *)calloc((size_t)(D > 0 ? D : 1), sizeof(int32_t));
+  orc_clade_counts(ts, iThread1, 0, available, c1);
+  orc_clade_counts(ts, iThread2, 0, available, c2);
+  int nTotal = 0, nMax = 0;
+  for (int64_t id = 0; id < D; id++) {
+    if (c1[id] == 0) continue; /* map1.keySet() */
+    int i1 = c1[id], i2 = c2[id];
+    nTotal += i1;
+    int a = i1 - i2;
+    if (a < 0) a = -a;
+    if (a > nMax) nMax = a;
+  }
+  free(c1);
+  free(c2);
+  int m_nClades = available > 0 ? ts->n_taxa : 1; /* :25 initial value 1 until a tree is processed */
+  return nMax / (double)(nTotal / m_nClades);
+}
+
+/* Java Math.max(double, double): NaN if either is NaN. */
+static double java_max(double a, double b) {
+  if (a != a) return a;
+  if (b != b) return b;
+  return a > b ? a : b;
+}
+
+/* CladeDifference.java:41-65 converged(burnin, available). */
+int32_t orc_clade_difference_converged(const orc_treeset *ts, int32_t nChains, int32_t available, double threshold,
+                                       double *max_out) {
+  double fMaxCladeProbDiff = 0;
+  for (int i = 0; i < nChains; i++)
+    for (int k = 0; k < nChains; k++)
+      fMaxCladeProbDiff = java_max(fMaxCladeProbDiff, orc_max_clade_difference(ts, i, k, available));
+  if (max_out) *max_out = fMaxCladeProbDiff;
+  return fMaxCladeProbDiff < threshold;
+}

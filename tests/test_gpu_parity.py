@@ -275,3 +275,44 @@ def test_errors_are_codes_not_crashes(gpu, small_chains):
         assert e.value.code == gpu.ASM_E_RANGE
     with pytest.raises(gpu.AsmGpuError):
         gpu.GpuContext(0)
+
+
+# ---------------------------------------------------------------- GelmanRubin / CladeDifference
+def test_gelman_rubin_and_clade_difference_criteria(gpu, multi_chains):
+    from asm_b200 import criteria as K
+    ch = multi_chains
+    rng = np.random.default_rng(11)
+    n, n_cols = 700, 5
+    logs = [np.cumsum(rng.normal(size=(n_cols, n)), axis=1) * 0.02 + rng.normal(size=(n_cols, n)) + 0.3 * c for c in range(4)]
+    ti = K.TraceInfo(4)
+    ti.setTaxonCount(ch.n_taxa)
+    for c in range(4):
+        l, r, root = ch.topo[c]
+        for i in range(n):
+            ti.addTree(c, l[i], r[i], int(root[i]))
+            ti.addLogLine(c, logs[c][:, i])
+    gr, cd = K.GelmanRubin(threshold=1.05), K.CladeDifference(threshold=0.25)
+    gr.setup(4, ti)
+    cd.setup(4, ti)
+    for available in (0, 1, 2, 50, 333, 700):
+        want, stats = O.gelman_rubin_converged(logs, available, 1.05)
+        assert gr.converged([0, 0, 0, 0], available) == want, available
+        if available > 2:
+            assert bits_equal(np.array([gr.lastValue]), np.array([max(0.0, np.nanmax(stats))]))
+        want_c, mx = O.clade_difference_converged(ch.ts, available, 0.25)
+        assert cd.converged([0, 0, 0, 0], available) == want_c, available
+        assert bits_equal(np.array([cd.lastValue]), np.array([mx]))
+    with pytest.raises(K.IllegalArgumentException):
+        gr.converged([0, 0, 0, 0], 701)   # "Expected traces of sufficient length" (GelmanRubin.java:56-58)
+    # raw moments, Java order
+    with gpu.GpuContext(2) as ctx:
+        for c in range(2):
+            ctx.traces_append(c, np.ascontiguousarray(logs[c].T))
+        s, q = ctx.trace_moments(500)
+        for c in range(2):
+            for k in range(n_cols):
+                ws = wq = 0.0
+                for d in logs[c][k, :500]:
+                    ws += d
+                    wq += d * d
+                assert s[c, k] == ws and q[c, k] == wq

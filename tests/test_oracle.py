@@ -169,3 +169,43 @@ def test_burnin_detector():
     # nothing fits -> lb = 3*end/4 (:77)
     y = np.arange(n, dtype=float) ** 2
     assert O.burnin([np.stack([y, y])], [1], "Automatic", 0, n)[0] == 300
+
+
+# ---------------------------------------------------------------- GelmanRubin / CladeDifference
+def test_gelman_rubin_oracle():
+    rng = np.random.default_rng(2)
+    a, b = rng.normal(size=500), rng.normal(size=500)
+    # textbook potential scale reduction for two chains of equal length
+    n = 400
+    W = (a[:n].var(ddof=1) + b[:n].var(ddof=1)) / 2
+    m1, m2 = a[:n].mean(), b[:n].mean()
+    B = m1 * m1 + m2 * m2 - 2 * ((m1 + m2) / 2) ** 2
+    want = np.sqrt((n - 1) / n + B / W / n)
+    got = O.lib().orc_gr_stat(n, a.ctypes.data_as(__import__("ctypes").c_void_p), b.ctypes.data_as(__import__("ctypes").c_void_p))
+    assert abs(got / want - 1) < 1e-12
+    logs = [np.stack([np.arange(500.0), a, a * 2]), np.stack([np.arange(500.0), b, b * 2])]
+    conv, gr = O.gelman_rubin_converged(logs, 400, 1.05)
+    assert conv and gr.shape == (1, 3) and abs(gr[0, 0] - np.sqrt(399 / 400)) < 1e-9   # identical Sample columns: fB = 0
+    shifted = [logs[0], np.stack([np.arange(500.0), b + 20, b])]
+    conv, gr = O.gelman_rubin_converged(shifted, 400, 1.05)
+    assert not conv and gr[0, 1] > 1.05
+    conv, gr = O.gelman_rubin_converged(logs, 0, 1.05)       # sampleCount 0: every statistic NaN, nothing exceeds
+    assert conv and np.isnan(gr).all()
+
+
+def test_clade_difference_oracle(multi_chains):
+    ch = multi_chains
+    n = ch.n_taxa
+    conv, mx = O.clade_difference_converged(ch.ts, 300, 0.25)
+    # independent recomputation from the bit rows
+    cnt = [np.unpackbits(b[:300].view(np.uint8), axis=-1, bitorder="little").sum(0).astype(np.int64) for b in ch.bits]
+    want = 0.0
+    for i in range(4):
+        for k in range(4):
+            if i != k:
+                sel = cnt[i] > 0
+                n_total = int(cnt[i][sel].sum())
+                want = max(want, np.abs(cnt[i][sel] - cnt[k][sel]).max() / float(n_total // n))
+    assert mx == want and conv == (mx < 0.25)
+    conv0, mx0 = O.clade_difference_converged(ch.ts, 0, 0.25)   # no trees: 0 / (0 / 1) = NaN -> not converged
+    assert np.isnan(mx0) and conv0 is False
