@@ -42,6 +42,15 @@ CFG3 = dict(n_traces=1000, n_samples=1_000_000, seed0=777)
 PHIS, MUS = [0.0, 0.5, 0.9, 0.99], [0.0, 1.0, -1e4]
 
 
+def measured_traffic(key):
+    """DRAM bytes per launch of the named kernel from the committed ncu capture (profiles/traffic.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(key)
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -342,7 +351,8 @@ def bench_psrf(args, rank, world, local, dist):
         achieved = alg / (k_ms * 1e-3) / 1e12
         peak = 2.0 * peaks["bf16_tflops"]  # int8 dense = 2 x bf16 dense on B200; bf16 is the measured figure
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "rf_i8_psrf_kernel", "kernel_ms": k_ms,
+                "traffic": measured_traffic("rf_i8x2_kernel@cfg2") if (world == 1 and args.workload == "psrf") else None,
+                "kernel": "rf_i8x2_kernel", "kernel_ms": k_ms,
                 "peak_source": f"2 x bf16_tflops ({peaks['source']}); int8 dense is 2x bf16 dense on B200",
                 "algorithmic": "D*T*(T-1) int8 flop per launch (unordered pairs, 2 flop per MAC)"}
     else:
@@ -351,7 +361,9 @@ def bench_psrf(args, rank, world, local, dist):
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9
         words_pairs = (D / 64.0) * T * (T - 1) / 2 / world
         roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "kernel": "rf_popc_psrf_kernel", "kernel_ms": k_ms,
+                "frac": achieved / peaks["hbm_gbs"],
+                "traffic": measured_traffic("rf_popc_psrf_kernel@cfg2") if (world == 1 and args.workload == "psrf") else None,
+                "kernel": "rf_popc_psrf_kernel", "kernel_ms": k_ms,
                 "peak_source": f"hbm_gbs ({peaks['source']})",
                 "algorithmic": "T*D/8 operand bytes + 8*T*C S bytes per launch",
                 "note": "integer-pipe (LOP3+POPC) bound, not HBM bound: see int_pipe",
@@ -378,7 +390,8 @@ def bench_psrf(args, rank, world, local, dist):
            "d2h_bytes_per_step": int(C * C * 8), "ms_per_step": e_ms}
 
     line = {"metric": "tree-pairs/sec (RF+PSRF)", "value": value, "unit": "tree-pairs/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong" if args.workload == "cfg5" else "weak",
             "vs_baseline": None, "dtype": "int8->s32 (tcgen05), int64 sums, f64 psrf" if method == L.ASM_RF_I8 else "u64 popc, int64 sums, f64 psrf",
             "data": "synthetic",
             "config": {"workload": f"{'cfg5' if args.workload == 'cfg5' else 'cfg2'}: {C} chains x {n_trees} trees x {cfg['n_taxa']} taxa, "
