@@ -78,6 +78,10 @@ struct asm_ctx {
       ess_sls, ess_out, tile_counter, rf_out;
   PsrfLayout layout;
   std::vector<int2> meta_host;  // staging for tile metadata
+  std::vector<uint32_t> walk_host;  // Morton tile walk of the int8 kernel (rebuilt when the block count changes)
+  DevBuf walk_dev;
+  long long walk_nb = -1;
+  uint32_t func_attr_done = 0;  // bit per kernel whose max-dynamic-smem attribute is set on this device
   // measurement
   cudaEvent_t timer[16] = {};
   bool profile = false;
@@ -89,6 +93,8 @@ struct asm_ctx {
   long long ess_lag_slots = 0;  // (trace, lag) chains evaluated by the last ESS call
   std::string err;
 };
+
+constexpr uint32_t kAttrPopc = 1, kAttrI8 = 2, kAttrI8Dump = 4, kAttrI8x2 = 8, kAttrEss = 16;
 
 // ---- error plumbing ---------------------------------------------------------------------------------
 int32_t asm_fail(asm_ctx* ctx, int32_t code, const char* fmt, ...);

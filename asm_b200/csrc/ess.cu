@@ -396,11 +396,10 @@ static int32_t ess_run_groups(asm_ctx* ctx, EssGroup* groups, int n_groups, int3
   if (!ctx->h_pinned) ASM_CUDA(ctx, cudaMallocHost(&ctx->h_pinned, 64));
   sc.h_counter = (int*)ctx->h_pinned;
 
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!(ctx->func_attr_done & kAttrEss)) {
     ASM_CUDA(ctx, cudaFuncSetAttribute(ess_lag_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kRingMax * 8));
     ASM_CUDA(ctx, cudaFuncSetAttribute(ess_lag_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kRingMax * 8));
-    attr_set = true;
+    ctx->func_attr_done |= kAttrEss;
   }
   int bounds[5];
   int n_stage;

@@ -25,6 +25,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <mutex>
+#include <vector>
 
 #include "asm_internal.h"
 
@@ -524,8 +525,9 @@ struct WorkQueue {
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 rf_i8x2_kernel(const __grid_constant__ CUtensorMap tm, int nkb, const int* __restrict__ nbits,
-               const int2* __restrict__ tile_meta, long long n_slots, int nb, int shard_index, int shard_count,
-               unsigned long long* __restrict__ slot_counter, unsigned long long* __restrict__ S, int C) {
+               const int2* __restrict__ tile_meta, long long n_slots, const uint32_t* __restrict__ walk_tiles, int nb,
+               int shard_index, int shard_count, unsigned long long* __restrict__ slot_counter,
+               unsigned long long* __restrict__ S, int C) {
   extern __shared__ __align__(1024) unsigned char smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   unsigned char* aux = smem + (size_t)kStages2 * kStageBytes2;
@@ -588,8 +590,11 @@ rf_i8x2_kernel(const __grid_constant__ CUtensorMap tm, int nkb, const int* __res
             ib = jb = -1;
             break;
           }
-          ib = (int)compact_bits((unsigned long long)t);
-          jb = (int)compact_bits((unsigned long long)t >> 1);
+          // slot -> (8x8 Morton tile of the precomputed walk, Morton position inside the tile)
+          const uint32_t tile = walk_tiles[t >> 6];
+          const unsigned long long local = (unsigned long long)(t & 63);
+          ib = (int)(tile & 0xFFFFu) * 8 + (int)compact_bits(local);
+          jb = (int)(tile >> 16) * 8 + (int)compact_bits(local >> 1);
           PairInfo tmp;
           if (ib <= jb && jb < nb && pair_flags(ib, jb, 0, tile_meta, tmp)) break;
         }
@@ -769,10 +774,10 @@ int32_t make_tmap(asm_ctx* ctx, CUtensorMap* m, const void* base, uint64_t rows,
 
 template <bool kDump>
 int32_t set_smem_attr(asm_ctx* ctx) {
-  static bool done = false;
-  if (!done) {
+  const uint32_t bit = kDump ? kAttrI8Dump : kAttrI8;
+  if (!(ctx->func_attr_done & bit)) {
     ASM_CUDA(ctx, cudaFuncSetAttribute(rf_i8_kernel<kDump>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    done = true;
+    ctx->func_attr_done |= bit;
   }
   return ASM_OK;
 }
@@ -830,15 +835,38 @@ int32_t rf_i8_sums(asm_ctx* ctx, asm_shard shard) {
   if (use_two_cta()) {
     L.tiles_total = n_pairs;  // 256x256 block pairs of the upper triangle
     L.tiles_done = (n_pairs - shard.shard_index + shard.shard_count - 1) / shard.shard_count;
-    static bool attr = false;
-    if (!attr) {
+    if (!(ctx->func_attr_done & kAttrI8x2)) {
       ASM_CUDA(ctx, cudaFuncSetAttribute(rf_i8x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes2x));
-      attr = true;
+      ctx->func_attr_done |= kAttrI8x2;
     }
-    // Morton walk over the P x P square that covers the triangle, P = next power of two >= nb
-    long long P = 1;
-    while (P < nb) P <<= 1;
-    const long long n_morton = P * P;
+    // The walk: 8x8 tiles of block pairs in Morton order, only the tiles that touch the triangle ib <= jb < nb
+    // (built on the host when nb changes; 4 bytes per 64 pairs).  Inside a tile the 64 pairs are again in Morton
+    // order, so any ~74 consecutive slots form a compact 2-D patch and almost every slot is a real pair.
+    if (ctx->walk_nb != nb) {
+      const long long nt = (nb + 7) / 8;
+      long long Pt = 1;
+      while (Pt < nt) Pt <<= 1;
+      auto compact = [](unsigned long long v) {
+        v &= 0x5555555555555555ULL;
+        v = (v | (v >> 1)) & 0x3333333333333333ULL;
+        v = (v | (v >> 2)) & 0x0F0F0F0F0F0F0F0FULL;
+        v = (v | (v >> 4)) & 0x00FF00FF00FF00FFULL;
+        v = (v | (v >> 8)) & 0x0000FFFF0000FFFFULL;
+        v = (v | (v >> 16)) & 0x00000000FFFFFFFFULL;
+        return (uint32_t)v;
+      };
+      std::vector<uint32_t>& tiles = ctx->walk_host;
+      tiles.clear();
+      for (unsigned long long m = 0; m < (unsigned long long)(Pt * Pt); m++) {
+        const uint32_t ti = compact(m), tj = compact(m >> 1);
+        if (ti <= tj && (long long)tj < nt) tiles.push_back(ti | (tj << 16));
+      }
+      if ((rc = asm_reserve(ctx, ctx->walk_dev, sizeof(uint32_t) * tiles.size())) != ASM_OK) return rc;
+      ASM_CUDA(ctx, cudaMemcpyAsync(ctx->walk_dev.p, tiles.data(), sizeof(uint32_t) * tiles.size(), cudaMemcpyHostToDevice,
+                                    ctx->stream));
+      ctx->walk_nb = nb;
+    }
+    const long long n_morton = (long long)ctx->walk_host.size() * 64;
     if ((rc = asm_reserve(ctx, ctx->tile_counter, sizeof(unsigned long long))) != ASM_OK) return rc;
     ASM_CUDA(ctx, cudaMemsetAsync(ctx->tile_counter.p, 0, sizeof(unsigned long long), ctx->stream));
     const int clusters = (int)std::min<long long>(L.tiles_done, ctx->sm_count / 2);
@@ -846,8 +874,9 @@ int32_t rf_i8_sums(asm_ctx* ctx, asm_shard shard) {
     {
       LaunchScope ls(ctx, ASM_K_RF_I8);
       rf_i8x2_kernel<<<2 * clusters, kThreads, kSmemBytes2x, ctx->stream>>>(
-          tm, (int)(Dp / kBlockK), (const int*)ctx->nbits.p, (const int2*)ctx->blk_meta.p, n_morton, (int)nb,
-          shard.shard_index, shard.shard_count, (unsigned long long*)ctx->tile_counter.p,
+          tm, (int)(Dp / kBlockK), (const int*)ctx->nbits.p, (const int2*)ctx->blk_meta.p, n_morton,
+          (const uint32_t*)ctx->walk_dev.p, (int)nb, shard.shard_index, shard.shard_count,
+          (unsigned long long*)ctx->tile_counter.p,
           (unsigned long long*)ctx->S_pad.p, L.C);
     }
     ASM_CUDA(ctx, cudaGetLastError());

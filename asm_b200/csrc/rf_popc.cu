@@ -227,10 +227,9 @@ int32_t rf_popc_sums(asm_ctx* ctx, asm_shard shard) {
   int32_t rc = asm_reserve(ctx, ctx->tile_counter, sizeof(unsigned long long));
   if (rc != ASM_OK) return rc;
   ASM_CUDA(ctx, cudaMemsetAsync(ctx->tile_counter.p, 0, sizeof(unsigned long long), ctx->stream));
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!(ctx->func_attr_done & kAttrPopc)) {
     ASM_CUDA(ctx, cudaFuncSetAttribute(rf_popc_psrf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    attr_set = true;
+    ctx->func_attr_done |= kAttrPopc;
   }
   const int grid = (int)std::min<long long>(L.tiles_done, ctx->sm_count);
   if (grid <= 0) return ASM_OK;
