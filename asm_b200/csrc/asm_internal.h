@@ -74,7 +74,7 @@ struct asm_ctx {
   std::vector<ChainTrees> trees;
   std::vector<ChainTraces> traces;
   // scratch
-  DevBuf opnd_bits, opnd_i8, nbits, S_pad, blk_meta, seg_dev, S_compact, psrf_rows, psrf_mean, misc, flush, ess_tr,
+  DevBuf opnd_bits, opnd_i8, nbits, S_pad, blk_meta, S_compact, psrf_rows, psrf_mean, misc, flush, ess_tr,
       ess_sls, ess_out, tile_counter, rf_out;
   PsrfLayout layout;
   std::vector<int2> meta_host;  // staging for tile metadata
@@ -120,7 +120,6 @@ struct LaunchScope {
 // psrf_layout.cu
 int32_t psrf_build_layout(asm_ctx* ctx, const int32_t* burnin, int32_t row_start, int32_t end, int32_t delta);
 int32_t psrf_gather_bits(asm_ctx* ctx);  // layout -> opnd_bits [Tp][Wp], nbits [Tp], blk_meta
-int32_t psrf_expand_i8(asm_ctx* ctx);    // opnd_bits -> opnd_i8 [Tp][64*Wp] (unused by the default path)
 int32_t psrf_gather_i8(asm_ctx* ctx);    // layout -> opnd_i8 [Tp][pitch8] directly, nbits [Tp], blk_meta
 int32_t psrf_compact(asm_ctx* ctx, asm_shard shard, int64_t* d_S_out);  // S_pad -> [C][n_rows][C], pad-corrected
 int32_t psrf_finish(asm_ctx* ctx, const int64_t* d_S, int32_t n_rows, double* psrf_rows_host, double* psrf_mean_host);

@@ -223,7 +223,7 @@ int32_t asm_destroy(asm_ctx* ctx) {
     if (t.d_bits) cudaFree(t.d_bits);
   for (auto& t : ctx->traces)
     if (t.d_vals) cudaFree(t.d_vals);
-  DevBuf* bufs[] = {&ctx->opnd_bits, &ctx->opnd_i8, &ctx->nbits, &ctx->S_pad, &ctx->blk_meta, &ctx->seg_dev,
+  DevBuf* bufs[] = {&ctx->opnd_bits, &ctx->opnd_i8, &ctx->nbits, &ctx->S_pad, &ctx->blk_meta,
                     &ctx->S_compact, &ctx->psrf_rows, &ctx->psrf_mean, &ctx->misc, &ctx->flush, &ctx->ess_tr,
                     &ctx->ess_sls, &ctx->ess_out, &ctx->tile_counter, &ctx->rf_out, &ctx->walk_dev};
   for (DevBuf* b : bufs)

@@ -5,7 +5,7 @@
 //                                   "A" segment (burn-in trees that are rows but not columns) and a
 //                                   "B" segment (column trees), each zero-padded to 256 rows, so that
 //                                   every 128-row tile belongs to one chain and one class
-//   operand  i8   [Tp][64*Wp] int8  the same matrix as 0/1 bytes (tcgen05 path only)
+//   operand  i8   [Tp][pitch8] int8 the same matrix as 0/1 bytes (tcgen05 path; written instead of `bits`)
 //   nbits    [Tp] int32             popcount of every row (= number of clades of the tree)
 //   S_pad    [Tp][C] int64          sum over the column trees i of chain c of (RF(p,i)+1)^2
 //   S        [C][n_rows][C] int64   the rows the caller asked for, zero-padding removed in closed form
@@ -91,24 +91,6 @@ __global__ void __launch_bounds__(256) gather_i8_kernel(const __grid_constant__ 
     }
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     if (lane == 0) nbits[p] = cnt;
-  }
-}
-
-// bits -> 0/1 bytes.  One thread expands one 64-bit word into 64 bytes (four 16-byte stores).
-__global__ void __launch_bounds__(256) expand_i8_kernel(const uint64_t* __restrict__ bits, uint4* __restrict__ out,
-                                                         size_t n_words) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  for (; i < n_words; i += (size_t)gridDim.x * blockDim.x) {
-    uint64_t w = bits[i];
-    uint4 q[4];
-    uint32_t* o = reinterpret_cast<uint32_t*>(q);
-#pragma unroll
-    for (int k = 0; k < 16; k++) {
-      uint32_t b = (uint32_t)(w >> (4 * k)) & 0xFu;
-      o[k] = (b * 0x00204081u) & 0x01010101u;  // bit t of the nibble -> byte t
-    }
-#pragma unroll
-    for (int k = 0; k < 4; k++) out[i * 4 + k] = q[k];
   }
 }
 
@@ -310,20 +292,6 @@ int32_t psrf_gather_i8(asm_ctx* ctx) {
     LaunchScope ls(ctx, ASM_K_GATHER);
     int blocks = (int)std::min<int64_t>((L.Tp + 7) / 8, (int64_t)ctx->sm_count * 16);
     gather_i8_kernel<<<blocks, 256, 0, ctx->stream>>>(tab, (uint4*)ctx->opnd_i8.p, L.pitch8 / 64, (int32_t*)ctx->nbits.p);
-  }
-  ASM_CUDA(ctx, cudaGetLastError());
-  return ASM_OK;
-}
-
-int32_t psrf_expand_i8(asm_ctx* ctx) {
-  PsrfLayout& L = ctx->layout;
-  const size_t n_words = (size_t)L.Tp * L.Wp;
-  int32_t rc = asm_reserve(ctx, ctx->opnd_i8, n_words * 64);
-  if (rc != ASM_OK) return rc;
-  {
-    LaunchScope ls(ctx, ASM_K_GATHER);
-    int blocks = (int)std::min<size_t>((n_words + 255) / 256, (size_t)ctx->sm_count * 32);
-    expand_i8_kernel<<<blocks, 256, 0, ctx->stream>>>((const uint64_t*)ctx->opnd_bits.p, (uint4*)ctx->opnd_i8.p, n_words);
   }
   ASM_CUDA(ctx, cudaGetLastError());
   return ASM_OK;
