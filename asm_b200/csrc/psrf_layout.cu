@@ -94,6 +94,14 @@ __global__ void __launch_bounds__(256) gather_i8_kernel(const __grid_constant__ 
   }
 }
 
+__global__ void __launch_bounds__(256) max_bits_kernel(const int32_t* __restrict__ nbits, long long n, int* __restrict__ out) {
+  int m = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    m = max(m, nbits[i]);
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
 struct CompactParams {
   int32_t C, n_rows, subtract_pad;
   int64_t row_pos0[ASM_MAX_CHAINS], row_posB[ASM_MAX_CHAINS], padB[ASM_MAX_CHAINS];
@@ -294,6 +302,23 @@ int32_t psrf_gather_i8(asm_ctx* ctx) {
     gather_i8_kernel<<<blocks, 256, 0, ctx->stream>>>(tab, (uint4*)ctx->opnd_i8.p, L.pitch8 / 64, (int32_t*)ctx->nbits.p);
   }
   ASM_CUDA(ctx, cudaGetLastError());
+  return ASM_OK;
+}
+
+int32_t psrf_check_max_bits(asm_ctx* ctx, int32_t limit) {
+  PsrfLayout& L = ctx->layout;
+  int32_t rc = asm_reserve(ctx, ctx->misc, sizeof(int));
+  if (rc != ASM_OK) return rc;
+  ASM_CUDA(ctx, cudaMemsetAsync(ctx->misc.p, 0, sizeof(int), ctx->stream));
+  {
+    LaunchScope ls(ctx, ASM_K_MISC);
+    max_bits_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>((const int32_t*)ctx->nbits.p, L.Tp, (int*)ctx->misc.p);
+  }
+  int m = 0;
+  ASM_CUDA(ctx, cudaMemcpyAsync(&m, ctx->misc.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  ASM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (m > limit)
+    return asm_fail(ctx, ASM_E_UNSUPPORTED, "ASM_RF_I8 supports trees with at most %d clades (found %d); use ASM_RF_POPC", limit, m);
   return ASM_OK;
 }
 

@@ -821,6 +821,13 @@ int32_t rf_i8_sums(asm_ctx* ctx, asm_shard shard) {
   const long long nb = L.Tp / kBlockRows;
   const uint64_t Dp = (uint64_t)L.pitch8;
   L.bits_used = (int64_t)Dp;
+  // The epilogue adds 32 values of (d+1)^2 in 32 bits (REDUX / per-chunk row sums): d + 1 <= 2*maxbits + 1 must stay
+  // below sqrt(2^32 / 32) = 11585, i.e. rows with at most 5,791 clades.  Rows cannot have more bits than the
+  // operand is wide, so narrow dictionaries need no check; wide ones are checked against the row popcounts.
+  if (Dp >= 5792) {
+    int32_t rcg = psrf_check_max_bits(ctx, 5791);
+    if (rcg != ASM_OK) return rcg;
+  }
   CUtensorMap tm;
   int32_t rc = make_tmap(ctx, &tm, ctx->opnd_i8.p, (uint64_t)L.Tp, Dp);
   if (rc != ASM_OK) return rc;

@@ -13,7 +13,7 @@
 // SASS) and tracked with mbarrier transaction counts.  Rows are padded to 144 bytes in shared memory
 // so that the 16-byte row reads of a quarter warp fall into 8 different bank groups.
 //
-// Bound: integer pipe (LOP3 + POPC issue), not HBM: a tile pair reads 2*128*Wp*8 bytes and does
+// Bound: integer pipes (POPC issue first, LOP3 second), not HBM: a tile pair reads 2*128*Wp*8 bytes and does
 // 128*128*Wp 64-bit XOR-popcounts.
 #include <algorithm>
 #include <cmath>
@@ -144,10 +144,19 @@ rf_popc_psrf_kernel(const uint64_t* __restrict__ bits, int Wp, const int2* __res
           a[r] = *reinterpret_cast<const ulonglong2*>(As + (ty + 16 * r) * kRowStride + kk);
           b[r] = *reinterpret_cast<const ulonglong2*>(Bs + (tx + 16 * r) * kRowStride + kk);
         }
+        // 3:2 carry-save step: the four 32-bit XOR words w0..w3 of a 128-bit slice need three POPCs instead of four
+        // (popc(w0)+popc(w1)+popc(w2) = popc(w0^w1^w2) + 2*popc(maj(w0,w1,w2))); POPC is the binding pipe (16/clk/SM),
+        // the extra LOP3s go to the ALU pipe (64/clk/SM).
 #pragma unroll
         for (int r = 0; r < 8; r++)
 #pragma unroll
-          for (int c = 0; c < 8; c++) acc[r][c] += __popcll(a[r].x ^ b[c].x) + __popcll(a[r].y ^ b[c].y);
+          for (int c = 0; c < 8; c++) {
+            const unsigned long long x = a[r].x ^ b[c].x, y = a[r].y ^ b[c].y;
+            const uint32_t w0 = (uint32_t)x, w1 = (uint32_t)(x >> 32), w2 = (uint32_t)y, w3 = (uint32_t)(y >> 32);
+            const uint32_t sum = w0 ^ w1 ^ w2;
+            const uint32_t carry = (w0 & w1) | (w2 & (w0 ^ w1));
+            acc[r][c] += __popc(sum) + __popc(w3) + 2 * __popc(carry);
+          }
       }
       __syncthreads();  // all reads of this stage are done before it is refilled
       if (kc + kStages < nk) {
