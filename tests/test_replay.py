@@ -111,3 +111,27 @@ def test_tree_ess_pseudo_ess_and_one_sided(gpu, small_chains):
         assert g.converged([0, 0], end) == o.converged([0, 0], end), end
         assert bits_equal(g.grValues[:1], o.grValues[:1])
     assert g.converged([0, 0], 301) is False and g.threw  # past the stored trees: caught, false (TreePSRF.java:252-258)
+
+
+@pytest.mark.gpu
+def test_tree_convergence_check_tool(gpu, tmp_path):
+    """The offline batch caller (tools/TreeConvergenceCheck.java:44-80): one converged() call per pair of files."""
+    from asm_b200.tools import tree_convergence_check as T
+    prefixes = replay.make_run(tmp_path, 14, 3, 300, 1.6, seed=21)
+    files = [p + ".trees" for p in prefixes]
+    # oracle: same trees, same single call
+    import oracle as O2
+    for (i, j) in [(0, 1), (0, 2), (1, 2)]:
+        conv, gr, end = T.check_pair(files[i], files[j], burnin_pct=10, smoothing=0.9, b=0.2, targetESS=200)
+        ts = O2.TreeSet(2, 14)
+        for c, f in enumerate((files[i], files[j])):
+            for line in open(f):
+                if line.startswith("tree STATE"):
+                    l, r, root = replay.parse_newick(line[line.index("("):], 14)
+                    ts.add(c, l[None, :], r[None, :], np.array([root], dtype=np.int32))
+        crit = O2.TreePSRF(smoothing=0.9, b=0.2, targetESS=200, cacheLimit=max(1024, end + 1))
+        crit.setup(2, ts)
+        start = 10 * end // 100
+        assert crit.converged([start, start], end) == conv and end == 302
+        assert bits_equal(crit.grValues, gr)
+    assert T.main(["-tree", files[0], files[1], "-b", "0.2"]) == 0
