@@ -128,8 +128,6 @@ static int32_t trees_put(asm_ctx* ctx, int32_t chain, int64_t at, int64_t n_new,
                          cudaMemcpyKind kind) {
   if (chain < 0 || chain >= ctx->n_chains || n_new < 0 || words <= 0 || (n_new > 0 && !bits))
     return asm_fail(ctx, ASM_E_INVALID, "trees: bad argument (chain=%d n=%lld words=%d)", chain, (long long)n_new, words);
-  if (words < ctx->words && ctx->trees[chain].n + n_new > 0 && at > 0)
-    ;  // narrower rows are zero-extended below
   int32_t rc = ensure_tree_capacity(ctx, chain, at + n_new, words);
   if (rc != ASM_OK) return rc;
   ChainTrees& t = ctx->trees[chain];
