@@ -36,11 +36,20 @@ namespace {
 constexpr int kChunk = 512;  // samples per cp.async group
 constexpr int kRingMax = 4096;  // ring size in samples must be >= max lag of the CTA + 8 + 2*kChunk
 
+// XOR pattern of 64-byte block g.  A quarter warp reads 8 x 16 bytes that must fall into 8 different bank groups:
+// with 8 lags per thread the 8 lanes sit in 8 consecutive blocks (pattern of period 8 blocks), with 4 lags per
+// thread in 4 or 5 consecutive blocks, two lanes per block (pattern of period 4 blocks; the period-8 pattern
+// collides when the lanes straddle 5 blocks: ncu showed 25 % conflicting wavefronts).
+template <int R>
+__device__ __forceinline__ int ring_swz(int g) {
+  return R == 8 ? ((g >> 1) & 3) : ((g >> 1) & 1);
+}
 // logical ring index -> physical: 64-byte blocks, the four 16-byte sub-blocks XOR-swizzled
+template <int R>
 __device__ __forceinline__ int ring_phys(int e) {
   int g = e >> 3;
   int sub = (e >> 1) & 3;
-  return (g << 3) | (((sub ^ ((g >> 1) & 3)) << 1) | (e & 1));
+  return (g << 3) | (((sub ^ ring_swz<R>(g)) << 1) | (e & 1));
 }
 
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
@@ -58,7 +67,7 @@ template <int R>
 __device__ __forceinline__ void load_block(const double* ring, int mask, int e0, double (&v)[R]) {
   const int e = e0 & mask;
   const int g = e >> 3;
-  const int sw = (g >> 1) & 3;
+  const int sw = ring_swz<R>(g);
   const int first = (R == 8) ? 0 : ((e >> 2) & 1) * 2;  // first 16-byte sub-block of the group
   const double2* base = reinterpret_cast<const double2*>(ring + (g << 3));
 #pragma unroll
@@ -104,7 +113,7 @@ __global__ void __launch_bounds__(256) ess_lag_kernel(const double* __restrict__
     const long long base = c * kChunk;
     for (int e = tid; e < kChunk; e += NT) {
       const long long i = base + e;
-      double* dst = ring + ring_phys((int)(i & mask));
+      double* dst = ring + ring_phys<R>((int)(i & mask));
       if (i < n)
         cp_async8(dst, x + i);
       else
