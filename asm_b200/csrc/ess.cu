@@ -28,29 +28,36 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 
 #include "asm_internal.h"
 
 namespace {
 
 constexpr int kChunk = 512;  // samples per cp.async group
-constexpr int kRingMax = 4096;  // ring size in samples must be >= max lag of the CTA + 8 + 2*kChunk
+// Ring size in samples >= largest lag of the stage + 8 + 3*kChunk: a thread that has passed the barrier of chunk c
+// issues the copy of chunk c+1 while a slower thread of its group may still be reading the window of chunk c-1.
+constexpr int kRingMax = 4096;
 
-// XOR pattern of 64-byte block g.  A quarter warp reads 8 x 16 bytes that must fall into 8 different bank groups:
-// with 8 lags per thread the 8 lanes sit in 8 consecutive blocks (pattern of period 8 blocks), with 4 lags per
-// thread in 4 or 5 consecutive blocks, two lanes per block (pattern of period 4 blocks; the period-8 pattern
-// collides when the lanes straddle 5 blocks: ncu showed 25 % conflicting wavefronts).
+// Ring layout.  A thread reads its R new window values as R/2 16-byte loads; the 8 lanes of a quarter warp sit
+// 8*R bytes apart and must hit 8 different 16-byte bank groups.  Instead of an XOR swizzle (one LOP3 per load) the
+// ring is padded: 16 bytes after every 8 samples (R = 8: blocks 80 bytes apart, 5b mod 8 is a permutation) or after
+// every 4 samples (R = 4: half blocks 48 bytes apart, 3h mod 8 is a permutation); with 2 or 1 lags per thread a
+// quarter warp reads contiguous bytes and needs no padding.  An aligned block therefore starts at e * off(R) / R
+// bytes and its 16-byte pieces follow at immediates.  The first kChunk samples are mirrored behind the ring's end
+// so that the kChunk consecutive window blocks of one chunk never wrap: the inner loop only adds a constant to
+// its two addresses.
 template <int R>
-__device__ __forceinline__ int ring_swz(int g) {
-  return R == 8 ? ((g >> 1) & 3) : ((g >> 1) & 1);
-}
-// logical ring index -> physical: 64-byte blocks, the four 16-byte sub-blocks XOR-swizzled
-template <int R>
-__device__ __forceinline__ int ring_phys(int e) {
-  int g = e >> 3;
-  int sub = (e >> 1) & 3;
-  return (g << 3) | (((sub ^ ring_swz<R>(g)) << 1) | (e & 1));
-}
+struct Ring {
+  static constexpr int kPadShift = R == 8 ? 3 : (R == 4 ? 2 : 0);
+  __host__ __device__ static constexpr uint32_t off(uint32_t e) {
+    return e * 8u + (kPadShift ? (e >> kPadShift) * 16u : 0u);
+  }
+  // ring of `ring_size` samples + mirror of the first chunk + one block of read-ahead
+  __host__ __device__ static constexpr uint32_t bytes(uint32_t ring_size) {
+    return (off(ring_size + kChunk + 16) + 127u) & ~127u;
+  }
+};
 
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
   uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
@@ -62,19 +69,18 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// read the aligned R-sample block that starts at logical index e0 (multiple of R), R = 4 or 8
+// read the aligned R-sample block at byte offset `o` of the ring, R = 1, 2, 4 or 8
 template <int R>
-__device__ __forceinline__ void load_block(const double* ring, int mask, int e0, double (&v)[R]) {
-  const int e = e0 & mask;
-  const int g = e >> 3;
-  const int sw = ring_swz<R>(g);
-  const int first = (R == 8) ? 0 : ((e >> 2) & 1) * 2;  // first 16-byte sub-block of the group
-  const double2* base = reinterpret_cast<const double2*>(ring + (g << 3));
+__device__ __forceinline__ void load_block(const char* ring, uint32_t o, double (&v)[R]) {
+  if constexpr (R == 1) {
+    v[0] = *reinterpret_cast<const double*>(ring + o);
+  } else {
 #pragma unroll
-  for (int s = 0; s < R / 2; s++) {
-    double2 d = base[(first + s) ^ sw];
-    v[2 * s] = d.x;
-    v[2 * s + 1] = d.y;
+    for (int s = 0; s < R / 2; s++) {
+      double2 d = *reinterpret_cast<const double2*>(ring + o + 16 * s);
+      v[2 * s] = d.x;
+      v[2 * s + 1] = d.y;
+    }
   }
 }
 
@@ -86,13 +92,15 @@ __global__ void __launch_bounds__(256) ess_lag_kernel(const double* __restrict__
                                                       int lag_begin, const int* __restrict__ trace_ids, int n_open,
                                                       int lags_stride, double* __restrict__ sls, int gthreads,
                                                       int ring_size) {
-  extern __shared__ __align__(16) double ring_all[];
+  extern __shared__ __align__(128) char ring_all[];
   const int group = threadIdx.x / gthreads, tid = threadIdx.x - group * gthreads, NT = gthreads;
   const int groups = blockDim.x / gthreads;
   const int idx = blockIdx.x * groups + group;
   if (idx >= n_open) return;  // whole group idle; groups synchronise among themselves only
-  double* ring = ring_all + (size_t)group * ring_size;
+  const uint32_t ring_bytes = Ring<R>::bytes((uint32_t)ring_size);
+  char* ring = ring_all + (size_t)group * ring_bytes;
   const int mask = ring_size - 1;
+  const uint32_t mirror_off = Ring<R>::off((uint32_t)ring_size);
   const long long trace = trace_ids ? trace_ids[idx] : idx;
   const double* __restrict__ x = traces + trace * stride;
   const int l0 = lag_begin + (int)blockIdx.y * NT * R + tid * R;
@@ -103,7 +111,8 @@ __global__ void __launch_bounds__(256) ess_lag_kernel(const double* __restrict__
       asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(NT) : "memory");
   };
 
-  for (int e = tid; e < ring_size; e += NT) ring[e] = 0.0;  // x[i] = 0 for i < 0
+  for (uint32_t o = tid * 16; o < ring_bytes; o += NT * 16)  // x[i] = 0 for i < 0
+    *reinterpret_cast<double2*>(ring + o) = make_double2(0.0, 0.0);
   group_sync();
 
   const long long nR = (n + R - 1) / R * R;
@@ -111,13 +120,18 @@ __global__ void __launch_bounds__(256) ess_lag_kernel(const double* __restrict__
 
   auto load_chunk = [&](long long c) {
     const long long base = c * kChunk;
+    const uint32_t e0 = (uint32_t)(base & mask);  // the chunk occupies [e0, e0 + kChunk), no wrap
+    const bool mirror = e0 == 0;
     for (int e = tid; e < kChunk; e += NT) {
       const long long i = base + e;
-      double* dst = ring + ring_phys<R>((int)(i & mask));
-      if (i < n)
+      char* dst = ring + Ring<R>::off(e0 + (uint32_t)e);
+      if (i < n) {
         cp_async8(dst, x + i);
-      else
-        *dst = 0.0;  // tail padding: adds +-0.0, which leaves every accumulator unchanged
+        if (mirror) cp_async8(dst + mirror_off, x + i);
+      } else {  // tail padding: adds +-0.0, which leaves every accumulator unchanged
+        *reinterpret_cast<double*>(dst) = 0.0;
+        if (mirror) *reinterpret_cast<double*>(dst + mirror_off) = 0.0;
+      }
     }
     cp_async_commit();
   };
@@ -129,6 +143,7 @@ __global__ void __launch_bounds__(256) ess_lag_kernel(const double* __restrict__
 #pragma unroll
   for (int k = 0; k < 2 * R - 1; k++) w[k] = 0.0;
 
+  constexpr uint32_t kStep = Ring<R>::off(R);  // bytes from one aligned block to the next
   if (n_chunks > 0) load_chunk(0);
   for (long long c = 0; c < n_chunks; c++) {
     if (c + 1 < n_chunks) {
@@ -139,30 +154,35 @@ __global__ void __launch_bounds__(256) ess_lag_kernel(const double* __restrict__
     }
     group_sync();
     const long long i_begin = c * kChunk;
-    const long long i_end = min(i_begin + (long long)kChunk, nR);
-    // software pipeline: the loads of group g+1 are issued before the arithmetic of group g, so that a warp
-    // that has an SM sub-partition almost to itself does not stall on shared-memory latency
+    const int n_blocks = (int)((min(i_begin + (long long)kChunk, nR) - i_begin) / R);
+    // x[i..i+R) sits at xo, the window block x[i-l0..i-l0+R) at wo; both advance by kStep per block.
+    uint32_t xo = Ring<R>::off((uint32_t)(i_begin & mask));
+    uint32_t wo = Ring<R>::off((uint32_t)((i_begin - l0) & mask));
+    // software pipeline: the loads of block k+1 are issued before the arithmetic of block k, so that a warp
+    // that has an SM sub-partition almost to itself does not stall on shared-memory latency (the read-ahead of
+    // the last block lands in the next chunk / the mirror and is discarded)
     double xi[R], wn[R], xi_n[R], wn_n[R];
-    load_block<R>(ring, mask, (int)(i_begin & mask), xi);
-    load_block<R>(ring, mask, (int)((i_begin - l0) & mask), wn);
-#pragma unroll 2
-    for (long long i = i_begin; i < i_end; i += R) {
-      const long long in = (i + R < i_end) ? i + R : i;
-      load_block<R>(ring, mask, (int)(in & mask), xi_n);
-      load_block<R>(ring, mask, (int)((in - l0) & mask), wn_n);
+    load_block<R>(ring, xo, xi);
+    load_block<R>(ring, wo, wn);
+#pragma unroll(R >= 4 ? 2 : 4)
+    for (int k = 0; k < n_blocks; k++) {
+      xo += kStep;
+      wo += kStep;
+      load_block<R>(ring, xo, xi_n);
+      load_block<R>(ring, wo, wn_n);
 #pragma unroll
-      for (int k = 0; k < R; k++) w[R - 1 + k] = wn[k];
+      for (int k2 = 0; k2 < R; k2++) w[R - 1 + k2] = wn[k2];
       // w[k] = x[i - l0 - (R-1) + k]; lag l0+r pairs x[i+di] with x[i+di-l0-r] = w[R-1 + di - r]
 #pragma unroll
       for (int di = 0; di < R; di++)
 #pragma unroll
         for (int r = 0; r < R; r++) acc[r] = __dadd_rn(acc[r], __dmul_rn(w[R - 1 + di - r], xi[di]));
 #pragma unroll
-      for (int k = 0; k < R - 1; k++) w[k] = w[k + R];
+      for (int k2 = 0; k2 < R - 1; k2++) w[k2] = w[k2 + R];
 #pragma unroll
-      for (int k = 0; k < R; k++) {
-        xi[k] = xi_n[k];
-        wn[k] = wn_n[k];
+      for (int k2 = 0; k2 < R; k2++) {
+        xi[k2] = xi_n[k2];
+        wn[k2] = wn_n[k2];
       }
     }
   }
@@ -332,6 +352,37 @@ struct EssScratch {
   int* h_counter;  // pinned
 };
 
+// Thread shape of one stage: R lags per thread, groups of `gthreads` threads per (trace, lag block), CTAs of 128
+// threads (one warp per SM sub-partition).  8 lags per thread halves the shared-memory traffic per flop and runs
+// at the FP64 issue rate; fewer lags per thread give more, lighter warps for the thinly populated late stages.
+struct EssShape {
+  int R, gthreads, blocks_y, groups, ring;
+};
+
+EssShape ess_pick_shape(const asm_ctx* ctx, int n_open, int lags, int lag_end, int stage) {
+  int R = 0;
+  if (const char* env = getenv("ASM_ESS_R")) {  // tuning aid: "R0,R1,R2,R3" per stage, 0 = automatic
+    const char* p = env;
+    for (int k = 0; k < stage && p; k++) {
+      p = strchr(p, ',');
+      if (p) p++;
+    }
+    if (p) R = atoi(p);
+    if (R != 8 && R != 4 && R != 2 && R != 1) R = 0;
+  }
+  if (R == 0) {
+    const long long warps8 = (long long)n_open * (lags / 256);
+    R = (warps8 >= 4LL * ctx->sm_count) ? 8 : 4;
+  }
+  EssShape sh;
+  sh.R = R;
+  sh.gthreads = std::min(lags / R, 128);
+  sh.blocks_y = lags / (sh.gthreads * R);
+  sh.groups = std::max(1, 128 / sh.gthreads);
+  sh.ring = (lag_end + 8 + 3 * kChunk <= 2048) ? 2048 : kRingMax;
+  return sh;
+}
+
 int32_t ess_launch_stage(asm_ctx* ctx, EssGroup& g, const EssScratch& sc, const double* d_traces, int64_t stride,
                          int64_t n_samples, int32_t max_lag, const int* bounds, int n_stage, int lags_stride) {
   const long long L = std::min<long long>(n_samples, max_lag);
@@ -353,24 +404,20 @@ int32_t ess_launch_stage(asm_ctx* ctx, EssGroup& g, const EssScratch& sc, const 
   (void)L;
   const int lags = e - b;
   if (n_samples > 0) {
-    // Thread shape.  8 lags per thread (R = 8) halves the shared-memory traffic per flop and runs at the FP64
-    // issue rate; it needs at least one warp per SM sub-partition (4 x 148) to fill the machine.  With fewer
-    // open chains, 4 lags per thread doubles the number of warps.  A CTA always has a multiple of 4 warps.
-    const long long warps8 = (long long)g.n_open * (lags / 256);
-    const int R = (warps8 >= 4LL * ctx->sm_count) ? 8 : 4;
-    const int gthreads = std::min(lags / R, R == 8 ? 128 : 256);  // threads of one (trace, lag block) group
-    const int blocks_y = lags / (gthreads * R);
-    const int groups = std::max(1, 128 / gthreads);               // traces per CTA
-    const int ring = (e + R + 2 * kChunk <= 2048) ? 2048 : kRingMax;
-    const size_t smem = (size_t)groups * ring * sizeof(double);
-    dim3 grid((unsigned)((g.n_open + groups - 1) / groups), (unsigned)blocks_y);
+    const EssShape sh = ess_pick_shape(ctx, g.n_open, lags, e, s);
+    const int R = sh.R, gthreads = sh.gthreads;
+    dim3 grid((unsigned)((g.n_open + sh.groups - 1) / sh.groups), (unsigned)sh.blocks_y);
     LaunchScope ls(ctx, ASM_K_ESS_LAG, g.st);
-    if (R == 8)
-      ess_lag_kernel<8><<<grid, groups * gthreads, smem, g.st>>>(tr, stride, n_samples, b, g.ids_in, g.n_open, lags_stride,
-                                                                 sls, gthreads, ring);
-    else
-      ess_lag_kernel<4><<<grid, groups * gthreads, smem, g.st>>>(tr, stride, n_samples, b, g.ids_in, g.n_open, lags_stride,
-                                                                 sls, gthreads, ring);
+#define ASM_ESS_LAUNCH(RR)                                                                                     \
+  ess_lag_kernel<RR><<<grid, sh.groups * gthreads, (size_t)sh.groups * Ring<RR>::bytes(sh.ring), g.st>>>(      \
+      tr, stride, n_samples, b, g.ids_in, g.n_open, lags_stride, sls, gthreads, sh.ring)
+    switch (R) {
+      case 8: ASM_ESS_LAUNCH(8); break;
+      case 4: ASM_ESS_LAUNCH(4); break;
+      case 2: ASM_ESS_LAUNCH(2); break;
+      default: ASM_ESS_LAUNCH(1); break;
+    }
+#undef ASM_ESS_LAUNCH
     ctx->ess_lag_slots += (long long)g.n_open * lags;
   }
   ASM_CUDA(ctx, cudaGetLastError());
@@ -406,8 +453,10 @@ static int32_t ess_run_groups(asm_ctx* ctx, EssGroup* groups, int n_groups, int3
   sc.h_counter = (int*)ctx->h_pinned;
 
   if (!(ctx->func_attr_done & kAttrEss)) {
-    ASM_CUDA(ctx, cudaFuncSetAttribute(ess_lag_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kRingMax * 8));
-    ASM_CUDA(ctx, cudaFuncSetAttribute(ess_lag_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kRingMax * 8));
+    ASM_CUDA(ctx, cudaFuncSetAttribute(ess_lag_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * Ring<8>::bytes(kRingMax)));
+    ASM_CUDA(ctx, cudaFuncSetAttribute(ess_lag_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * Ring<4>::bytes(kRingMax)));
+    ASM_CUDA(ctx, cudaFuncSetAttribute(ess_lag_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * Ring<2>::bytes(kRingMax)));
+    ASM_CUDA(ctx, cudaFuncSetAttribute(ess_lag_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * Ring<1>::bytes(kRingMax)));
     ctx->func_attr_done |= kAttrEss;
   }
   int bounds[5];

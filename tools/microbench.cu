@@ -48,6 +48,37 @@ double run(const char* name, double ops_per_iter_chain, int sms) {
   return rate;
 }
 
+
+// Dependent-issue latency of FP64 adds: one warp, C independent accumulator chains, each step one DADD per chain
+// (MUL = 1: the addend is a fresh DMUL, as in the ESS lag kernel).  Reports clocks per step of one warp.
+template <int C, int MUL>
+__global__ void lat_k(double* out, long long* clk, int iters, double dseed) {
+  double a[C], m[C];
+  for (int c = 0; c < C; c++) { a[c] = dseed + c; m[c] = dseed * (c + 2) + threadIdx.x; }
+  long long t0 = clock64();
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+      if (MUL) { a[c] = __dadd_rn(a[c], m[c]); m[c] = __dmul_rn(m[c], dseed); } else a[c] = __dadd_rn(a[c], m[c]);
+    }
+  }
+  long long t1 = clock64();
+  double s = 0;
+  for (int c = 0; c < C; c++) s += a[c] + m[c];
+  if (threadIdx.x == 0 && blockIdx.x == 0) clk[0] = t1 - t0;
+  if (s == 1.2345) out[0] = s;
+}
+template <int C, int MUL>
+void run_lat(const char* name, int warps) {
+  double* d; long long* c; cudaMalloc(&d, 8); cudaMalloc(&c, 8);
+  int iters = 100000;
+  lat_k<C, MUL><<<1, 32 * warps>>>(d, c, 100, 1.0000001);
+  lat_k<C, MUL><<<1, 32 * warps>>>(d, c, iters, 1.0000001);
+  long long h; cudaMemcpy(&h, c, 8, cudaMemcpyDeviceToHost);
+  printf("  \"%s\": {\"chains\": %d, \"warps_in_cta\": %d, \"clk_per_step\": %.2f},\n", name, C, warps, (double)h / iters);
+  cudaFree(d); cudaFree(c);
+}
+
 int main() {
   cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
   printf("{\n  \"gpu\": \"%s\", \"sms\": %d, \"clock_khz\": %d,\n", p.name, p.multiProcessorCount, p.clockRate);
@@ -61,6 +92,18 @@ int main() {
   run<6>("dfma", 1, sms);
   run<7>("dmul_dadd_pair_instrs", 2, sms);
   run<8>("popc2_mix", 2, sms);
+  run_lat<1, 0>("dadd_dep_1chain", 1);
+  run_lat<2, 0>("dadd_dep_2chain", 1);
+  run_lat<4, 0>("dadd_dep_4chain", 1);
+  run_lat<8, 0>("dadd_dep_8chain", 1);
+  run_lat<1, 1>("dmul_dadd_dep_1chain", 1);
+  run_lat<2, 1>("dmul_dadd_dep_2chain", 1);
+  run_lat<4, 1>("dmul_dadd_dep_4chain", 1);
+  run_lat<8, 1>("dmul_dadd_dep_8chain", 1);
+  run_lat<4, 1>("dmul_dadd_dep_4chain_4warps", 4);
+  run_lat<4, 1>("dmul_dadd_dep_4chain_8warps", 8);
+  run_lat<8, 1>("dmul_dadd_dep_8chain_4warps", 4);
+  run_lat<8, 1>("dmul_dadd_dep_8chain_8warps", 8);
   printf("  \"note\": \"lane-ops per second; per_sm_per_ns ~ lane-ops per clock per SM at ~1 GHz (divide by the clock in GHz)\"\n}\n");
   return 0;
 }
