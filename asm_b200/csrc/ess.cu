@@ -20,7 +20,7 @@
 //
 // Staged evaluation: the integral of TraceESS.java:161-172 stops at the first even lag whose pair sum
 // autoCorrelation[lag-1] + autoCorrelation[lag] is not positive, so lags beyond that point cannot change
-// the result.  Lags are therefore evaluated in stages [0,256), [256,768), [768,1792), [1792,2048); after each stage
+// the result.  Lags are therefore evaluated in stages [0,128), [128,256), [256,768), [768,1792), [1792,2048); after each stage
 // K6 ess_scan_kernel advances every still-open trace's integral and retires the traces whose loop has
 // stopped (or has reached min(n, 2000) lags).  The output is bit-identical to evaluating all lags
 // (asm_ess_set_adaptive(ctx, 0) / ASM_ESS_ADAPTIVE=0 does exactly that, in one stage).
@@ -69,14 +69,15 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// read the aligned R-sample block at byte offset `o` of the ring, R = 1, 2, 4 or 8
-template <int R>
-__device__ __forceinline__ void load_block(const char* ring, uint32_t o, double (&v)[R]) {
-  if constexpr (R == 1) {
-    v[0] = *reinterpret_cast<const double*>(ring + o);
+// read N consecutive samples (no padding in between) at byte offset `o` of the ring
+template <int N, bool kAligned16>
+__device__ __forceinline__ void load_block(const char* ring, uint32_t o, double (&v)[N]) {
+  if constexpr (!kAligned16) {
+#pragma unroll
+    for (int s = 0; s < N; s++) v[s] = *reinterpret_cast<const double*>(ring + o + 8 * s);
   } else {
 #pragma unroll
-    for (int s = 0; s < R / 2; s++) {
+    for (int s = 0; s < N / 2; s++) {
       double2 d = *reinterpret_cast<const double2*>(ring + o + 16 * s);
       v[2 * s] = d.x;
       v[2 * s + 1] = d.y;
@@ -115,7 +116,8 @@ __global__ void __launch_bounds__(256) ess_lag_kernel(const double* __restrict__
     *reinterpret_cast<double2*>(ring + o) = make_double2(0.0, 0.0);
   group_sync();
 
-  const long long nR = (n + R - 1) / R * R;
+  constexpr int kRound = R >= 4 ? R : 8;  // samples per inner-loop step
+  const long long nR = (n + kRound - 1) / kRound * kRound;
   const long long n_chunks = (nR + kChunk - 1) / kChunk;
 
   auto load_chunk = [&](long long c) {
@@ -136,14 +138,18 @@ __global__ void __launch_bounds__(256) ess_lag_kernel(const double* __restrict__
     cp_async_commit();
   };
 
+  // SB samples per inner-loop step: R for the wide shapes; 8 for 1 or 2 lags per thread, whose steps would
+  // otherwise be shorter than the shared-memory latency that the one-step read-ahead has to cover.
+  constexpr int SB = R >= 4 ? R : 8;
+  constexpr bool kWinAligned = R >= 2;  // window blocks start at multiples of R samples
   double acc[R];
-  double w[2 * R - 1];
+  double w[R - 1 + SB];
 #pragma unroll
   for (int r = 0; r < R; r++) acc[r] = 0.0;
 #pragma unroll
-  for (int k = 0; k < 2 * R - 1; k++) w[k] = 0.0;
+  for (int k = 0; k < R - 1 + SB; k++) w[k] = 0.0;
 
-  constexpr uint32_t kStep = Ring<R>::off(R);  // bytes from one aligned block to the next
+  constexpr uint32_t kStep = Ring<R>::off(SB);  // bytes from one block of SB samples to the next
   if (n_chunks > 0) load_chunk(0);
   for (long long c = 0; c < n_chunks; c++) {
     if (c + 1 < n_chunks) {
@@ -154,33 +160,33 @@ __global__ void __launch_bounds__(256) ess_lag_kernel(const double* __restrict__
     }
     group_sync();
     const long long i_begin = c * kChunk;
-    const int n_blocks = (int)((min(i_begin + (long long)kChunk, nR) - i_begin) / R);
-    // x[i..i+R) sits at xo, the window block x[i-l0..i-l0+R) at wo; both advance by kStep per block.
+    const int n_blocks = (int)((min(i_begin + (long long)kChunk, nR) - i_begin) / SB);
+    // x[i..i+SB) sits at xo, the window block x[i-l0..i-l0+SB) at wo; both advance by kStep per block.
     uint32_t xo = Ring<R>::off((uint32_t)(i_begin & mask));
     uint32_t wo = Ring<R>::off((uint32_t)((i_begin - l0) & mask));
     // software pipeline: the loads of block k+1 are issued before the arithmetic of block k, so that a warp
     // that has an SM sub-partition almost to itself does not stall on shared-memory latency (the read-ahead of
     // the last block lands in the next chunk / the mirror and is discarded)
-    double xi[R], wn[R], xi_n[R], wn_n[R];
-    load_block<R>(ring, xo, xi);
-    load_block<R>(ring, wo, wn);
-#pragma unroll(R >= 4 ? 2 : 4)
+    double xi[SB], wn[SB], xi_n[SB], wn_n[SB];
+    load_block<SB, true>(ring, xo, xi);
+    load_block<SB, kWinAligned>(ring, wo, wn);
+#pragma unroll 2
     for (int k = 0; k < n_blocks; k++) {
       xo += kStep;
       wo += kStep;
-      load_block<R>(ring, xo, xi_n);
-      load_block<R>(ring, wo, wn_n);
+      load_block<SB, true>(ring, xo, xi_n);
+      load_block<SB, kWinAligned>(ring, wo, wn_n);
 #pragma unroll
-      for (int k2 = 0; k2 < R; k2++) w[R - 1 + k2] = wn[k2];
+      for (int k2 = 0; k2 < SB; k2++) w[R - 1 + k2] = wn[k2];
       // w[k] = x[i - l0 - (R-1) + k]; lag l0+r pairs x[i+di] with x[i+di-l0-r] = w[R-1 + di - r]
 #pragma unroll
-      for (int di = 0; di < R; di++)
+      for (int di = 0; di < SB; di++)
 #pragma unroll
         for (int r = 0; r < R; r++) acc[r] = __dadd_rn(acc[r], __dmul_rn(w[R - 1 + di - r], xi[di]));
 #pragma unroll
-      for (int k2 = 0; k2 < R - 1; k2++) w[k2] = w[k2 + R];
+      for (int k2 = 0; k2 < R - 1; k2++) w[k2] = w[k2 + SB];
 #pragma unroll
-      for (int k2 = 0; k2 < R; k2++) {
+      for (int k2 = 0; k2 < SB; k2++) {
         xi[k2] = xi_n[k2];
         wn[k2] = wn_n[k2];
       }
@@ -368,11 +374,25 @@ EssShape ess_pick_shape(const asm_ctx* ctx, int n_open, int lags, int lag_end, i
       if (p) p++;
     }
     if (p) R = atoi(p);
-    if (R != 8 && R != 4 && R != 2 && R != 1) R = 0;
+    if ((R != 8 && R != 4 && R != 2 && R != 1) || lags / R < 32) R = 0;
   }
   if (R == 0) {
-    const long long warps8 = (long long)n_open * (lags / 256);
-    R = (warps8 >= 4LL * ctx->sm_count) ? 8 : 4;
+    // Cost model, milliseconds per million samples on the busiest SM sub-partition.  A warp with R lags per
+    // thread issues 2R FP64 instructions per sample at one per 2.07 clocks (profiles/r01_microbench_pipes.json);
+    // `eff` is the share of issue slots left after its loads and address arithmetic (SASS instruction counts,
+    // confirmed by ncu).  A sub-partition runs ceil(warps / slots) warps, and no shape beats one dependent DADD
+    // per sample (8.3 clocks).  Stages are short-lived, so the least modelled time wins; ties go to the larger R.
+    static const int kR[4] = {8, 4, 2, 1};
+    static const double kEff[4] = {0.90, 0.82, 0.80, 0.65};
+    const double slots = 4.0 * ctx->sm_count;
+    double best = 0;
+    for (int k = 0; k < 4; k++) {
+      const int r = kR[k];
+      if (lags / r < 32) continue;
+      const double warps = (double)n_open * lags / (32.0 * r);
+      const double t = std::max(4.3, std::ceil(warps / slots) * r * 2.11 / kEff[k]);
+      if (R == 0 || t < best - 1e-9) best = t, R = r;
+    }
   }
   EssShape sh;
   sh.R = R;
@@ -453,16 +473,18 @@ static int32_t ess_run_groups(asm_ctx* ctx, EssGroup* groups, int n_groups, int3
   sc.h_counter = (int*)ctx->h_pinned;
 
   if (!(ctx->func_attr_done & kAttrEss)) {
-    ASM_CUDA(ctx, cudaFuncSetAttribute(ess_lag_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * Ring<8>::bytes(kRingMax)));
-    ASM_CUDA(ctx, cudaFuncSetAttribute(ess_lag_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * Ring<4>::bytes(kRingMax)));
-    ASM_CUDA(ctx, cudaFuncSetAttribute(ess_lag_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * Ring<2>::bytes(kRingMax)));
-    ASM_CUDA(ctx, cudaFuncSetAttribute(ess_lag_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * Ring<1>::bytes(kRingMax)));
+    int optin = 0;
+    ASM_CUDA(ctx, cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+    ASM_CUDA(ctx, cudaFuncSetAttribute(ess_lag_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+    ASM_CUDA(ctx, cudaFuncSetAttribute(ess_lag_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+    ASM_CUDA(ctx, cudaFuncSetAttribute(ess_lag_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+    ASM_CUDA(ctx, cudaFuncSetAttribute(ess_lag_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
     ctx->func_attr_done |= kAttrEss;
   }
-  int bounds[5];
+  int bounds[6];
   int n_stage;
   if (ctx->ess_adaptive) {
-    bounds[0] = 0, bounds[1] = 256, bounds[2] = 768, bounds[3] = 1792, bounds[4] = 2048, n_stage = 4;
+    bounds[0] = 0, bounds[1] = 128, bounds[2] = 256, bounds[3] = 768, bounds[4] = 1792, bounds[5] = 2048, n_stage = 5;
   } else {
     bounds[0] = 0, bounds[1] = 2048, n_stage = 1;
   }

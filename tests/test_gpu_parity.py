@@ -226,7 +226,26 @@ def test_ess_staged_equals_all_lags_and_wide_path(gpu):
         slots_f = ctx.ess_last_lag_count()
     assert bits_equal(act_a, want_act) and bits_equal(ess_a, want_ess)
     assert bits_equal(act_f, want_act) and bits_equal(ess_f, want_ess)
-    assert slots_f == n_tr * 2048 and n_tr * 256 <= slots_a < slots_f
+    assert slots_f == n_tr * 2048 and n_tr * 128 <= slots_a < slots_f
+
+
+@pytest.mark.parametrize("lags_per_thread", [8, 4, 2, 1])
+@pytest.mark.parametrize("n", [5003, 700])
+def test_ess_every_thread_shape(gpu, lags_per_thread, n, monkeypatch):
+    """Each lags-per-thread instantiation of the lag kernel (normally picked by the cost model) on its own,
+    on a ragged length, staged and unstaged."""
+    from asm_b200 import _lib as L
+    n_tr = 37
+    x = np.empty((n_tr, n))
+    for j in range(n_tr):
+        L.synth_ar1(n, [0.0, 1.0, -1e4][j % 3], [0.0, 0.5, 0.9, 0.99, 0.999][j % 5], 9100 + j, out=x[j])
+    want_act, want_ess = O.ess_batch(x)
+    monkeypatch.setenv("ASM_ESS_R", ",".join([str(lags_per_thread)] * 5))
+    with gpu.GpuContext(1) as ctx:
+        for adaptive in (True, False):
+            ctx.ess_set_adaptive(adaptive)
+            act, ess = ctx.ess_batch(x)
+            assert bits_equal(act, want_act) and bits_equal(ess, want_ess)
 
 
 def test_ess_edge_cases(gpu):

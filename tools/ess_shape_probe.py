@@ -20,7 +20,7 @@ with ThreadPoolExecutor(32) as ex:
 dev = torch.from_numpy(host).cuda()
 res = {}
 ref = None
-settings = sys.argv[1:] or ["0,0,0,0", "8,8,4,4", "8,8,8,4", "8,8,4,2", "8,8,4,1", "8,4,4,2", "8,8,2,2", "8,8,8,8", "4,4,4,4"]
+settings = sys.argv[1:] or ["0,0,0,0,0", "4,2,8,4,1", "4,4,8,4,1", "4,2,8,4,2", "4,2,8,2,1", "2,2,8,4,1", "4,2,4,4,1"]
 for setting in settings:
     os.environ["ASM_ESS_R"] = setting
     ctx.ess_set_adaptive(True)
