@@ -34,18 +34,17 @@
 
 namespace {
 
-constexpr int kChunk = 512;  // samples per cp.async group
-// Ring size in samples >= largest lag of the stage + 8 + 3*kChunk: a thread that has passed the barrier of chunk c
+constexpr int kChunkMax = 512;  // samples per cp.async group: 512, or 256 where that lets the ring be half as large
+// Ring size in samples >= largest lag of the stage + 8 + 3*chunk: a thread that has passed the barrier of chunk c
 // issues the copy of chunk c+1 while a slower thread of its group may still be reading the window of chunk c-1.
-constexpr int kRingMax = 4096;
 
 // Ring layout.  A thread reads its R new window values as R/2 16-byte loads; the 8 lanes of a quarter warp sit
 // 8*R bytes apart and must hit 8 different 16-byte bank groups.  Instead of an XOR swizzle (one LOP3 per load) the
 // ring is padded: 16 bytes after every 8 samples (R = 8: blocks 80 bytes apart, 5b mod 8 is a permutation) or after
 // every 4 samples (R = 4: half blocks 48 bytes apart, 3h mod 8 is a permutation); with 2 or 1 lags per thread a
 // quarter warp reads contiguous bytes and needs no padding.  An aligned block therefore starts at e * off(R) / R
-// bytes and its 16-byte pieces follow at immediates.  The first kChunk samples are mirrored behind the ring's end
-// so that the kChunk consecutive window blocks of one chunk never wrap: the inner loop only adds a constant to
+// bytes and its 16-byte pieces follow at immediates.  The first `chunk` samples are mirrored behind the ring's end
+// so that the consecutive window blocks of one chunk never wrap: the inner loop only adds a constant to
 // its two addresses.
 template <int R>
 struct Ring {
@@ -54,8 +53,8 @@ struct Ring {
     return e * 8u + (kPadShift ? (e >> kPadShift) * 16u : 0u);
   }
   // ring of `ring_size` samples + mirror of the first chunk + one block of read-ahead
-  __host__ __device__ static constexpr uint32_t bytes(uint32_t ring_size) {
-    return (off(ring_size + kChunk + 16) + 127u) & ~127u;
+  __host__ __device__ static constexpr uint32_t bytes(uint32_t ring_size, uint32_t chunk) {
+    return (off(ring_size + chunk + 16) + 127u) & ~127u;
   }
 };
 
@@ -92,13 +91,13 @@ template <int R>
 __global__ void __launch_bounds__(256) ess_lag_kernel(const double* __restrict__ traces, long long stride, long long n,
                                                       int lag_begin, const int* __restrict__ trace_ids, int n_open,
                                                       int lags_stride, double* __restrict__ sls, int gthreads,
-                                                      int ring_size) {
+                                                      int ring_size, int chunk) {
   extern __shared__ __align__(128) char ring_all[];
   const int group = threadIdx.x / gthreads, tid = threadIdx.x - group * gthreads, NT = gthreads;
   const int groups = blockDim.x / gthreads;
   const int idx = blockIdx.x * groups + group;
   if (idx >= n_open) return;  // whole group idle; groups synchronise among themselves only
-  const uint32_t ring_bytes = Ring<R>::bytes((uint32_t)ring_size);
+  const uint32_t ring_bytes = Ring<R>::bytes((uint32_t)ring_size, (uint32_t)chunk);
   char* ring = ring_all + (size_t)group * ring_bytes;
   const int mask = ring_size - 1;
   const uint32_t mirror_off = Ring<R>::off((uint32_t)ring_size);
@@ -118,13 +117,13 @@ __global__ void __launch_bounds__(256) ess_lag_kernel(const double* __restrict__
 
   constexpr int kRound = R >= 4 ? R : 8;  // samples per inner-loop step
   const long long nR = (n + kRound - 1) / kRound * kRound;
-  const long long n_chunks = (nR + kChunk - 1) / kChunk;
+  const long long n_chunks = (nR + chunk - 1) / chunk;
 
   auto load_chunk = [&](long long c) {
-    const long long base = c * kChunk;
-    const uint32_t e0 = (uint32_t)(base & mask);  // the chunk occupies [e0, e0 + kChunk), no wrap
+    const long long base = c * chunk;
+    const uint32_t e0 = (uint32_t)(base & mask);  // the chunk occupies [e0, e0 + chunk), no wrap
     const bool mirror = e0 == 0;
-    for (int e = tid; e < kChunk; e += NT) {
+    for (int e = tid; e < chunk; e += NT) {
       const long long i = base + e;
       char* dst = ring + Ring<R>::off(e0 + (uint32_t)e);
       if (i < n) {
@@ -159,8 +158,8 @@ __global__ void __launch_bounds__(256) ess_lag_kernel(const double* __restrict__
       cp_async_wait<0>();
     }
     group_sync();
-    const long long i_begin = c * kChunk;
-    const int n_blocks = (int)((min(i_begin + (long long)kChunk, nR) - i_begin) / SB);
+    const long long i_begin = c * chunk;
+    const int n_blocks = (int)((min(i_begin + (long long)chunk, nR) - i_begin) / SB);
     // x[i..i+SB) sits at xo, the window block x[i-l0..i-l0+SB) at wo; both advance by kStep per block.
     uint32_t xo = Ring<R>::off((uint32_t)(i_begin & mask));
     uint32_t wo = Ring<R>::off((uint32_t)((i_begin - l0) & mask));
@@ -362,7 +361,7 @@ struct EssScratch {
 // threads (one warp per SM sub-partition).  8 lags per thread halves the shared-memory traffic per flop and runs
 // at the FP64 issue rate; fewer lags per thread give more, lighter warps for the thinly populated late stages.
 struct EssShape {
-  int R, gthreads, blocks_y, groups, ring;
+  int R, gthreads, blocks_y, groups, ring, chunk;
 };
 
 EssShape ess_pick_shape(const asm_ctx* ctx, int n_open, int lags, int lag_end, int stage) {
@@ -399,7 +398,14 @@ EssShape ess_pick_shape(const asm_ctx* ctx, int n_open, int lags, int lag_end, i
   sh.gthreads = std::min(lags / R, 128);
   sh.blocks_y = lags / (sh.gthreads * R);
   sh.groups = std::max(1, 128 / sh.gthreads);
-  sh.ring = (lag_end + 8 + 3 * kChunk <= 2048) ? 2048 : kRingMax;
+  auto ring_for = [&](int chunk) {
+    int ring = 1024;
+    while (ring < lag_end + 8 + 3 * chunk) ring *= 2;
+    return ring;
+  };
+  sh.chunk = kChunkMax;
+  sh.ring = ring_for(kChunkMax);
+  if (ring_for(kChunkMax / 2) < sh.ring) sh.chunk = kChunkMax / 2, sh.ring = ring_for(kChunkMax / 2);
   return sh;
 }
 
@@ -429,8 +435,8 @@ int32_t ess_launch_stage(asm_ctx* ctx, EssGroup& g, const EssScratch& sc, const 
     dim3 grid((unsigned)((g.n_open + sh.groups - 1) / sh.groups), (unsigned)sh.blocks_y);
     LaunchScope ls(ctx, ASM_K_ESS_LAG, g.st);
 #define ASM_ESS_LAUNCH(RR)                                                                                     \
-  ess_lag_kernel<RR><<<grid, sh.groups * gthreads, (size_t)sh.groups * Ring<RR>::bytes(sh.ring), g.st>>>(      \
-      tr, stride, n_samples, b, g.ids_in, g.n_open, lags_stride, sls, gthreads, sh.ring)
+  ess_lag_kernel<RR><<<grid, sh.groups * gthreads, (size_t)sh.groups * Ring<RR>::bytes(sh.ring, sh.chunk), g.st>>>( \
+      tr, stride, n_samples, b, g.ids_in, g.n_open, lags_stride, sls, gthreads, sh.ring, sh.chunk)
     switch (R) {
       case 8: ASM_ESS_LAUNCH(8); break;
       case 4: ASM_ESS_LAUNCH(4); break;
