@@ -63,11 +63,13 @@ struct asm_ctx {
   int device = 0;
   int n_chains = 0;
   int sm_count = 0;
+  int smem_optin = 0;  // cudaDevAttrMaxSharedMemoryPerBlockOptin
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;  // side stream (ESS sum chain)
   cudaStream_t stream_copy = nullptr;  // H2D copies overlapped with compute (asm_ess_batch)
-  cudaStream_t group_stream[4] = {}, group_stream2[4] = {};   // ESS chunk groups
-  cudaEvent_t group_event[4] = {}, group_fork[4] = {}, group_join[4] = {};
+  static constexpr int kMaxGroups = 8;
+  cudaStream_t group_stream[kMaxGroups] = {}, group_stream2[kMaxGroups] = {};   // ESS chunk groups
+  cudaEvent_t group_event[kMaxGroups] = {}, group_fork[kMaxGroups] = {}, group_join[kMaxGroups] = {};
   void* h_pinned = nullptr;            // small page-locked scratch for asynchronous counters
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int32_t words = 0;  // stored row width of every chain (uint64 words)

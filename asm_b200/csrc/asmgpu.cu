@@ -185,6 +185,7 @@ int32_t asm_create(asm_ctx** out, int32_t device, int32_t n_chains) {
   ctx->device = device;
   ctx->n_chains = n_chains;
   ctx->sm_count = prop.multiProcessorCount;
+  ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
   ctx->trees.resize((size_t)n_chains);
   ctx->traces.resize((size_t)n_chains);
   {
@@ -197,7 +198,7 @@ int32_t asm_create(asm_ctx** out, int32_t device, int32_t n_chains) {
   }
   cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&ctx->stream_copy, cudaStreamNonBlocking);
-  for (int k = 0; k < 4; k++) {
+  for (int k = 0; k < asm_ctx::kMaxGroups; k++) {
     cudaStreamCreateWithFlags(&ctx->group_stream[k], cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&ctx->group_stream2[k], cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&ctx->group_event[k], cudaEventDisableTiming);
@@ -234,7 +235,7 @@ int32_t asm_destroy(asm_ctx* ctx) {
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->stream_copy) cudaStreamDestroy(ctx->stream_copy);
-  for (int k = 0; k < 4; k++) {
+  for (int k = 0; k < asm_ctx::kMaxGroups; k++) {
     if (ctx->group_stream[k]) cudaStreamDestroy(ctx->group_stream[k]);
     if (ctx->group_stream2[k]) cudaStreamDestroy(ctx->group_stream2[k]);
     if (ctx->group_event[k]) cudaEventDestroy(ctx->group_event[k]);

@@ -24,11 +24,15 @@
 // K6 ess_scan_kernel advances every still-open trace's integral and retires the traces whose loop has
 // stopped (or has reached min(n, 2000) lags).  The output is bit-identical to evaluating all lags
 // (asm_ess_set_adaptive(ctx, 0) / ASM_ESS_ADAPTIVE=0 does exactly that, in one stage).
-// ess_sum_kernel: the sequential `sum` chain, on a side stream underneath the first stage.
+// The sequential `sum` chain rides along in the first warp of each trace's first lag block (first stage).
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstdio>
 #include <cstring>
+#include <chrono>
+#include <thread>
+#include <type_traits>
 
 #include "asm_internal.h"
 
@@ -91,7 +95,7 @@ template <int R>
 __global__ void __launch_bounds__(256) ess_lag_kernel(const double* __restrict__ traces, long long stride, long long n,
                                                       int lag_begin, const int* __restrict__ trace_ids, int n_open,
                                                       int lags_stride, double* __restrict__ sls, int gthreads,
-                                                      int ring_size, int chunk) {
+                                                      int ring_size, int chunk, double* __restrict__ sums) {
   extern __shared__ __align__(128) char ring_all[];
   const int group = threadIdx.x / gthreads, tid = threadIdx.x - group * gthreads, NT = gthreads;
   const int groups = blockDim.x / gthreads;
@@ -148,16 +152,13 @@ __global__ void __launch_bounds__(256) ess_lag_kernel(const double* __restrict__
 #pragma unroll
   for (int k = 0; k < R - 1 + SB; k++) w[k] = 0.0;
 
+  // The sequential `sum` chain (TraceESS.java:137) rides along in the first warp of the trace's first lag block
+  // of the first stage: one more dependent DADD per sample in that warp, instead of a latency-bound kernel of
+  // its own whose warps would take a quarter of the FP64 issue slots of every sub-partition they sit on.
+  const bool do_sum = sums != nullptr && blockIdx.y == 0 && tid < 32;
+  double sum = 0.0;
   constexpr uint32_t kStep = Ring<R>::off(SB);  // bytes from one block of SB samples to the next
-  if (n_chunks > 0) load_chunk(0);
-  for (long long c = 0; c < n_chunks; c++) {
-    if (c + 1 < n_chunks) {
-      load_chunk(c + 1);
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    group_sync();
+  auto compute_chunk = [&](long long c, auto with_sum) {
     const long long i_begin = c * chunk;
     const int n_blocks = (int)((min(i_begin + (long long)chunk, nR) - i_begin) / SB);
     // x[i..i+SB) sits at xo, the window block x[i-l0..i-l0+SB) at wo; both advance by kStep per block.
@@ -182,6 +183,10 @@ __global__ void __launch_bounds__(256) ess_lag_kernel(const double* __restrict__
       for (int di = 0; di < SB; di++)
 #pragma unroll
         for (int r = 0; r < R; r++) acc[r] = __dadd_rn(acc[r], __dmul_rn(w[R - 1 + di - r], xi[di]));
+      if constexpr (decltype(with_sum)::value) {  // the zero padding behind sample n-1 adds +0.0 to a sum that is never -0.0
+#pragma unroll
+        for (int di = 0; di < SB; di++) sum = __dadd_rn(sum, xi[di]);
+      }
 #pragma unroll
       for (int k2 = 0; k2 < R - 1; k2++) w[k2] = w[k2 + SB];
 #pragma unroll
@@ -190,43 +195,29 @@ __global__ void __launch_bounds__(256) ess_lag_kernel(const double* __restrict__
         wn[k2] = wn_n[k2];
       }
     }
+  };
+  if (n_chunks > 0) load_chunk(0);
+  for (long long c = 0; c < n_chunks; c++) {
+    if (c + 1 < n_chunks) {
+      load_chunk(c + 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    group_sync();
+    // Two copies of the chunk loop, with and without the sum chain: a predicated-off DADD still takes its FP64
+    // issue slot, so the warps that do not carry the sum must not see those instructions at all.
+    if (do_sum)
+      compute_chunk(c, std::true_type{});
+    else
+      compute_chunk(c, std::false_type{});
   }
+  if (do_sum && tid == 0) sums[trace] = sum;
   if (l0 + R <= lags_stride) {
     double* out = sls + trace * (long long)lags_stride + l0;
 #pragma unroll
     for (int r = 0; r < R; r++) out[r] = acc[r];
   }
-}
-
-// The sequential `sum` chain (TraceESS.java:137): one warp per trace, 8 traces per block (few, fat blocks,
-// so that the lag kernel keeps its CTA slots).  The lanes stage 256 samples in shared memory while lane 0
-// adds the previous 256 in order.  Latency-bound (one dependent DADD per sample).
-constexpr int kSumWarps = 8;
-__global__ void __launch_bounds__(32 * kSumWarps) ess_sum_kernel(const double* __restrict__ traces, long long stride,
-                                                                 long long n, int n_traces, double* __restrict__ sums) {
-  __shared__ double bufs[kSumWarps][2][256];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const long long trace = (long long)blockIdx.x * kSumWarps + wid;
-  if (trace >= n_traces) return;
-  double(*buf)[256] = bufs[wid];
-  const double* __restrict__ x = traces + trace * stride;
-  double sum = 0.0;
-  int cur = 0;
-  for (int k = lane; k < 256 && k < n; k += 32) buf[0][k] = x[k];
-  __syncwarp();
-  for (long long base = 0; base < n; base += 256) {
-    const int m = (int)min(256LL, n - base);
-    const long long nb = base + 256;
-    if (lane != 0) {  // lanes 1..31 prefetch the next block while lane 0 adds
-      for (long long k = nb + lane - 1; k < nb + 256 && k < n; k += 31) buf[cur ^ 1][k - nb] = x[k];
-    } else {
-#pragma unroll 8
-      for (int k = 0; k < m; k++) sum = __dadd_rn(sum, buf[cur][k]);
-    }
-    __syncwarp();
-    cur ^= 1;
-  }
-  if (lane == 0) sums[trace] = sum;
 }
 
 // per-trace state of the integral loop carried from stage to stage
@@ -348,6 +339,12 @@ struct EssGroup {
   int stage = 0, n_open = 0;
   const int* ids_in = nullptr;
   bool done = false;
+  int bounds[8] = {0, 2048};  // stage s evaluates the lags [bounds[s], bounds[s+1])
+  int n_stage = 1;
+  void plan(std::initializer_list<int> b) {
+    n_stage = (int)b.size() - 1;
+    std::copy(b.begin(), b.end(), bounds);
+  }
 };
 
 struct EssScratch {
@@ -373,7 +370,7 @@ EssShape ess_pick_shape(const asm_ctx* ctx, int n_open, int lags, int lag_end, i
       if (p) p++;
     }
     if (p) R = atoi(p);
-    if ((R != 8 && R != 4 && R != 2 && R != 1) || lags / R < 32) R = 0;
+    if ((R != 8 && R != 4 && R != 2 && R != 1) || lags % (32 * R) != 0) R = 0;
   }
   if (R == 0) {
     // Cost model, milliseconds per million samples on the busiest SM sub-partition.  A warp with R lags per
@@ -387,7 +384,7 @@ EssShape ess_pick_shape(const asm_ctx* ctx, int n_open, int lags, int lag_end, i
     double best = 0;
     for (int k = 0; k < 4; k++) {
       const int r = kR[k];
-      if (lags / r < 32) continue;
+      if (lags % (32 * r) != 0) continue;
       const double warps = (double)n_open * lags / (32.0 * r);
       const double t = std::max(4.3, std::ceil(warps / slots) * r * 2.11 / kEff[k]);
       if (R == 0 || t < best - 1e-9) best = t, R = r;
@@ -395,7 +392,8 @@ EssShape ess_pick_shape(const asm_ctx* ctx, int n_open, int lags, int lag_end, i
   }
   EssShape sh;
   sh.R = R;
-  sh.gthreads = std::min(lags / R, 128);
+  sh.gthreads = 128;  // the widest group whose lag blocks tile the stage
+  while (sh.gthreads > 32 && (sh.gthreads * R > lags || lags % (sh.gthreads * R) != 0)) sh.gthreads /= 2;
   sh.blocks_y = lags / (sh.gthreads * R);
   sh.groups = std::max(1, 128 / sh.gthreads);
   auto ring_for = [&](int chunk) {
@@ -410,22 +408,15 @@ EssShape ess_pick_shape(const asm_ctx* ctx, int n_open, int lags, int lag_end, i
 }
 
 int32_t ess_launch_stage(asm_ctx* ctx, EssGroup& g, const EssScratch& sc, const double* d_traces, int64_t stride,
-                         int64_t n_samples, int32_t max_lag, const int* bounds, int n_stage, int lags_stride) {
+                         int64_t n_samples, int32_t max_lag, int lags_stride) {
   const long long L = std::min<long long>(n_samples, max_lag);
   const int s = g.stage;
-  const int b = bounds[s], e = bounds[s + 1];
+  const int b = g.bounds[s], e = g.bounds[s + 1];
   const double* tr = d_traces + (size_t)g.t0 * stride;
   double* sls = sc.sls + (size_t)g.t0 * lags_stride;
   if (s == 0) {
     if (g.ready) ASM_CUDA(ctx, cudaStreamWaitEvent(g.st, g.ready, 0));
     ASM_CUDA(ctx, cudaMemsetAsync(sc.state + g.t0, 0, sizeof(EssState) * (size_t)g.nt, g.st));
-    // the sequential `sum` chain runs on the group's side stream, underneath the first lag stage
-    ASM_CUDA(ctx, cudaEventRecord(g.fork, g.st));
-    ASM_CUDA(ctx, cudaStreamWaitEvent(g.st2, g.fork, 0));
-    ctx->launches++;
-    ess_sum_kernel<<<(g.nt + kSumWarps - 1) / kSumWarps, 32 * kSumWarps, 0, g.st2>>>(tr, stride, n_samples, g.nt,
-                                                                                     sc.sums + g.t0);
-    ASM_CUDA(ctx, cudaEventRecord(g.join, g.st2));
   }
   (void)L;
   const int lags = e - b;
@@ -433,10 +424,17 @@ int32_t ess_launch_stage(asm_ctx* ctx, EssGroup& g, const EssScratch& sc, const 
     const EssShape sh = ess_pick_shape(ctx, g.n_open, lags, e, s);
     const int R = sh.R, gthreads = sh.gthreads;
     dim3 grid((unsigned)((g.n_open + sh.groups - 1) / sh.groups), (unsigned)sh.blocks_y);
+    // A CTA stays where it is placed for the whole walk over the samples, and the block scheduler is free to
+    // stack the CTAs of a small grid on few SMs when other groups' kernels are resident.  Asking for just too
+    // much shared memory for one more CTA than an even spread needs keeps them apart.
+    const int per_sm = ((int)(grid.x * grid.y) + ctx->sm_count - 1) / ctx->sm_count;
+    const size_t smem_spread = std::min<size_t>((size_t)ctx->smem_optin, (size_t)ctx->smem_optin / (per_sm + 1) + 1024);
     LaunchScope ls(ctx, ASM_K_ESS_LAG, g.st);
 #define ASM_ESS_LAUNCH(RR)                                                                                     \
-  ess_lag_kernel<RR><<<grid, sh.groups * gthreads, (size_t)sh.groups * Ring<RR>::bytes(sh.ring, sh.chunk), g.st>>>( \
-      tr, stride, n_samples, b, g.ids_in, g.n_open, lags_stride, sls, gthreads, sh.ring, sh.chunk)
+  ess_lag_kernel<RR><<<grid, sh.groups * gthreads,                                                             \
+                       std::max(smem_spread, (size_t)sh.groups * Ring<RR>::bytes(sh.ring, sh.chunk)), g.st>>>(  \
+      tr, stride, n_samples, b, g.ids_in, g.n_open, lags_stride, sls, gthreads, sh.ring, sh.chunk,              \
+      s == 0 ? sc.sums + g.t0 : nullptr)
     switch (R) {
       case 8: ASM_ESS_LAUNCH(8); break;
       case 4: ASM_ESS_LAUNCH(4); break;
@@ -447,7 +445,6 @@ int32_t ess_launch_stage(asm_ctx* ctx, EssGroup& g, const EssScratch& sc, const 
     ctx->ess_lag_slots += (long long)g.n_open * lags;
   }
   ASM_CUDA(ctx, cudaGetLastError());
-  if (s == 0) ASM_CUDA(ctx, cudaStreamWaitEvent(g.st, g.join, 0));  // the scan needs the sums
   return ASM_OK;
 }
 
@@ -479,28 +476,20 @@ static int32_t ess_run_groups(asm_ctx* ctx, EssGroup* groups, int n_groups, int3
   sc.h_counter = (int*)ctx->h_pinned;
 
   if (!(ctx->func_attr_done & kAttrEss)) {
-    int optin = 0;
-    ASM_CUDA(ctx, cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+    const int optin = ctx->smem_optin;
     ASM_CUDA(ctx, cudaFuncSetAttribute(ess_lag_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
     ASM_CUDA(ctx, cudaFuncSetAttribute(ess_lag_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
     ASM_CUDA(ctx, cudaFuncSetAttribute(ess_lag_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
     ASM_CUDA(ctx, cudaFuncSetAttribute(ess_lag_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
     ctx->func_attr_done |= kAttrEss;
   }
-  int bounds[6];
-  int n_stage;
-  if (ctx->ess_adaptive) {
-    bounds[0] = 0, bounds[1] = 128, bounds[2] = 256, bounds[3] = 768, bounds[4] = 1792, bounds[5] = 2048, n_stage = 5;
-  } else {
-    bounds[0] = 0, bounds[1] = 2048, n_stage = 1;
-  }
   ctx->ess_lag_slots = 0;
 
   auto launch = [&](int gi) -> int32_t {
     EssGroup& g = groups[gi];
-    int32_t r = ess_launch_stage(ctx, g, sc, d_traces, stride, n_samples, max_lag, bounds, n_stage, lags_stride);
+    int32_t r = ess_launch_stage(ctx, g, sc, d_traces, stride, n_samples, max_lag, lags_stride);
     if (r != ASM_OK) return r;
-    const int e = bounds[g.stage + 1];
+    const int e = g.bounds[g.stage + 1];
     ASM_CUDA(ctx, cudaMemsetAsync(sc.counter + gi, 0, sizeof(int), g.st));
     {
       LaunchScope ls(ctx, ASM_K_ESS_FINISH, g.st);
@@ -525,14 +514,36 @@ static int32_t ess_run_groups(asm_ctx* ctx, EssGroup* groups, int n_groups, int3
       remaining++;
     }
   }
+  // Whichever group finishes its stage first is served first: with several groups in flight the host polls their
+  // streams instead of blocking on them in turn (a blocked host would hold back the short late stages of one
+  // group behind the long early stage of another).
+  const bool trace_on = getenv("ASM_ESS_TRACE") != nullptr;  // tuning aid: host-side timeline on stderr
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto now_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
+  bool seen_ready[asm_ctx::kMaxGroups] = {};
   while (remaining > 0) {
+    bool progressed = false;
     for (int gi = 0; gi < n_groups; gi++) {
       EssGroup& g = groups[gi];
+      if (trace_on && g.ready && !seen_ready[gi] && cudaEventQuery(g.ready) == cudaSuccess) {
+        seen_ready[gi] = true;
+        fprintf(stderr, "[ess %8.2f ms] group %d (%d traces) uploaded\n", now_ms(), gi, g.nt);
+      }
       if (g.done) continue;
-      ASM_CUDA(ctx, cudaStreamSynchronize(g.st));  // stage finished: the open count is on the host
+      if (remaining == 1) {
+        ASM_CUDA(ctx, cudaStreamSynchronize(g.st));  // nothing else to serve: block
+      } else {
+        const cudaError_t q = cudaStreamQuery(g.st);
+        if (q == cudaErrorNotReady) continue;
+        ASM_CUDA(ctx, q);
+      }
+      progressed = true;  // stage finished: the open count is on the host
       const int cnt = sc.h_counter[gi];
+      if (trace_on)
+        fprintf(stderr, "[ess %8.2f ms] group %d stage %d [%d,%d) done, %d of %d traces still open\n", now_ms(), gi, g.stage,
+                g.bounds[g.stage], g.bounds[g.stage + 1], cnt, g.n_open);
       const int next = g.stage + 1;
-      if (next < n_stage && cnt > 0 && bounds[next] < L) {
+      if (next < g.n_stage && cnt > 0 && g.bounds[next] < L) {
         g.ids_in = sc.ids[g.stage & 1] + g.t0;
         g.n_open = cnt;
         g.stage = next;
@@ -548,6 +559,7 @@ static int32_t ess_run_groups(asm_ctx* ctx, EssGroup* groups, int n_groups, int3
                                         cudaMemcpyDeviceToHost, g.st));
       }
     }
+    if (!progressed) std::this_thread::sleep_for(std::chrono::microseconds(20));
   }
   for (int gi = 0; gi < n_groups; gi++) ASM_CUDA(ctx, cudaStreamSynchronize(groups[gi].st));
   return ASM_OK;
@@ -562,6 +574,7 @@ int32_t ess_batch_device(asm_ctx* ctx, int32_t n_traces, int64_t n_samples, int6
   g.st2 = ctx->stream2;
   g.fork = ctx->ev_fork;
   g.join = ctx->ev_join;
+  if (ctx->ess_adaptive) g.plan({0, 128, 256, 768, 1792, 2048});
   return ess_run_groups(ctx, &g, 1, n_traces, n_samples, stride, d_traces, max_lag, act_out_host, ess_out_host);
 }
 
@@ -571,12 +584,59 @@ int32_t ess_batch_host(asm_ctx* ctx, int32_t n_traces, int64_t n_samples, int64_
                        int64_t n_pad, double* d_tr, int32_t max_lag, double* act_out_host, double* ess_out_host) {
   int n_groups = 1;
   if (n_traces >= 512 && (int64_t)n_traces * n_pad * 8 >= (1LL << 30)) n_groups = 4;
-  EssGroup groups[4];
-  const int chunk = (n_traces + n_groups - 1) / n_groups;
+  if (const char* env = getenv("ASM_ESS_H2D_GROUPS")) {  // tuning aid
+    const int v = atoi(env);
+    if (v >= 1 && v <= asm_ctx::kMaxGroups) n_groups = v;
+  }
+  EssGroup groups[asm_ctx::kMaxGroups];
+  // Chunk plan.  The upload (PCIe) is the long pole, so the chunks that land last are on the critical path.  Every
+  // stage costs at least one walk of its slowest warp over all samples, however few traces it has, so the last
+  // two chunks are small and use two wide stages (twice the lag sums of the five-stage plan, but for few traces);
+  // the early chunks are large and get the full five-stage plan, whose latency hides under the rest of the upload.
+  int sizes[asm_ctx::kMaxGroups];
+  const bool tapered = n_groups == 4 && !getenv("ASM_ESS_H2D_GROUPS") && ctx->ess_adaptive;
+  if (tapered) {
+    const int one_wave = std::max(8, (4 * ctx->sm_count / 8) & ~7);
+    sizes[3] = std::min(one_wave, n_traces / 8);
+    sizes[2] = std::min(2 * one_wave, n_traces / 4);
+    sizes[1] = n_traces / 4;
+    sizes[0] = n_traces - sizes[1] - sizes[2] - sizes[3];
+  } else {
+    const int chunk = (n_traces + n_groups - 1) / n_groups;
+    for (int k = 0; k < n_groups; k++) sizes[k] = std::max(0, std::min(chunk, n_traces - k * chunk));
+  }
+  int codes[asm_ctx::kMaxGroups];
+  for (int k = 0; k < n_groups; k++) codes[k] = (tapered && k >= 2) ? 2 : 5;
+  if (const char* env = getenv("ASM_ESS_H2D_PLAN")) {  // tuning aid: "traces:stages,traces:stages,..." (last takes the rest)
+    int k = 0, used = 0;
+    for (const char* q = env; q && *q && k < asm_ctx::kMaxGroups; k++) {
+      int m = 0, c = 5;
+      if (sscanf(q, "%d:%d", &m, &c) < 1) break;
+      sizes[k] = std::max(0, std::min(m, n_traces - used));
+      codes[k] = c;
+      used += sizes[k];
+      q = strchr(q, ',');
+      if (q) q++;
+    }
+    if (k > 0) {
+      sizes[k - 1] += n_traces - used;
+      n_groups = k;
+    }
+  }
+  int t0 = 0;
   for (int k = 0; k < n_groups; k++) {
     EssGroup& g = groups[k];
-    g.t0 = k * chunk;
-    g.nt = std::max(0, std::min(chunk, n_traces - g.t0));
+    g.t0 = t0;
+    g.nt = sizes[k];
+    t0 += sizes[k];
+    if (ctx->ess_adaptive) {
+      switch (codes[k]) {
+        case 1: g.plan({0, 2048}); break;
+        case 2: g.plan({0, 256, 2048}); break;
+        case 3: g.plan({0, 128, 512, 2048}); break;
+        default: g.plan({0, 128, 256, 768, 1792, 2048}); break;
+      }
+    }
     g.st = ctx->group_stream[k];
     g.st2 = ctx->group_stream2[k];
     g.ready = ctx->group_event[k];

@@ -6,7 +6,7 @@ import asm_b200 as A
 from asm_b200 import _lib as L
 import bench
 from concurrent.futures import ThreadPoolExecutor
-n_tr, n = 1000, 1_000_000
+n_tr, n = (int(sys.argv[1]) if len(sys.argv) > 1 else 1000), 1_000_000
 ctx = A.GpuContext(1)
 host = np.empty((n_tr, n))
 def one(j):
