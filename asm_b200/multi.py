@@ -4,7 +4,8 @@ PSRF: the tile pairs of the symmetric distance matrix are dealt round-robin to t
 (asm_shard); each rank produces a partial S table of exact int64 sums; ONE all-reduce (ncclSum on
 int64 is exact in any order) gives every rank the full table; the per-row PSRF values
 and the reference-order sequential means are then computed locally.  The operand (bit rows of every
-chain) is replicated on every rank.
+chain) is replicated on every rank: `trees_set_sharded` sends each row over PCIe once per job (rank r
+uploads the r-th slice of every chain) and replicates it with one all-gather over NVLink.
 
 ESS: traces are independent, so trace j goes to rank j % world; the ESS vector is all-gathered and
 the min is taken on the host with Java's NaN-propagating Math.min (TraceESS.java:63) -- NCCL's
@@ -44,6 +45,45 @@ def psrf_eval_multi(ctx, dist, burnin: Sequence[int], row_start: int, end: int, 
         if S.is_cuda:
             torch.cuda.current_stream(S.device).synchronize()  # the library works on its own stream
     return ctx.psrf_finish_device(S.data_ptr(), n_rows, want_rows=want_rows), S
+
+
+def gather_tree_shards(dist, bits_per_chain, device):
+    """bits_per_chain[c]: the whole [n_c][words] uint64 bit-row matrix of chain c in (pinned) host memory, as a
+    numpy array or a torch tensor, identical on every rank.  Rank r copies rows [r*per_c, (r+1)*per_c) of every
+    chain to its device; ONE all-gather hands every rank every slice.  Returns one [n_c][words] int64 device
+    tensor per chain (bit patterns unchanged)."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    src = []
+    for b in bits_per_chain:
+        t = b if isinstance(b, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(b).view(np.int64))
+        src.append(t.view(torch.int64) if t.dtype != torch.int64 else t)
+    words = src[0].shape[1] if src else 0
+    per = [(t.shape[0] + world - 1) // world for t in src]
+    slot = sum(per)  # rows every rank contributes (short slices are zero-padded)
+    full = torch.zeros((world, max(slot, 1), max(words, 1)), dtype=torch.int64, device=device)
+    mine = full[rank]
+    off = 0
+    for t, p in zip(src, per):
+        lo, hi = min(rank * p, t.shape[0]), min((rank + 1) * p, t.shape[0])
+        if hi > lo:
+            mine[off:off + hi - lo].copy_(t[lo:hi], non_blocking=True)
+        off += p
+    dist.all_gather(list(full.unbind(0)), mine.clone())
+    out, off = [], 0
+    for t, p in zip(src, per):
+        out.append(full[:, off:off + p].reshape(world * p, max(words, 1))[: t.shape[0]].contiguous())
+        off += p
+    return out
+
+
+def trees_set_sharded(ctx, dist, bits_per_chain, device):
+    """asm_trees_set for every chain with the host->device traffic divided by the world size."""
+    full = gather_tree_shards(dist, bits_per_chain, device)
+    if full and full[0].is_cuda:
+        torch.cuda.current_stream(full[0].device).synchronize()  # the library copies on its own stream
+    for c, t in enumerate(full):
+        ctx.trees_set_device(c, t.data_ptr(), t.shape[0], t.shape[1])
+    return full
 
 
 def my_traces(n_traces: int, rank: int, world: int):

@@ -43,6 +43,10 @@ class StandInCtx:
         part[mask] = full[mask]
         self._view(d_S_ptr, (C, n, C), np.int64)[...] = part
 
+    def trees_set_device(self, chain, d_ptr, n_trees, words):
+        self.trees = getattr(self, "trees", {})
+        self.trees[chain] = self._view(d_ptr, (n_trees, words), np.uint64).copy()
+
     def psrf_finish_device(self, d_S_ptr, n_rows, want_rows=False):
         C = self.n_chains
         S = self._view(d_S_ptr, (C, max(n_rows, 1), C), np.int64)[:, :n_rows, :].astype(np.float64)
@@ -75,6 +79,14 @@ def _worker(rank, world, port, q):
             for b in range(3):
                 if a != b:
                     ok &= mean[a, b] == ch.ts.psrf_rows_mean(a, b, start, burnin, end, delta)
+        # sharded upload: ragged row counts (odd, smaller than the world, empty), bit patterns with the top bit set
+        rng = np.random.default_rng(5)
+        bits = [rng.integers(0, 2**64, size=(n, 3), dtype=np.uint64) for n in (7, 1, 0)]
+        multi.trees_set_sharded(ctx, dist, bits, "cpu")
+        ok &= all(np.array_equal(ctx.trees[c], bits[c]) for c in range(3))
+        pinned = [torch.from_numpy(b.copy()) for b in bits]  # uint64 tensors, as bench.py passes them
+        full = multi.gather_tree_shards(dist, pinned, "cpu")
+        ok &= all(np.array_equal(full[c].numpy().view(np.uint64), bits[c]) for c in range(3))
         # ESS: 5 traces over 2 ranks, one of them constant (NaN)
         rng = np.random.default_rng(0)
         x = rng.normal(size=(5, 400))
