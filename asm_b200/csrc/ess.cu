@@ -375,18 +375,21 @@ EssShape ess_pick_shape(const asm_ctx* ctx, int n_open, int lags, int lag_end, i
   if (R == 0) {
     // Cost model, milliseconds per million samples on the busiest SM sub-partition.  A warp with R lags per
     // thread issues 2R FP64 instructions per sample at one per 2.07 clocks (profiles/r01_microbench_pipes.json);
-    // `eff` is the share of issue slots left after its loads and address arithmetic (SASS instruction counts,
-    // confirmed by ncu).  A sub-partition runs ceil(warps / slots) warps, and no shape beats one dependent DADD
-    // per sample (8.3 clocks).  Stages are short-lived, so the least modelled time wins; ties go to the larger R.
+    // `eff` is the share of the FP64 issue rate it reaches (ncu, profiles/r01_ncu_ess_lag_padded_ring_summary.md).
+    // A sub-partition runs ceil(warps / slots) warps.  With 1 or 2 lags per thread a warp is bound by the latency
+    // of its dependent adds, not by issue: measured 8.0-8.4 ms per million samples however few warps run (one floor
+    // for both, so that the 2-lag shape with half the warps and loads wins the tie).
+    // Stages are short-lived, so the least modelled time wins; ties go to the larger R.
     static const int kR[4] = {8, 4, 2, 1};
-    static const double kEff[4] = {0.90, 0.82, 0.80, 0.65};
+    static const double kEff[4] = {0.85, 0.76, 0.70, 0.65};
+    static const double kFloor[4] = {0.0, 0.0, 8.4, 8.4};
     const double slots = 4.0 * ctx->sm_count;
     double best = 0;
     for (int k = 0; k < 4; k++) {
       const int r = kR[k];
       if (lags % (32 * r) != 0) continue;
       const double warps = (double)n_open * lags / (32.0 * r);
-      const double t = std::max(4.3, std::ceil(warps / slots) * r * 2.11 / kEff[k]);
+      const double t = std::max(kFloor[k], std::ceil(warps / slots) * r * 2.11 / kEff[k]);
       if (R == 0 || t < best - 1e-9) best = t, R = r;
     }
   }
