@@ -339,7 +339,7 @@ struct EssGroup {
   int stage = 0, n_open = 0;
   const int* ids_in = nullptr;
   bool done = false;
-  int bounds[8] = {0, 2048};  // stage s evaluates the lags [bounds[s], bounds[s+1])
+  int bounds[12] = {0, 2048};  // stage s evaluates the lags [bounds[s], bounds[s+1]); a stage may be narrowed
   int n_stage = 1;
   void plan(std::initializer_list<int> b) {
     n_stage = (int)b.size() - 1;
@@ -361,38 +361,8 @@ struct EssShape {
   int R, gthreads, blocks_y, groups, ring, chunk;
 };
 
-EssShape ess_pick_shape(const asm_ctx* ctx, int n_open, int lags, int lag_end, int stage) {
-  int R = 0;
-  if (const char* env = getenv("ASM_ESS_R")) {  // tuning aid: "R0,R1,R2,R3" per stage, 0 = automatic
-    const char* p = env;
-    for (int k = 0; k < stage && p; k++) {
-      p = strchr(p, ',');
-      if (p) p++;
-    }
-    if (p) R = atoi(p);
-    if ((R != 8 && R != 4 && R != 2 && R != 1) || lags % (32 * R) != 0) R = 0;
-  }
-  if (R == 0) {
-    // Cost model, milliseconds per million samples on the busiest SM sub-partition.  A warp with R lags per
-    // thread issues 2R FP64 instructions per sample at one per 2.07 clocks (profiles/r01_microbench_pipes.json);
-    // `eff` is the share of the FP64 issue rate it reaches (ncu, profiles/r01_ncu_ess_lag_padded_ring_summary.md).
-    // A sub-partition runs ceil(warps / slots) warps.  With 1 or 2 lags per thread a warp is bound by the latency
-    // of its dependent adds, not by issue: measured 8.0-8.4 ms per million samples however few warps run (one floor
-    // for both, so that the 2-lag shape with half the warps and loads wins the tie).
-    // Stages are short-lived, so the least modelled time wins; ties go to the larger R.
-    static const int kR[4] = {8, 4, 2, 1};
-    static const double kEff[4] = {0.85, 0.76, 0.70, 0.65};
-    static const double kFloor[4] = {0.0, 0.0, 8.4, 8.4};
-    const double slots = 4.0 * ctx->sm_count;
-    double best = 0;
-    for (int k = 0; k < 4; k++) {
-      const int r = kR[k];
-      if (lags % (32 * r) != 0) continue;
-      const double warps = (double)n_open * lags / (32.0 * r);
-      const double t = std::max(kFloor[k], std::ceil(warps / slots) * r * 2.11 / kEff[k]);
-      if (R == 0 || t < best - 1e-9) best = t, R = r;
-    }
-  }
+// groups, grid rows and ring of a stage of `lags` lags ending at `lag_end`, R lags per thread
+EssShape ess_shape_for(int R, int lags, int lag_end) {
   EssShape sh;
   sh.R = R;
   sh.gthreads = 128;  // the widest group whose lag blocks tile the stage
@@ -410,6 +380,59 @@ EssShape ess_pick_shape(const asm_ctx* ctx, int n_open, int lags, int lag_end, i
   return sh;
 }
 
+// Picks the shape of the stage that starts at lag `lag_begin` and is planned to end at `*lag_end`.  May move
+// `*lag_end` down (see below); the caller evaluates [lag_begin, *lag_end) and leaves the rest to the next stage.
+EssShape ess_pick_shape(const asm_ctx* ctx, int n_open, int lag_begin, int* lag_end, int stage, bool can_narrow, bool last) {
+  const int lags = *lag_end - lag_begin;
+  int R = 0, width = lags;
+  if (const char* env = getenv("ASM_ESS_R")) {  // tuning aid: "R0,R1,R2,R3" per stage, 0 = automatic
+    const char* p = env;
+    for (int k = 0; k < stage && p; k++) {
+      p = strchr(p, ',');
+      if (p) p++;
+    }
+    if (p) R = atoi(p);
+    if ((R != 8 && R != 4 && R != 2 && R != 1) || lags % (32 * R) != 0) R = 0;
+  }
+  if (R == 0) {
+    // Cost model, milliseconds per million samples on the busiest SM sub-partition.  A warp with R lags per
+    // thread issues 2R FP64 instructions per sample at one per 2.07 clocks (profiles/r01_microbench_pipes.json);
+    // `eff` is the share of the FP64 issue rate it reaches (ncu, profiles/r01_ncu_ess_lag_padded_ring_summary.md).
+    // A sub-partition runs ceil(warps / slots) warps.  With 1 or 2 lags per thread a warp is bound by the latency
+    // of its dependent adds, not by issue: measured 8.0-8.4 ms per million samples however few warps run (one floor
+    // for both, so that the 2-lag shape with half the warps and loads wins the tie).
+    // Stages are short-lived, so the least modelled time wins; ties go to the larger R.
+    //
+    // Wave cliff: a warp stays on its sub-partition for the whole walk, so a stage with a few warps more than
+    // slots takes twice as long as one with a few less.  When an R needs two or more waves for the planned
+    // width but at least half of that width fits in one, the narrower stage is a candidate too (at a small
+    // handicap); the lags it drops are picked up by the next stage, which has fewer traces.
+    static const int kR[4] = {8, 4, 2, 1};
+    static const double kEff[4] = {0.85, 0.76, 0.70, 0.65};
+    static const double kFloor[4] = {0.0, 0.0, 8.4, 8.4};
+    const double slots = 4.0 * ctx->sm_count;
+    double best = 0;
+    for (int k = 0; k < 4; k++) {
+      const int r = kR[k];
+      if (lags % (32 * r) != 0) continue;
+      const double warps = (double)n_open * lags / (32.0 * r);
+      const double waves = std::ceil(warps / slots);
+      const double t = std::max(kFloor[k], waves * r * 2.11 / kEff[k]);
+      if (R == 0 || t < best - 1e-9) best = t, R = r, width = lags;
+      if (can_narrow && waves >= 2 && n_open > 0) {
+        const int one_wave = (int)(slots / n_open) * 32 * r;  // widest stage of this R that is a single wave
+        if (one_wave >= 32 * r && 2 * one_wave >= lags) {
+          // handicap: the dropped lags cost the next stage little, unless a stage has to be added for them
+          const double t1 = std::max(kFloor[k], r * 2.11 / kEff[k]) + (last ? 9.0 : 1.0);
+          if (t1 < best - 1e-9) best = t1, R = r, width = one_wave;
+        }
+      }
+    }
+  }
+  *lag_end = lag_begin + width;
+  return ess_shape_for(R, width, *lag_end);
+}
+
 int32_t ess_launch_stage(asm_ctx* ctx, EssGroup& g, const EssScratch& sc, const double* d_traces, int64_t stride,
                          int64_t n_samples, int32_t max_lag, int lags_stride) {
   const long long L = std::min<long long>(n_samples, max_lag);
@@ -422,9 +445,19 @@ int32_t ess_launch_stage(asm_ctx* ctx, EssGroup& g, const EssScratch& sc, const 
     ASM_CUDA(ctx, cudaMemsetAsync(sc.state + g.t0, 0, sizeof(EssState) * (size_t)g.nt, g.st));
   }
   (void)L;
-  const int lags = e - b;
   if (n_samples > 0) {
-    const EssShape sh = ess_pick_shape(ctx, g.n_open, lags, e, s);
+    int e_fit = e;
+    const bool last = s + 1 == g.n_stage;
+    const bool room = g.n_stage + 2 <= (int)(sizeof(g.bounds) / sizeof(g.bounds[0]));
+    const EssShape sh = ess_pick_shape(ctx, g.n_open, b, &e_fit, s, ctx->ess_adaptive && (!last || room), last);
+    if (e_fit < e) {  // narrowed to a single wave: the next stage starts where this one stops
+      if (last) {     // ... and if there was none, one is added for the rest
+        g.bounds[g.n_stage + 1] = g.bounds[g.n_stage];
+        g.n_stage++;
+      }
+      g.bounds[s + 1] = e_fit;
+    }
+    const int lags = g.bounds[s + 1] - b;
     const int R = sh.R, gthreads = sh.gthreads;
     dim3 grid((unsigned)((g.n_open + sh.groups - 1) / sh.groups), (unsigned)sh.blocks_y);
     // A CTA stays where it is placed for the whole walk over the samples, and the block scheduler is free to

@@ -248,6 +248,25 @@ def test_ess_every_thread_shape(gpu, lags_per_thread, n, monkeypatch):
             assert bits_equal(act, want_act) and bits_equal(ess, want_ess)
 
 
+def test_ess_narrowed_stage(gpu):
+    """More open traces in a late stage than one wave of warps holds (148 SMs x 4 sub-partitions): the stage is
+    narrowed to a single wave and the next one picks up the rest.  Same bits as the oracle and as all lags."""
+    from asm_b200 import _lib as L
+    n_tr, n = 130, 2500
+    x = np.empty((n_tr, n))
+    for j in range(n_tr):
+        L.synth_ar1(n, 0.0, 0.9995 if j < 100 else 0.3, 7300 + j, out=x[j])
+    want_act, want_ess = O.ess_batch(x)
+    with gpu.GpuContext(1) as ctx:
+        act, ess = ctx.ess_batch(x)
+        used = ctx.ess_last_lag_count()
+        ctx.ess_set_adaptive(False)
+        act_f, ess_f = ctx.ess_batch(x)
+    assert bits_equal(act, want_act) and bits_equal(ess, want_ess)
+    assert bits_equal(act_f, want_act) and bits_equal(ess_f, want_ess)
+    assert used < n_tr * 2048
+
+
 def test_ess_edge_cases(gpu):
     with gpu.GpuContext(1) as ctx:
         act, ess = ctx.ess_batch(np.full((2, 100), 3.25))  # constant trace: ac[0] = 0 -> NaN
