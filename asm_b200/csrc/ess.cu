@@ -405,7 +405,7 @@ EssShape ess_pick_shape(const asm_ctx* ctx, int n_open, int lag_begin, int* lag_
     //
     // Wave cliff: a warp stays on its sub-partition for the whole walk, so a stage with a few warps more than
     // slots takes twice as long as one with a few less.  When an R needs two or more waves for the planned
-    // width but at least half of that width fits in one, the narrower stage is a candidate too (at a small
+    // width but at least three quarters of that width fit in one, the narrower stage is a candidate too (at a small
     // handicap); the lags it drops are picked up by the next stage, which has fewer traces.
     static const int kR[4] = {8, 4, 2, 1};
     static const double kEff[4] = {0.85, 0.76, 0.70, 0.65};
@@ -421,7 +421,7 @@ EssShape ess_pick_shape(const asm_ctx* ctx, int n_open, int lag_begin, int* lag_
       if (R == 0 || t < best - 1e-9) best = t, R = r, width = lags;
       if (can_narrow && waves >= 2 && n_open > 0) {
         const int one_wave = (int)(slots / n_open) * 32 * r;  // widest stage of this R that is a single wave
-        if (one_wave >= 32 * r && 2 * one_wave >= lags) {
+        if (one_wave >= 32 * r && 4 * one_wave >= 3 * lags) {
           // handicap: the dropped lags cost the next stage little, unless a stage has to be added for them
           const double t1 = std::max(kFloor[k], r * 2.11 / kEff[k]) + (last ? 9.0 : 1.0);
           if (t1 < best - 1e-9) best = t1, R = r, width = one_wave;
