@@ -4,6 +4,7 @@ defaults are the reference's."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Sequence
 
 import numpy as np
@@ -41,6 +42,8 @@ HOST_SIGNATURES = {
     "asmh_tree_psrf_state": (_i32, [_p, _i32p, _i32p, _i32p, _p, _i32, _i32p]),
     "asmh_trace_ess_current": (_i32, [_p, _p, _i32, _i32p, C.POINTER(_f64)]),
     "asmh_criterion_last_log": (C.c_char_p, [_p]),
+    "asmh_combine_logs": (_i32, [_i32, _i32, C.POINTER(C.c_char_p), _p, _i32, _i64, C.c_char_p, C.c_char_p, C.c_char_p,
+                                 C.POINTER(_i64)]),
 }
 
 _bound = False
@@ -234,3 +237,19 @@ class CladeDifference(_Criterion):
         v = C.c_double()
         _check(_h().asmh_criterion_last_value(self._c, C.byref(v)))
         return v.value
+
+
+def combine_logs(tree_mode: bool, chain_paths: Sequence[str], burnin: Sequence[int], last_reported: int,
+                 sample_delta: int, out_path: str, header: str = None, footer: str = None) -> int:
+    """AutoStopMCMC.combinelogs for one logger (AutoStopMCMC.java:247-317): the samples [burnin[i], last_reported)
+    of every chain's log, renumbered 0, sample_delta, ... into out_path.  `header`/`footer` stand for what BEAST's
+    Logger prints around them.  Returns the number of samples written; a chain file that ends early raises
+    AsmGpuError(ASM_E_RANGE) (the reference's NullPointerException) and leaves out_path alone."""
+    n = len(chain_paths)
+    paths = (C.c_char_p * max(n, 1))(*[os.fsencode(p) for p in chain_paths])
+    b = np.ascontiguousarray(burnin, dtype=np.int32)
+    lines = C.c_int64()
+    _check(_h().asmh_combine_logs(1 if tree_mode else 0, n, paths, b.ctypes.data_as(_p), int(last_reported),
+                                  int(sample_delta), None if header is None else header.encode(),
+                                  None if footer is None else footer.encode(), os.fsencode(out_path), C.byref(lines)))
+    return lines.value

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <fstream>
 #include <sstream>
 
 #include "../../include/asm_criteria.hpp"
@@ -600,6 +601,98 @@ struct asmh_criterion {
   CladeDifference* cd = nullptr;
 };
 
+
+// ---- AutoStopMCMC.combinelogs (AutoStopMCMC.java:247-317) ------------------------------------------------------
+// The output format on the far side of the path: once the criteria have agreed, the post-burn-in samples of every
+// chain's log are appended to one file and renumbered 0, delta, 2*delta, ...  BEAST's Logger (un-vendored) writes
+// the header (logger.init(), :254) and the footer; here the caller passes both as text.
+namespace {
+
+// BufferedReader.readLine: a line ends at \n, \r or \r\n; returns false at end of stream (Java: null)
+bool java_read_line(std::istream& in, std::string& out) {
+  out.clear();
+  int c = in.get();
+  if (c == EOF) return false;
+  for (; c != EOF; c = in.get()) {
+    if (c == '\n') return true;
+    if (c == '\r') {
+      if (in.peek() == '\n') in.get();
+      return true;
+    }
+    out.push_back((char)c);
+  }
+  return true;
+}
+bool java_ready(std::istream& in) { return in.peek() != EOF; }  // BufferedReader.ready() on a file
+bool is_java_space(char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\x0B' || c == '\f' || c == '\r'; }
+bool starts_with(const std::string& s, const char* p) { return s.rfind(p, 0) == 0; }
+
+// str.replaceFirst("[0-9]+\t", "") (:308): the leftmost run of digits that is followed by a tab, wherever it is
+std::string drop_first_number_tab(const std::string& s) {
+  for (size_t i = 0; i < s.size();) {
+    if (s[i] < '0' || s[i] > '9') {
+      i++;
+      continue;
+    }
+    size_t j = i;
+    while (j < s.size() && s[j] >= '0' && s[j] <= '9') j++;
+    if (j < s.size() && s[j] == '\t') return s.substr(0, i) + s.substr(j + 1);
+    i = j;
+  }
+  return s;
+}
+
+struct NullPointer : std::out_of_range {  // str.matches(...) / str.replaceFirst(...) on the null of a finished stream
+  using std::out_of_range::out_of_range;
+};
+
+}  // namespace
+
+int64_t asmgpu::combineLogs(bool treeMode, const std::vector<std::string>& chainFiles, const int* burnIn, int lastReported,
+                            int64_t sampleDelta, std::ostream& out) {
+  int64_t sampleNr = 0, written = 0;  // :252
+  for (size_t i = 0; i < chainFiles.size(); i++) {
+    std::ifstream fin(chainFiles[i], std::ios::binary);
+    if (!fin) throw std::runtime_error("FileNotFoundException: " + chainFiles[i]);
+    std::string str;
+    bool have = false;  // Java: str == null
+    if (treeMode) {
+      int skipped = 0;  // :266-272: burn-in counts trees, other lines are passed over
+      while (java_ready(fin) && skipped < burnIn[i]) {
+        have = java_read_line(fin, str);
+        if (starts_with(str, "tree STATE")) skipped++;  // str.matches("^tree STATE.*")
+      }
+      for (int j = burnIn[i]; j < lastReported; j++) {  // :276-284: one LINE per j, printed only if it is a tree
+        if (!java_read_line(fin, str)) throw NullPointer("NullPointerException: " + chainFiles[i] + " ended before sample " + std::to_string(j));
+        if (starts_with(str, "tree STATE")) {
+          if (starts_with(str, "tree STATE_")) {  // replaceAll("^tree STATE_[^\\s]*", "")
+            size_t k = 11;
+            while (k < str.size() && !is_java_space(str[k])) k++;
+            str = str.substr(k);
+          }
+          out << "tree STATE_" << sampleNr << str << "\n";
+          sampleNr += sampleDelta;
+          written++;
+        }
+      }
+    } else {
+      while (java_ready(fin) && (!have || !starts_with(str, "Sample"))) have = java_read_line(fin, str);  // :292-294
+      int skipped = 0;  // :297-301
+      while (java_ready(fin) && skipped < burnIn[i]) {
+        java_read_line(fin, str);
+        skipped++;
+      }
+      for (int j = burnIn[i]; j < lastReported; j++) {  // :305-310
+        if (!java_read_line(fin, str)) throw NullPointer("NullPointerException: " + chainFiles[i] + " ended before sample " + std::to_string(j));
+        out << sampleNr << "\t" << drop_first_number_tab(str) << "\n";
+        sampleNr += sampleDelta;
+        written++;
+      }
+    }
+  }
+  return written;
+}
+
 static thread_local std::string g_host_err;
 static int32_t host_fail(const std::exception& e) {
   g_host_err = e.what();
@@ -797,6 +890,30 @@ int32_t asmh_trace_ess_current(asmh_criterion* c, double* ess_out, int32_t cap, 
   if (min_out) *min_out = c->tess->lastMinESS;
   return ASM_OK;
 }
+int32_t asmh_combine_logs(int32_t mode, int32_t n_chains, const char* const* chain_paths, const int32_t* burnin,
+                          int32_t last_reported, int64_t sample_delta, const char* header, const char* footer,
+                          const char* out_path, int64_t* lines_out) {
+  if ((mode != 0 && mode != 1) || n_chains < 0 || (n_chains > 0 && (!chain_paths || !burnin)) || !out_path) {
+    g_host_err = "combine_logs: bad argument";
+    return ASM_E_INVALID;
+  }
+  try {
+    std::vector<std::string> files;
+    for (int i = 0; i < n_chains; i++) files.emplace_back(chain_paths[i] ? chain_paths[i] : "");
+    std::ostringstream body;  // nothing reaches out_path if a chain file ends early
+    const int64_t n = combineLogs(mode == 1, files, burnin, last_reported, sample_delta, body);
+    std::ofstream out(out_path, std::ios::binary | std::ios::trunc);
+    if (!out) throw std::runtime_error(std::string("cannot write ") + out_path);
+    if (header) out << header;
+    out << body.str();
+    if (footer) out << footer;
+    if (lines_out) *lines_out = n;
+    return ASM_OK;
+  } catch (const std::exception& e) {
+    return host_fail(e);
+  }
+}
+
 const char* asmh_criterion_last_log(asmh_criterion* c) {
   static thread_local std::string s;
   s = c->tree ? c->tree->lastLog : std::string();

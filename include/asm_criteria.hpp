@@ -17,6 +17,7 @@
 #pragma once
 #include <cstdint>
 #include <map>
+#include <ostream>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -211,5 +212,13 @@ class CladeDifference : public MCMCConvergenceCriterion {  // CladeDifference.ja
   int nChains = 0;
   double acceptedThreshold = 0.25;
 };
+
+// AutoStopMCMC.combinelogs (AutoStopMCMC.java:247-317) for one logger: appends the samples [burnIn[i],
+// lastReported) of every chain's log file to `out`, renumbered 0, sampleDelta, 2*sampleDelta, ... across the
+// chains; treeMode selects the tree-log branch (:260-285) or the trace-log branch (:287-312).  Returns the
+// number of samples written.  A file that ends early throws (the reference's NullPointerException).  The header
+// BEAST's Logger.init() prints (:254) is the caller's business.
+int64_t combineLogs(bool treeMode, const std::vector<std::string>& chainFiles, const int* burnIn, int lastReported,
+                    int64_t sampleDelta, std::ostream& out);
 
 }  // namespace asmgpu

@@ -62,6 +62,15 @@ int32_t asmh_tree_psrf_state(asmh_criterion* c, int32_t* delta, int32_t* start0,
 int32_t asmh_trace_ess_current(asmh_criterion* c, double* ess_out, int32_t cap, int32_t* n_out, double* min_out);
 const char* asmh_criterion_last_log(asmh_criterion* c);
 
+/* AutoStopMCMC.combinelogs (AutoStopMCMC.java:247-317) for one logger.  mode 0 = trace log (:287-312), 1 = tree
+ * log (:260-285).  Writes `header` (may be NULL; stands for BEAST's Logger.init(), :254), then the samples
+ * [burnin[i], last_reported) of every chain file renumbered 0, sample_delta, 2*sample_delta, ... (sample_delta =
+ * (long)(logLines[0][0].get(1) - logLines[0][0].get(0)), :253), then `footer` (may be NULL), to out_path.
+ * A chain file that ends early is the reference's NullPointerException: ASM_E_RANGE, out_path is not touched. */
+int32_t asmh_combine_logs(int32_t mode, int32_t n_chains, const char* const* chain_paths, const int32_t* burnin,
+                          int32_t last_reported, int64_t sample_delta, const char* header, const char* footer,
+                          const char* out_path, int64_t* lines_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -291,3 +291,60 @@ def clade_difference_converged(ts: "TreeSet", available: int, threshold: float =
 
 def num_threads() -> int:
     return int(lib().orc_num_threads())
+
+
+def combine_logs(tree_mode: bool, chain_paths, burnin, last_reported: int, sample_delta: int) -> str:
+    """AutoStopMCMC.combinelogs (AutoStopMCMC.java:247-317) for one logger, restated line by line with Java's
+    regular expressions; returns what `out` receives after logger.init().  Raises TypeError where the Java
+    dereferences the null of a finished stream (str.matches / str.replaceFirst, :272 / :306-308).
+    Test infrastructure only (pure Python: the files of the parity cases are small)."""
+    import io
+    import re
+
+    class Reader:  # BufferedReader over a file: readLine() splits on \n, \r, \r\n and returns None at the end
+        def __init__(self, path):
+            data = open(path, "rb").read().decode("latin-1")
+            self.lines = re.split(r"\r\n|\n|\r", data)
+            if self.lines and self.lines[-1] == "":
+                self.lines.pop()
+            self.pos = 0
+
+        def ready(self):
+            return self.pos < len(self.lines)
+
+        def read_line(self):
+            if self.pos >= len(self.lines):
+                return None
+            self.pos += 1
+            return self.lines[self.pos - 1]
+
+    out = io.StringIO()
+    sample_nr = 0  # :252
+    for i, path in enumerate(chain_paths):
+        fin = Reader(path)
+        s = None
+        if tree_mode:  # :260-285
+            skipped = 0
+            while fin.ready() and skipped < burnin[i]:
+                s = fin.read_line()
+                if re.fullmatch(r"^tree STATE.*", s):
+                    skipped += 1
+            for _ in range(burnin[i], last_reported):
+                s = fin.read_line()
+                if re.fullmatch(r"^tree STATE.*", s):  # TypeError on None = NullPointerException
+                    s = re.sub(r"^tree STATE_[^\s]*", "", s)
+                    out.write("tree STATE_" + str(sample_nr) + s + "\n")
+                    sample_nr += sample_delta
+        else:  # :287-312
+            while fin.ready() and (s is None or not s.startswith("Sample")):
+                s = fin.read_line()
+            skipped = 0
+            while fin.ready() and skipped < burnin[i]:
+                s = fin.read_line()
+                skipped += 1
+            for _ in range(burnin[i], last_reported):
+                s = fin.read_line()
+                s = re.sub(r"[0-9]+\t", "", s, count=1)  # TypeError on None = NullPointerException
+                out.write(str(sample_nr) + "\t" + s + "\n")
+                sample_nr += sample_delta
+    return out.getvalue()
