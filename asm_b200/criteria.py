@@ -42,6 +42,7 @@ HOST_SIGNATURES = {
     "asmh_tree_psrf_state": (_i32, [_p, _i32p, _i32p, _i32p, _p, _i32, _i32p]),
     "asmh_trace_ess_current": (_i32, [_p, _p, _i32, _i32p, C.POINTER(_f64)]),
     "asmh_criterion_last_log": (C.c_char_p, [_p]),
+    "asmh_burn_in": (_i32, [_p, _i32, _i32, _i32, _p]),
     "asmh_combine_logs": (_i32, [_i32, _i32, C.POINTER(C.c_char_p), _p, _i32, _i64, C.c_char_p, C.c_char_p, C.c_char_p,
                                  C.POINTER(_i64)]),
 }
@@ -237,6 +238,21 @@ class CladeDifference(_Criterion):
         v = C.c_double()
         _check(_h().asmh_criterion_last_value(self._c, C.byref(v)))
         return v.value
+
+
+class BurnInDetector:
+    """asm.inference.BurnInDetector (BurnInDetector.java): burnin[] for every converged() call."""
+
+    def __init__(self, traceInfo: "TraceInfo", strategy: str = "Automatic", burnInPercent: Optional[int] = None):
+        if strategy not in ("Automatic", "Running"):
+            raise IllegalArgumentException("burnInStrat must be Automatic or Running")
+        self._ti, self._running = traceInfo, strategy == "Running"
+        self._pct = (10 if self._running else 0) if burnInPercent is None else int(burnInPercent)  # BurnInStrategy.java:11-27
+
+    def burnIn(self, end: int):
+        out = np.zeros(self._ti.chainCount(), dtype=np.int32)
+        _check(_h().asmh_burn_in(self._ti._p, 1 if self._running else 0, self._pct, int(end), out.ctypes.data_as(_p)))
+        return out
 
 
 def combine_logs(tree_mode: bool, chain_paths: Sequence[str], burnin: Sequence[int], last_reported: int,

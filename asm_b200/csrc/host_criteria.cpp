@@ -108,6 +108,9 @@ void TraceInfo::setLabels(const std::vector<std::string>& labels) {
 void TraceInfo::addLogLine(int chain, const double* values, int n) {
   if (chain < 0 || chain >= chainCount()) throw IllegalArgumentException("chain out of range");
   GPU_CHECK(ctx_, asm_traces_append(ctx_, chain, n, 1, values));
+  if (hostLogs_.empty()) hostLogs_.resize(nLines_.size()), hostCols_.assign(nLines_.size(), 0);
+  if (hostCols_[(size_t)chain] == 0) hostCols_[(size_t)chain] = n;
+  hostLogs_[(size_t)chain].insert(hostLogs_[(size_t)chain].end(), values, values + n);  // asm_traces_append checked n
   nLines_[(size_t)chain]++;
 }
 
@@ -602,6 +605,48 @@ struct asmh_criterion {
 };
 
 
+// ---- BurnInDetector (BurnInDetector.java:12-80) ------------------------------------------------------------
+std::vector<int> asmgpu::BurnInDetector::burnIn(int end) {
+  const int chainCount = traceInfo->chainCount();
+  std::vector<int> burnin((size_t)chainCount, 0);
+  if (burnInStrat.kind == BurnInStrategy::Automatic) {
+    for (int i = 0; i < chainCount; i++) burnin[(size_t)i] = burnIn(i, end);
+  } else {
+    const double burnPercent = (double)burnInStrat.burnInPercent / 100;  // :32
+    std::fill(burnin.begin(), burnin.end(), (int)std::ceil(burnPercent * end));
+  }
+  return burnin;
+}
+
+int asmgpu::BurnInDetector::burnIn(int chainNr, int end) {
+  int maxBurnin = 0;
+  const std::vector<int>& map = traceInfo->getMap();
+  for (size_t j = 0; j < map.size(); j++) maxBurnin = std::max(burnIn(chainNr, map[j], end), maxBurnin);
+  return maxBurnin;
+}
+
+int asmgpu::BurnInDetector::burnIn(int chainNr, int col, int end) {
+  if (end > traceInfo->logCount(chainNr)) throw std::out_of_range("IndexOutOfBoundsException: burn-in past the end of the trace");
+  // mean and stdev of the last 25 % (:52-64), sequential sums as written
+  double m2 = 0, sq2 = 0;
+  const int lb = 3 * end / 4;
+  for (int i = lb; i < end; i++) m2 += traceInfo->logValue(chainNr, col, i);
+  m2 = m2 / (end - lb);
+  for (int i = lb; i < end; i++) {
+    const double d = traceInfo->logValue(chainNr, col, i);
+    sq2 += (d - m2) * (d - m2);
+  }
+  const double stdev2 = std::sqrt(sq2 / (end - lb - 1));
+  // first moving average inside m2 +/- stdev2 (:67-76)
+  for (int i = 0; i + WINDOW_SIZE < lb; i++) {
+    double sum = 0;
+    for (int j = 0; j < WINDOW_SIZE; j++) sum += traceInfo->logValue(chainNr, col, i + j);
+    sum /= WINDOW_SIZE;
+    if (m2 - stdev2 < sum && sum < m2 + stdev2) return i + WINDOW_SIZE;
+  }
+  return lb;
+}
+
 // ---- AutoStopMCMC.combinelogs (AutoStopMCMC.java:247-317) ------------------------------------------------------
 // The output format on the far side of the path: once the criteria have agreed, the post-burn-in samples of every
 // chain's log are appended to one file and renumbered 0, delta, 2*delta, ...  BEAST's Logger (un-vendored) writes
@@ -890,6 +935,19 @@ int32_t asmh_trace_ess_current(asmh_criterion* c, double* ess_out, int32_t cap, 
   if (min_out) *min_out = c->tess->lastMinESS;
   return ASM_OK;
 }
+/* BurnInDetector.burnIn(end) (BurnInDetector.java:21-36): strategy 0 = Automatic, 1 = Running(percent) */
+int32_t asmh_burn_in(asmh_trace_info* ti, int32_t strategy, int32_t percent, int32_t end, int32_t* burnin_out) {
+  if (!ti || !burnin_out || (strategy != 0 && strategy != 1) || end < 0) {
+    g_host_err = "burn_in: bad argument";
+    return ASM_E_INVALID;
+  }
+  HOST_TRY({
+    BurnInStrategy st = strategy == 1 ? BurnInStrategy::running(percent) : BurnInStrategy::automatic();
+    std::vector<int> b = BurnInDetector(TI(ti), st).burnIn(end);
+    for (size_t i = 0; i < b.size(); i++) burnin_out[i] = b[i];
+  })
+}
+
 int32_t asmh_combine_logs(int32_t mode, int32_t n_chains, const char* const* chain_paths, const int32_t* burnin,
                           int32_t last_reported, int64_t sample_delta, const char* header, const char* footer,
                           const char* out_path, int64_t* lines_out) {

@@ -62,6 +62,8 @@ class TraceInfo {  // TraceInfo.java
 
   int64_t treeCount(int chain) const { return nTrees_[(size_t)chain]; }
   int64_t logCount(int chain) const { return nLines_[(size_t)chain]; }
+  // logLines[chain][col].get(x): the host copy the burn-in detector reads (the criteria read the GPU copy)
+  double logValue(int chain, int col, int64_t x) const { return hostLogs_[(size_t)chain][(size_t)x * (size_t)hostCols_[(size_t)chain] + (size_t)col]; }
   int taxonCount() const { return nTaxa_; }
   int64_t cladeCount() const;
   asm_ctx* ctx() const { return ctx_; }
@@ -71,6 +73,8 @@ class TraceInfo {  // TraceInfo.java
   asm_encoder* enc_ = nullptr;
   int nTaxa_ = 0;
   std::vector<int64_t> nTrees_, nLines_;
+  std::vector<std::vector<double>> hostLogs_;  // [chain][line * cols + col]
+  std::vector<int> hostCols_;
   std::vector<std::string> labels_, traces_;
   std::vector<int> map_;
   bool haveMap_ = false, haveLabels_ = false;
@@ -81,6 +85,38 @@ class TraceInfo {  // TraceInfo.java
   std::vector<int32_t> idsScratch_;
   std::vector<uint64_t> bitsScratch_;
   void appendIds_(int chain);
+};
+
+// BurnInStrategy.java:3-37
+struct BurnInStrategy {
+  enum Kind { Running, Automatic } kind = Automatic;
+  int burnInPercent = 0;  // Automatic: 0; Running: 10 (DEFAULT_BURN_IN_PERCENT :11)
+  static BurnInStrategy running(int percent = 10) {
+    BurnInStrategy s;
+    s.kind = Running;
+    s.setBurnInPercent(percent);
+    return s;
+  }
+  static BurnInStrategy automatic() { return BurnInStrategy(); }
+  void setBurnInPercent(int p) {  // :30-36
+    if (p < 0 || p > 99) throw IllegalArgumentException("BurnInPercent must be between 0 and 99");
+    burnInPercent = p;
+  }
+};
+
+// BurnInDetector.java:12-80 -- supplies burnin[] to every converged() call (AutoStopMCMC.java:397-409).  Host code, as
+// in the reference: it is the caller of the path, O(end) per column per check, not part of it.
+class BurnInDetector {
+ public:
+  BurnInDetector(TraceInfo* traceInfo, BurnInStrategy burnInStrat) : traceInfo(traceInfo), burnInStrat(burnInStrat) {}
+  std::vector<int> burnIn(int end);  // :21-36
+  static constexpr int WINDOW_SIZE = 10;  // :49
+
+ private:
+  TraceInfo* traceInfo;
+  BurnInStrategy burnInStrat;
+  int burnIn(int chainNr, int end);           // :38-47
+  int burnIn(int chainNr, int col, int end);  // :51-78
 };
 
 class MCMCConvergenceCriterion {  // MCMCConvergenceCriterion.java:8-31

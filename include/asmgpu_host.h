@@ -62,6 +62,11 @@ int32_t asmh_tree_psrf_state(asmh_criterion* c, int32_t* delta, int32_t* start0,
 int32_t asmh_trace_ess_current(asmh_criterion* c, double* ess_out, int32_t cap, int32_t* n_out, double* min_out);
 const char* asmh_criterion_last_log(asmh_criterion* c);
 
+/* BurnInDetector.burnIn(end) (BurnInDetector.java:21-36), the supplier of burnin[] for every converged() call
+ * (AutoStopMCMC.java:397-409).  strategy 0 = Automatic (BurnInStrategy.java:5), 1 = Running with `percent` (0..99,
+ * default 10); burnin_out has one entry per chain.  Host code, as in the reference. */
+int32_t asmh_burn_in(asmh_trace_info* ti, int32_t strategy, int32_t percent, int32_t end, int32_t* burnin_out);
+
 /* AutoStopMCMC.combinelogs (AutoStopMCMC.java:247-317) for one logger.  mode 0 = trace log (:287-312), 1 = tree
  * log (:260-285).  Writes `header` (may be NULL; stands for BEAST's Logger.init(), :254), then the samples
  * [burnin[i], last_reported) of every chain file renumbered 0, sample_delta, 2*sample_delta, ... (sample_delta =

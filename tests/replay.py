@@ -217,6 +217,11 @@ class Replay:
         logs = self._logs_arrays(end)
         burnin = O.burnin(logs, self.map, self.strategy, self.percent, end) if end > 0 else np.zeros(self.n_chains, np.int32)
         rec = {"end": end, "burnin": burnin.tolist(), "n_trees": self.ts.num_trees(0), "n_logs": len(self.cols[0][0])}
+        if self.ti:  # the GPU side gets its burn-in from the product's BurnInDetector (BurnInDetector.java:21-36)
+            burnin_gpu = self.K.BurnInDetector(self.ti, self.strategy, self.percent).burnIn(end)
+            rec["burnin_gpu"] = burnin_gpu.tolist()
+        else:
+            burnin_gpu = burnin
         # ---- oracle ----
         conv_o = True
         if self.oracle_psrf is not None:
@@ -230,7 +235,7 @@ class Replay:
         # ---- GPU ----
         conv_g = True
         for c in self.gpu_criteria:
-            r = c.converged(burnin, end)
+            r = c.converged(burnin_gpu, end)
             conv_g &= r
             if isinstance(c, self.K.TreePSRF):
                 rec["psrf_gpu"] = (r, c.grValues.copy(), c.delta, c.start0)

@@ -59,6 +59,7 @@ def test_replay_stop_decision_identical(gpu, tmp_path, name, method):
     h = rp.history
     assert len(h) >= SCENARIOS[name]["n_samples"]
     for r in h:
+        assert r["burnin"] == r["burnin_gpu"], f"BurnInDetector differs at check {r['end']}"
         po, pg = r["psrf_oracle"], r["psrf_gpu"]
         assert po[0] == pg[0], f"TreePSRF decision differs at check {r['end']}"
         assert bits_equal(po[1], pg[1]), f"grValues differ at check {r['end']}: {po[1]} vs {pg[1]}"
