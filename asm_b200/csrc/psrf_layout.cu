@@ -131,17 +131,22 @@ __global__ void __launch_bounds__(256) compact_kernel(const __grid_constant__ Co
 
 // One block per ordered chain pair (a, b).  The per-row values are produced in parallel into shared
 // memory, then thread 0 adds them in ascending row order: the sequential sum of TreePSRF.mean
-// (TreePSRF.java:264-271).  Row value: TreePSRF.java:287-292.
-constexpr int kFinishChunk = 4096;
+// (TreePSRF.java:264-271).  Row value: TreePSRF.java:287-292.  The sum is one dependent DADD per row
+// (8.3 clocks each) and cannot be split, so it is the long pole: warps 1..7 fill the next chunk of row
+// values into the other half of the buffer while thread 0 adds the current one.
+constexpr int kFinishChunk = 2048;
 __global__ void __launch_bounds__(256) psrf_finish_kernel(const long long* __restrict__ S, int C, int n_rows,
                                                            double* __restrict__ psrf_rows,
                                                            double* __restrict__ psrf_mean) {
-  __shared__ double vals[kFinishChunk];
+  __shared__ double vals[2][kFinishChunk];
   const int a = blockIdx.x / C, b = blockIdx.x % C;
-  double sum = 0;
-  for (int r0 = 0; r0 < n_rows; r0 += kFinishChunk) {
+  const int n_chunks = (n_rows + kFinishChunk - 1) / kFinishChunk;
+  // rows [ck*kFinishChunk, ...) -> vals[ck & 1], by the threads first .. first+count-1
+  auto fill = [&](int ck, int first, int count) {
+    const int r0 = ck * kFinishChunk;
     const int n = min(kFinishChunk, n_rows - r0);
-    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+    double* dst = vals[ck & 1];
+    for (int k = (int)threadIdx.x - first; k < n; k += count) {
       const long long* row = S + ((size_t)a * n_rows + (r0 + k)) * C;
       const double varIn = (double)row[a];
       const double varBetween = (double)row[b];
@@ -151,15 +156,23 @@ __global__ void __launch_bounds__(256) psrf_finish_kernel(const long long* __res
       } else {
         psrf = sqrt(varBetween);
       }
-      vals[k] = psrf;
+      dst[k] = psrf;
       if (psrf_rows) psrf_rows[((size_t)a * n_rows + (r0 + k)) * C + b] = psrf;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
+  };
+  double sum = 0;
+  if (n_chunks > 0) fill(0, 0, blockDim.x);
+  __syncthreads();
+  for (int ck = 0; ck < n_chunks; ck++) {
+    if (threadIdx.x >= 32) {
+      if (ck + 1 < n_chunks) fill(ck + 1, 32, blockDim.x - 32);
+    } else if (threadIdx.x == 0) {
+      const double* v = vals[ck & 1];
+      const int n = min(kFinishChunk, n_rows - ck * kFinishChunk);
       int k = 0;
       for (; k + 8 <= n; k += 8) {  // loads first, then the dependent chain of 8 adds
-        const double v0 = vals[k], v1 = vals[k + 1], v2 = vals[k + 2], v3 = vals[k + 3];
-        const double v4 = vals[k + 4], v5 = vals[k + 5], v6 = vals[k + 6], v7 = vals[k + 7];
+        const double v0 = v[k], v1 = v[k + 1], v2 = v[k + 2], v3 = v[k + 3];
+        const double v4 = v[k + 4], v5 = v[k + 5], v6 = v[k + 6], v7 = v[k + 7];
         sum = __dadd_rn(sum, v0);
         sum = __dadd_rn(sum, v1);
         sum = __dadd_rn(sum, v2);
@@ -169,9 +182,9 @@ __global__ void __launch_bounds__(256) psrf_finish_kernel(const long long* __res
         sum = __dadd_rn(sum, v6);
         sum = __dadd_rn(sum, v7);
       }
-      for (; k < n; k++) sum = __dadd_rn(sum, vals[k]);
+      for (; k < n; k++) sum = __dadd_rn(sum, v[k]);
     }
-    __syncthreads();
+    __syncthreads();  // chunk ck is consumed and chunk ck+1 is complete
   }
   if (threadIdx.x == 0) psrf_mean[a * C + b] = sum / (double)n_rows;  // 0/0 = NaN for no rows, as in Java
 }
