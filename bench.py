@@ -488,7 +488,10 @@ def bench_ess(args, rank, world, local, dist, n_traces=None):
     flops_full = 2.0 * (lmax * n - lmax * (lmax - 1) / 2) * n_tr
     flops = 2.0 * slots * n  # (trace, lag) chains evaluated x n mul+add pairs (upper bound: ignores the i < lag head)
     roof = {"bound": "hbm", "achieved": 8.0 * n_tr * n / (k_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-            "frac": 8.0 * n_tr * n / (k_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None, "kernel": "ess_lag_kernel",
+            "frac": 8.0 * n_tr * n / (k_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+            "traffic": measured_traffic("ess_lag_kernel@cfg3_staged_5_launches") if world == 1 else None,
+            "traffic_note": "sum over the five staged launches of one step (each stage re-reads its open traces)",
+            "kernel": "ess_lag_kernel",
             "kernel_ms": k_ms, "finish_ms": f_ms,
             "note": "FP64-pipe bound (~500 flop/byte), not HBM bound: see fp64",
             "fp64": {"achieved_tflops": flops / (k_ms * 1e-3) / 1e12, "unit": "TFLOP/s (separate DMUL+DADD, no FMA)",
