@@ -248,6 +248,25 @@ def test_ess_every_thread_shape(gpu, lags_per_thread, n, monkeypatch):
             assert bits_equal(act, want_act) and bits_equal(ess, want_ess)
 
 
+@pytest.mark.parametrize("plan", ["20:5,10:3,8:2,4:1", "1:5,41:2", "30:1,12:5"])
+def test_ess_host_upload_groups_and_stage_plans(gpu, plan, monkeypatch):
+    """The host-pointer entry uploads in chunks, each a group on its own stream with its own stage plan
+    (five / three / two stages or all lags at once), served by a polling host loop.  Normally that engages
+    only for gigabyte inputs; ASM_ESS_H2D_PLAN forces it on a small one."""
+    from asm_b200 import _lib as L
+    n_tr, n = 42, 5003
+    x = np.empty((n_tr, n))
+    for j in range(n_tr):
+        L.synth_ar1(n, [0.0, -1e4][j % 2], [0.0, 0.5, 0.9, 0.99, 0.999][j % 5], 8800 + j, out=x[j])
+    want_act, want_ess = O.ess_batch(x)
+    monkeypatch.setenv("ASM_ESS_H2D_PLAN", plan)
+    with gpu.GpuContext(1) as ctx:
+        act, ess = ctx.ess_batch(x)
+        act_s, ess_s = ctx.ess_batch(np.ascontiguousarray(np.pad(x, ((0, 0), (0, 5))))[:, :n])  # row stride > n
+    assert bits_equal(act, want_act) and bits_equal(ess, want_ess)
+    assert bits_equal(act_s, want_act) and bits_equal(ess_s, want_ess)
+
+
 def test_ess_narrowed_stage(gpu):
     """More open traces in a late stage than one wave of warps holds (148 SMs x 4 sub-partitions): the stage is
     narrowed to a single wave and the next one picks up the rest.  Same bits as the oracle and as all lags."""
