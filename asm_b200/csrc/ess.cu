@@ -611,6 +611,15 @@ int32_t ess_batch_device(asm_ctx* ctx, int32_t n_traces, int64_t n_samples, int6
   g.fork = ctx->ev_fork;
   g.join = ctx->ev_join;
   if (ctx->ess_adaptive) g.plan({0, 128, 256, 768, 1792, 2048});
+  if (const char* env = getenv("ASM_ESS_BOUNDS")) {  // tuning aid: "0,128,256,...,2048"
+    int k = 0;
+    for (const char* q = env; q && *q && k < 10; k++) {
+      g.bounds[k] = atoi(q);
+      q = strchr(q, ',');
+      if (q) q++;
+    }
+    if (k >= 2 && g.bounds[0] == 0 && g.bounds[k - 1] == 2048) g.n_stage = k - 1;
+  }
   return ess_run_groups(ctx, &g, 1, n_traces, n_samples, stride, d_traces, max_lag, act_out_host, ess_out_host);
 }
 
