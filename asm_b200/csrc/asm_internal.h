@@ -35,8 +35,13 @@ struct PsrfLayout {
   int64_t Tp = 0;                 // padded rows, multiple of 256
   int32_t Wp = 0;                 // padded words per row, multiple of 16 (popcount operand)
   int32_t pitch8 = 0;             // bytes per row of the int8 operand, multiple of 128
-  int64_t row_pos0[ASM_MAX_CHAINS];   // padded position of output row r of chain a:
-  int64_t row_posB[ASM_MAX_CHAINS];   //   r < rowsA[a] ? row_pos0[a] + r : row_posB[a] + (r - rowsA[a])
+  int32_t pitch4 = 0;             // bytes per row of the fp4 operand (two clades per byte), multiple of 128
+  int32_t block_real = 256;       // live rows per 256-row block: 256, or 240 for the fp4 kernel (N = 240 tiles)
+  // padded position of output row r of chain a: r < rowsA[a] ? phys(segA_off[a], rowA0[a] + r)
+  //                                                          : phys(segB_off[a], rowB0[a] + r - rowsA[a]),
+  // phys(off, k) = off + (k / block_real) * 256 + k % block_real
+  int64_t segA_off[ASM_MAX_CHAINS], segB_off[ASM_MAX_CHAINS];
+  int64_t rowA0[ASM_MAX_CHAINS], rowB0[ASM_MAX_CHAINS];
   int32_t rowsA[ASM_MAX_CHAINS];
   int64_t padB[ASM_MAX_CHAINS];   // zero-padding rows inside the column segment of chain c
   int64_t tiles_total = 0, tiles_done = 0;
@@ -76,7 +81,7 @@ struct asm_ctx {
   std::vector<ChainTrees> trees;
   std::vector<ChainTraces> traces;
   // scratch
-  DevBuf opnd_bits, opnd_i8, nbits, S_pad, blk_meta, S_compact, psrf_rows, psrf_mean, misc, flush, ess_tr,
+  DevBuf opnd_bits, opnd_i8, opnd_f4, nbits, S_pad, blk_meta, S_compact, psrf_rows, psrf_mean, misc, flush, ess_tr,
       ess_sls, ess_out, tile_counter, rf_out;
   PsrfLayout layout;
   std::vector<int2> meta_host;  // staging for tile metadata
@@ -120,9 +125,11 @@ struct LaunchScope {
 
 // ---- kernels (launchers live next to their kernels) ---------------------------------------------------
 // psrf_layout.cu
-int32_t psrf_build_layout(asm_ctx* ctx, const int32_t* burnin, int32_t row_start, int32_t end, int32_t delta);
+int32_t psrf_build_layout(asm_ctx* ctx, const int32_t* burnin, int32_t row_start, int32_t end, int32_t delta,
+                          int32_t block_real = kBlockRows);
 int32_t psrf_gather_bits(asm_ctx* ctx);  // layout -> opnd_bits [Tp][Wp], nbits [Tp], blk_meta
 int32_t psrf_gather_i8(asm_ctx* ctx);    // layout -> opnd_i8 [Tp][pitch8] directly, nbits [Tp], blk_meta
+int32_t psrf_gather_f4(asm_ctx* ctx);    // layout (block_real = 240) -> opnd_f4 [Tp][pitch4] e2m1 nibbles, nbits, blk_meta
 int32_t psrf_check_max_bits(asm_ctx* ctx, int32_t limit);  // ASM_E_UNSUPPORTED if a gathered row has more set bits
 int32_t psrf_compact(asm_ctx* ctx, asm_shard shard, int64_t* d_S_out);  // S_pad -> [C][n_rows][C], pad-corrected
 int32_t psrf_finish(asm_ctx* ctx, const int64_t* d_S, int32_t n_rows, double* psrf_rows_host, double* psrf_mean_host);

@@ -21,10 +21,36 @@ struct SegTableDev {
   int32_t delta;
   int32_t words;   // stored words per source row
   int32_t Wp;      // padded words per operand row
+  int32_t block_real;  // live rows per 256-row block (256, or 240 for the fp4 operand)
   int64_t Tp;
   const uint64_t* chain_bits[ASM_MAX_CHAINS];
   Segment seg[kMaxSegments];
 };
+
+
+// padded row p -> (segment, live?, index of the tree inside the segment).  A segment is a run of 256-row blocks
+// of which the first `block_real` rows are trees and the rest zero padding.
+struct RowRef {
+  const Segment* seg;
+  bool live;
+  int64_t k;
+};
+__device__ __forceinline__ RowRef locate_row(const SegTableDev* tab, int64_t p) {
+  int lo = 0, hi = tab->n_seg - 1;
+  while (lo < hi) {  // last segment with dst_off <= p
+    int mid = (lo + hi + 1) >> 1;
+    if (tab->seg[mid].dst_off <= p) lo = mid; else hi = mid - 1;
+  }
+  const Segment& s = tab->seg[lo];
+  const int64_t j = p - s.dst_off;
+  const int64_t o = j & (kBlockRows - 1);
+  const int64_t k = (j >> 8) * tab->block_real + o;
+  RowRef r;
+  r.seg = &s;
+  r.k = k;
+  r.live = o < tab->block_real && k < s.n;
+  return r;
+}
 
 // One warp per padded row: copy (zero-extended) or zero-fill, and count the set bits.
 __global__ void __launch_bounds__(256) gather_bits_kernel(const __grid_constant__ SegTableDev tab_,
@@ -33,19 +59,13 @@ __global__ void __launch_bounds__(256) gather_bits_kernel(const __grid_constant_
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const int64_t Tp = tab->Tp;
-  const int Wp = tab->Wp, words = tab->words, delta = tab->delta, n_seg = tab->n_seg;
+  const int Wp = tab->Wp, words = tab->words, delta = tab->delta;
   for (int64_t p = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); p < Tp;
        p += (int64_t)gridDim.x * warps_per_block) {
-    // binary search: last segment with dst_off <= p
-    int lo = 0, hi = n_seg - 1;
-    while (lo < hi) {
-      int mid = (lo + hi + 1) >> 1;
-      if (tab->seg[mid].dst_off <= p) lo = mid; else hi = mid - 1;
-    }
-    const Segment& s = tab->seg[lo];
-    const int64_t j = p - s.dst_off;
-    const bool live = j < s.n;
-    const uint64_t* src = live ? tab->chain_bits[s.chain] + (size_t)(s.src_first + j * delta) * words : nullptr;
+    const RowRef rr = locate_row(tab, p);
+    const Segment& s = *rr.seg;
+    const bool live = rr.live;
+    const uint64_t* src = live ? tab->chain_bits[s.chain] + (size_t)(s.src_first + rr.k * delta) * words : nullptr;
     int cnt = 0;
     for (int w = lane; w < Wp; w += 32) {
       uint64_t v = (live && w < words) ? __ldg(src + w) : 0ULL;
@@ -66,18 +86,13 @@ __global__ void __launch_bounds__(256) gather_i8_kernel(const __grid_constant__ 
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const int64_t Tp = tab->Tp;
-  const int words = tab->words, delta = tab->delta, n_seg = tab->n_seg;
+  const int words = tab->words, delta = tab->delta;
   for (int64_t p = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); p < Tp;
        p += (int64_t)gridDim.x * warps_per_block) {
-    int lo = 0, hi = n_seg - 1;
-    while (lo < hi) {
-      int mid = (lo + hi + 1) >> 1;
-      if (tab->seg[mid].dst_off <= p) lo = mid; else hi = mid - 1;
-    }
-    const Segment& s = tab->seg[lo];
-    const int64_t j = p - s.dst_off;
-    const bool live = j < s.n;
-    const uint64_t* src = live ? tab->chain_bits[s.chain] + (size_t)(s.src_first + j * delta) * words : nullptr;
+    const RowRef rr = locate_row(tab, p);
+    const Segment& s = *rr.seg;
+    const bool live = rr.live;
+    const uint64_t* src = live ? tab->chain_bits[s.chain] + (size_t)(s.src_first + rr.k * delta) * words : nullptr;
     int cnt = 0;
     for (int w = lane; w < W8; w += 32) {
       const uint64_t v = (live && w < words) ? __ldg(src + w) : 0ULL;
@@ -94,6 +109,46 @@ __global__ void __launch_bounds__(256) gather_i8_kernel(const __grid_constant__ 
   }
 }
 
+// fp4 path: the same gather, written as e2m1 nibbles (clade k -> nibble k of the row, 1.0 = 0x2, 0.0 = 0x0; the
+// even clade in the low nibble).  One source byte becomes one 32-bit word through a 256-entry table in shared
+// memory; one 64-bit word -> 32 bytes, two 16-byte stores per lane.
+__global__ void __launch_bounds__(256) gather_f4_kernel(const __grid_constant__ SegTableDev tab_, uint4* __restrict__ out,
+                                                         int W4, int32_t* __restrict__ nbits) {
+  __shared__ uint32_t lut[256];
+  {
+    uint32_t v = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) v |= ((threadIdx.x >> k) & 1u) << (4 * k + 1);
+    lut[threadIdx.x] = v;
+  }
+  __syncthreads();
+  const SegTableDev* tab = &tab_;
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const int64_t Tp = tab->Tp;
+  const int words = tab->words, delta = tab->delta;
+  for (int64_t p = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); p < Tp;
+       p += (int64_t)gridDim.x * warps_per_block) {
+    const RowRef rr = locate_row(tab, p);
+    const Segment& s = *rr.seg;
+    const bool live = rr.live;
+    const uint64_t* src = live ? tab->chain_bits[s.chain] + (size_t)(s.src_first + rr.k * delta) * words : nullptr;
+    int cnt = 0;
+    for (int w = lane; w < W4; w += 32) {
+      const uint64_t v = (live && w < words) ? __ldg(src + w) : 0ULL;
+      cnt += __popcll(v);
+      uint4 q[2];
+      uint32_t* o = reinterpret_cast<uint32_t*>(q);
+#pragma unroll
+      for (int k = 0; k < 8; k++) o[k] = lut[(uint32_t)(v >> (8 * k)) & 0xFFu];
+      out[((size_t)p * W4 + w) * 2] = q[0];
+      out[((size_t)p * W4 + w) * 2 + 1] = q[1];
+    }
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) nbits[p] = cnt;
+  }
+}
+
 __global__ void __launch_bounds__(256) max_bits_kernel(const int32_t* __restrict__ nbits, long long n, int* __restrict__ out) {
   int m = 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -104,7 +159,9 @@ __global__ void __launch_bounds__(256) max_bits_kernel(const int32_t* __restrict
 
 struct CompactParams {
   int32_t C, n_rows, subtract_pad;
-  int64_t row_pos0[ASM_MAX_CHAINS], row_posB[ASM_MAX_CHAINS], padB[ASM_MAX_CHAINS];
+  int32_t block_real;
+  int64_t segA_off[ASM_MAX_CHAINS], segB_off[ASM_MAX_CHAINS], rowA0[ASM_MAX_CHAINS], rowB0[ASM_MAX_CHAINS];
+  int64_t padB[ASM_MAX_CHAINS];
   int32_t rowsA[ASM_MAX_CHAINS];
 };
 
@@ -119,7 +176,9 @@ __global__ void __launch_bounds__(256) compact_kernel(const __grid_constant__ Co
     int64_t ar = i / C;
     int r = (int)(ar % n_rows);
     int a = (int)(ar / n_rows);
-    int64_t p = r < prm->rowsA[a] ? prm->row_pos0[a] + r : prm->row_posB[a] + (r - prm->rowsA[a]);
+    const bool inA = r < prm->rowsA[a];
+    const int64_t k = inA ? prm->rowA0[a] + r : prm->rowB0[a] + (r - prm->rowsA[a]);
+    const int64_t p = (inA ? prm->segA_off[a] : prm->segB_off[a]) + (k / prm->block_real) * kBlockRows + k % prm->block_real;
     long long v = S_pad[p * C + c];
     if (prm->subtract_pad) {
       long long e = (long long)nbits[p] + 1;  // RF(tree, empty row) + 1
@@ -193,7 +252,8 @@ inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 
 }  // namespace
 
-int32_t psrf_build_layout(asm_ctx* ctx, const int32_t* burnin, int32_t row_start, int32_t end, int32_t delta) {
+int32_t psrf_build_layout(asm_ctx* ctx, const int32_t* burnin, int32_t row_start, int32_t end, int32_t delta,
+                          int32_t block_real) {
   PsrfLayout& L = ctx->layout;
   const int C = ctx->n_chains;
   if (delta < 1) return asm_fail(ctx, ASM_E_INVALID, "psrf: delta must be >= 1, not %d", delta);
@@ -213,6 +273,9 @@ int32_t psrf_build_layout(asm_ctx* ctx, const int32_t* burnin, int32_t row_start
   L.n_rows = end > row_start ? (end - row_start + delta - 1) / delta : 0;
   L.Wp = (int32_t)round_up(ctx->words > 0 ? ctx->words : 1, kBitsPad / 64);
   L.pitch8 = (int32_t)round_up((int64_t)(ctx->words > 0 ? ctx->words : 1) * 64, 128);  // int8 operand row pitch: whole 128-byte K blocks
+  L.pitch4 = (int32_t)round_up((int64_t)(ctx->words > 0 ? ctx->words : 1) * 32, 128);  // fp4: two clades per byte
+  L.block_real = block_real;
+  auto padded = [&](int64_t n) { return (n + block_real - 1) / block_real * kBlockRows; };  // rows a segment occupies
   if (L.n_rows == 0) return ASM_OK;
   int64_t off = 0;
   for (int c = 0; c < C; c++) {
@@ -225,19 +288,21 @@ int32_t psrf_build_layout(asm_ctx* ctx, const int32_t* burnin, int32_t row_start
     int64_t offA = off;
     if (nA > 0) {
       L.seg[L.n_seg++] = Segment{off, nA, u, c, 0};
-      off += round_up(nA, kBlockRows);
+      off += padded(nA);
     }
     int64_t offB = off;
     if (nB > 0) {
       L.seg[L.n_seg++] = Segment{off, nB, u + kq * delta, c, 1};
-      off += round_up(nB, kBlockRows);
-      L.padB[c] = round_up(nB, kBlockRows) - nB;
+      off += padded(nB);
+      L.padB[c] = padded(nB) / kBlockRows * block_real - nB;  // zero rows among the rows the kernels use as columns
     } else {
       L.padB[c] = 0;
     }
     L.rowsA[c] = (int32_t)std::max<int64_t>(0, kq - kr);
-    L.row_pos0[c] = offA + kr;
-    L.row_posB[c] = offB + std::max<int64_t>(kr - kq, 0);
+    L.segA_off[c] = offA;
+    L.segB_off[c] = offB;
+    L.rowA0[c] = kr;
+    L.rowB0[c] = std::max<int64_t>(kr - kq, 0);
   }
   L.Tp = off;
   return ASM_OK;
@@ -254,6 +319,7 @@ static int32_t psrf_prepare(asm_ctx* ctx, SegTableDev& tab) {
   tab.delta = L.delta;
   tab.words = ctx->words;
   tab.Wp = L.Wp;
+  tab.block_real = L.block_real;
   tab.Tp = L.Tp;
   for (int c = 0; c < ctx->n_chains; c++) tab.chain_bits[c] = ctx->trees[c].d_bits;
   for (int s = 0; s < L.n_seg; s++) tab.seg[s] = L.seg[s];
@@ -263,17 +329,20 @@ static int32_t psrf_prepare(asm_ctx* ctx, SegTableDev& tab) {
   meta.resize((size_t)n_tiles);
   for (int s = 0; s < L.n_seg; s++) {
     const Segment& g = L.seg[s];
-    const int64_t padded = round_up(g.n, kBlockRows);
-    // first live position (within the segment) that is an output row
+    const int64_t n_tiles_seg = (g.n + L.block_real - 1) / L.block_real * (kBlockRows / kTileRows);
+    // first tree (index within the segment) that is an output row
     int64_t first_row;
     if (!g.is_col) {
-      first_row = (L.rowsA[g.chain] > 0) ? (L.row_pos0[g.chain] - g.dst_off) : g.n;
+      first_row = (L.rowsA[g.chain] > 0) ? L.rowA0[g.chain] : g.n;
     } else {
-      first_row = L.row_posB[g.chain] - g.dst_off;
+      first_row = L.rowB0[g.chain];
       if (L.n_rows - L.rowsA[g.chain] <= 0) first_row = g.n;
     }
-    for (int64_t t = 0; t < padded / kTileRows; t++) {
-      int64_t lo = t * kTileRows, hi = std::min<int64_t>(lo + kTileRows, g.n);
+    for (int64_t t = 0; t < n_tiles_seg; t++) {
+      // trees of this 128-row tile: block t/2, rows [0,128) or [128, block_real) of it
+      const int64_t base = (t / 2) * L.block_real;
+      const int64_t lo = base + (t & 1) * kTileRows;
+      const int64_t hi = std::min<int64_t>(base + std::min<int64_t>(L.block_real, (t & 1) * kTileRows + kTileRows), g.n);
       uint32_t f = g.is_col ? kFlagCol : 0;
       if (hi > lo && hi > first_row) f |= kFlagRows;
       meta[(size_t)(g.dst_off / kTileRows + t)] = make_int2(g.chain, (int)f);
@@ -318,6 +387,21 @@ int32_t psrf_gather_i8(asm_ctx* ctx) {
   return ASM_OK;
 }
 
+int32_t psrf_gather_f4(asm_ctx* ctx) {
+  PsrfLayout& L = ctx->layout;
+  int32_t rc;
+  if ((rc = asm_reserve(ctx, ctx->opnd_f4, (size_t)L.Tp * L.pitch4)) != ASM_OK) return rc;
+  SegTableDev tab;
+  if ((rc = psrf_prepare(ctx, tab)) != ASM_OK) return rc;
+  {
+    LaunchScope ls(ctx, ASM_K_GATHER);
+    int blocks = (int)std::min<int64_t>((L.Tp + 7) / 8, (int64_t)ctx->sm_count * 16);
+    gather_f4_kernel<<<blocks, 256, 0, ctx->stream>>>(tab, (uint4*)ctx->opnd_f4.p, L.pitch4 / 32, (int32_t*)ctx->nbits.p);
+  }
+  ASM_CUDA(ctx, cudaGetLastError());
+  return ASM_OK;
+}
+
 int32_t psrf_check_max_bits(asm_ctx* ctx, int32_t limit) {
   PsrfLayout& L = ctx->layout;
   int32_t rc = asm_reserve(ctx, ctx->misc, sizeof(int));
@@ -340,10 +424,13 @@ int32_t psrf_compact(asm_ctx* ctx, asm_shard shard, int64_t* d_S_out) {
   CompactParams prm;
   prm.C = L.C;
   prm.n_rows = L.n_rows;
+  prm.block_real = L.block_real;
   prm.subtract_pad = shard.shard_index == 0 ? 1 : 0;  // the closed-form pad term is removed exactly once
   for (int c = 0; c < L.C; c++) {
-    prm.row_pos0[c] = L.row_pos0[c];
-    prm.row_posB[c] = L.row_posB[c];
+    prm.segA_off[c] = L.segA_off[c];
+    prm.segB_off[c] = L.segB_off[c];
+    prm.rowA0[c] = L.rowA0[c];
+    prm.rowB0[c] = L.rowB0[c];
     prm.padB[c] = L.padB[c];
     prm.rowsA[c] = L.rowsA[c];
   }
