@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libasmgpu.so")
 
 ASM_OK, ASM_E_INVALID, ASM_E_NO_DEVICE, ASM_E_CUDA, ASM_E_RANGE, ASM_E_NOMEM, ASM_E_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
-ASM_RF_POPC, ASM_RF_I8 = 0, 1
+ASM_RF_POPC, ASM_RF_I8, ASM_RF_FP4 = 0, 1, 2
 ASM_MAX_LAG = 2000
 K_GATHER, K_RF_POPC, K_RF_I8, K_PSRF_FINISH, K_CLADE_COUNTS, K_ESS_LAG, K_ESS_FINISH, K_MISC = range(8)
 _ERR_NAMES = {-1: "ASM_E_INVALID", -2: "ASM_E_NO_DEVICE", -3: "ASM_E_CUDA", -4: "ASM_E_RANGE", -5: "ASM_E_NOMEM",

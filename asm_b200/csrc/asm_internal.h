@@ -101,7 +101,7 @@ struct asm_ctx {
   std::string err;
 };
 
-constexpr uint32_t kAttrPopc = 1, kAttrI8 = 2, kAttrI8Dump = 4, kAttrI8x2 = 8, kAttrEss = 16;
+constexpr uint32_t kAttrPopc = 1, kAttrI8 = 2, kAttrI8Dump = 4, kAttrI8x2 = 8, kAttrEss = 16, kAttrF4x2 = 32;
 
 // ---- error plumbing ---------------------------------------------------------------------------------
 int32_t asm_fail(asm_ctx* ctx, int32_t code, const char* fmt, ...);
@@ -139,6 +139,7 @@ int32_t rf_popc_block(asm_ctx* ctx, int32_t chainA, int64_t r0, int64_t r1, int3
                       uint16_t* out_host);
 // rf_i8.cu
 int32_t rf_i8_sums(asm_ctx* ctx, asm_shard shard);
+int32_t rf_f4_sums(asm_ctx* ctx, asm_shard shard);  // block-scaled FP4 variant (layout with 240 live rows per block)
 int32_t rf_i8_block(asm_ctx* ctx, int32_t chainA, int64_t r0, int64_t r1, int32_t chainB, int64_t c0, int64_t c1,
                     uint16_t* out_host);
 // clade.cu

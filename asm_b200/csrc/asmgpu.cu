@@ -222,7 +222,7 @@ int32_t asm_destroy(asm_ctx* ctx) {
     if (t.d_bits) cudaFree(t.d_bits);
   for (auto& t : ctx->traces)
     if (t.d_vals) cudaFree(t.d_vals);
-  DevBuf* bufs[] = {&ctx->opnd_bits, &ctx->opnd_i8, &ctx->nbits, &ctx->S_pad, &ctx->blk_meta,
+  DevBuf* bufs[] = {&ctx->opnd_bits, &ctx->opnd_i8, &ctx->opnd_f4, &ctx->nbits, &ctx->S_pad, &ctx->blk_meta,
                     &ctx->S_compact, &ctx->psrf_rows, &ctx->psrf_mean, &ctx->misc, &ctx->flush, &ctx->ess_tr,
                     &ctx->ess_sls, &ctx->ess_out, &ctx->tile_counter, &ctx->rf_out, &ctx->walk_dev};
   for (DevBuf* b : bufs)
@@ -285,6 +285,7 @@ int32_t asm_rf_block(asm_ctx* ctx, int32_t chainA, int64_t r0, int64_t r1, int32
   if (r1 == r0 || c1 == c0) return ASM_OK;
   if (method == ASM_RF_POPC) return rf_popc_block(ctx, chainA, r0, r1, chainB, c0, c1, out);
   if (method == ASM_RF_I8) return rf_i8_block(ctx, chainA, r0, r1, chainB, c0, c1, out);
+  if (method == ASM_RF_FP4) return asm_fail(ctx, ASM_E_UNSUPPORTED, "rf_block: the fp4 kernel has no distance dump; use ASM_RF_I8 or ASM_RF_POPC");
   return asm_fail(ctx, ASM_E_INVALID, "rf_block: unknown method %d", method);
 }
 
@@ -300,11 +301,15 @@ static int32_t psrf_sums_impl(asm_ctx* ctx, const int32_t* burnin, int32_t row_s
                               int32_t method, asm_shard shard, int64_t* d_S_out) {
   if (shard.shard_count < 1 || shard.shard_index < 0 || shard.shard_index >= shard.shard_count)
     return asm_fail(ctx, ASM_E_INVALID, "psrf: bad shard {%d,%d}", shard.shard_index, shard.shard_count);
-  if (method != ASM_RF_POPC && method != ASM_RF_I8) return asm_fail(ctx, ASM_E_INVALID, "psrf: unknown method %d", method);
-  int32_t rc = psrf_build_layout(ctx, burnin, row_start, end, delta);
+  if (method != ASM_RF_POPC && method != ASM_RF_I8 && method != ASM_RF_FP4)
+    return asm_fail(ctx, ASM_E_INVALID, "psrf: unknown method %d", method);
+  int32_t rc = psrf_build_layout(ctx, burnin, row_start, end, delta, method == ASM_RF_FP4 ? 240 : kBlockRows);
   if (rc != ASM_OK) return rc;
   if (ctx->layout.n_rows == 0) return ASM_OK;
-  if (method == ASM_RF_I8) {
+  if (method == ASM_RF_FP4) {
+    if ((rc = psrf_gather_f4(ctx)) != ASM_OK) return rc;
+    if ((rc = rf_f4_sums(ctx, shard)) != ASM_OK) return rc;
+  } else if (method == ASM_RF_I8) {
     if ((rc = psrf_gather_i8(ctx)) != ASM_OK) return rc;
     if ((rc = rf_i8_sums(ctx, shard)) != ASM_OK) return rc;
   } else {

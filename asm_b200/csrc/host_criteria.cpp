@@ -293,7 +293,7 @@ double TreeESS::pseudoESS(int treeSet, int cutStart, int cutEnd) {  // :117-166
   std::vector<double> trace((size_t)N * (size_t)len);
   for (int j = 0; j < N; j++) {  // :139-148, one reference tree at a time
     GPU_CHECK(ctx, asm_rf_block(ctx, treeSet, indices[(size_t)j], indices[(size_t)j] + 1, treeSet, cutStart, cutEnd,
-                                methodInput, d.data()));
+                                methodInput == ASM_RF_FP4 ? ASM_RF_I8 : methodInput, d.data()));  // fp4 has no distance dump
     int k = 0;
     for (int i = cutStart; i < cutEnd && k < len; i += delta)
       trace[(size_t)j * len + k++] = (i != indices[(size_t)j]) ? (double)((float)d[(size_t)(i - cutStart)] + 1) : 0.0;

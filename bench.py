@@ -266,7 +266,7 @@ def bench_psrf(args, rank, world, local, dist):
     peaks = measured_peaks()
     cfg = CFG5 if args.workload == "cfg5" else CFG2
     n_trees = cfg["n_trees"] if args.workload == "cfg5" else int(round(cfg["n_trees"] * math.sqrt(world)))
-    method = L.ASM_RF_I8 if args.method == "i8" else L.ASM_RF_POPC
+    method = {"i8": L.ASM_RF_I8, "fp4": L.ASM_RF_FP4, "popc": L.ASM_RF_POPC}[args.method]
     C = cfg["n_chains"]
     T = C * n_trees
     enc, bits, _ = gen_psrf_input(cfg, n_trees)
@@ -340,7 +340,7 @@ def bench_psrf(args, rank, world, local, dist):
     for _ in range(1 if args.workload == "cfg5" else max(3, min(args.steps, 10))):
         ctx.flush_l2()
         step_resident()
-    fam = L.K_RF_I8 if method == L.ASM_RF_I8 else L.K_RF_POPC
+    fam = L.K_RF_POPC if method == L.ASM_RF_POPC else L.K_RF_I8  # both tensor-core kernels report under K_RF_I8
     k_ms, k_n = ctx.profile_get(fam)
     fam_ms = {name: ctx.profile_get(f)[0] / max(k_n, 1) for name, f in
               [("gather", L.K_GATHER), ("rf", fam), ("finish", L.K_PSRF_FINISH)]}
@@ -361,6 +361,17 @@ def bench_psrf(args, rank, world, local, dist):
                                f"~72% of nominal on this pool, this kernel ~86-93% of nominal int8, hence frac > 1",
                 "frac_of_nominal_int8_4500": achieved / 4500.0, "frac_of_cublaslt_int8_3626": achieved / 3626.0,
                 "algorithmic": "D*T*(T-1) int8 flop per launch (unordered pairs, 2 flop per MAC)"}
+    elif method == L.ASM_RF_FP4:
+        alg = D * T * (T - 1) / world
+        achieved = alg / (k_ms * 1e-3) / 1e12
+        peak = 4.0 * peaks["bf16_tflops"]  # fp4 dense = 4 x bf16 dense on B200; bf16 is the measured figure
+        roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": measured_traffic("rf_f4x2_kernel@cfg2") if (world == 1 and args.workload == "psrf") else None,
+                "kernel": "rf_f4x2_kernel", "kernel_ms": k_ms,
+                "peak_source": f"4 x bf16_tflops ({peaks['source']}); block-scaled fp4 dense is 4x bf16 dense on B200 (9 PFLOP/s nominal)",
+                "frac_of_nominal_fp4_9000": achieved / 9000.0,
+                "algorithmic": "D*T*(T-1) flop per launch (unordered pairs, 2 flop per MAC); e2m1 indicators, unit UE8M0 "
+                               "scales, f32 accumulators: exact"}
     else:
         # popcount variant: integer-pipe bound; HBM algorithmic bytes = operand read once + S written
         alg_bytes = (Tp * Dp / 8 + 8 * Tp * C) / world
@@ -399,7 +410,7 @@ def bench_psrf(args, rank, world, local, dist):
     line = {"metric": "tree-pairs/sec (RF+PSRF)", "value": value, "unit": "tree-pairs/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong" if args.workload == "cfg5" else "weak",
-            "vs_baseline": None, "dtype": "int8->s32 (tcgen05), int64 sums, f64 psrf" if method == L.ASM_RF_I8 else "u64 popc, int64 sums, f64 psrf",
+            "vs_baseline": None, "dtype": {L.ASM_RF_I8: "int8->s32 (tcgen05), int64 sums, f64 psrf", L.ASM_RF_FP4: "e2m1->f32 (tcgen05 mxf4, exact on 0/1), int64 sums, f64 psrf", L.ASM_RF_POPC: "u64 popc, int64 sums, f64 psrf"}[method],
             "data": "synthetic",
             "config": {"workload": f"{'cfg5' if args.workload == 'cfg5' else 'cfg2'}: {C} chains x {n_trees} trees x {cfg['n_taxa']} taxa, "
                                    f"burnin=0 smoothing=1 delta=1", "method": args.method, "clades_D": int(D),
@@ -528,7 +539,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="psrf", choices=["psrf", "ess", "cfg5"])
-    ap.add_argument("--method", default=os.environ.get("ASM_BENCH_METHOD", "i8"), choices=["i8", "popc"])
+    ap.add_argument("--method", default=os.environ.get("ASM_BENCH_METHOD", "i8"), choices=["i8", "fp4", "popc"])
     ap.add_argument("--cpu-rows", type=int, default=2048, help="row trees per chain in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ess", action="store_true", help="skip the secondary ESS block of the default run")

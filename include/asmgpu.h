@@ -44,6 +44,8 @@ extern "C" {
 /* distance-kernel selector ("method") */
 #define ASM_RF_POPC 0 /* XOR + POPC tiles on the integer pipe, bulk-async (TMA) smem staging  */
 #define ASM_RF_I8 1   /* int8 tcgen05.mma (UTCIMMA) contraction, TMA operands, TMEM accumulators */
+#define ASM_RF_FP4 2  /* the same contraction on the block-scaled FP4 path (e2m1 indicators, unit scales, f32
+                         accumulators: exact), twice the K per instruction; PSRF sums only (no asm_rf_block) */
 
 #define ASM_MAX_CHAINS 64
 #define ASM_MAX_LAG 2000 /* TraceESS.java:21 */

@@ -11,7 +11,8 @@ pytestmark = pytest.mark.gpu
 
 REL_TOL = 1e-12  # north-star tolerance for PSRF / ESS doubles; the tests below demand bit equality
 
-METHODS = [0, 1]  # ASM_RF_POPC, ASM_RF_I8
+METHODS = [0, 1, 2]  # ASM_RF_POPC, ASM_RF_I8, ASM_RF_FP4
+BLOCK_METHODS = [0, 1]  # the fp4 kernel has no distance dump
 
 
 def _ctx(gpu, chains):
@@ -21,7 +22,7 @@ def _ctx(gpu, chains):
 
 
 # ---------------------------------------------------------------- RF distances (TreeESS.java:179-180)
-@pytest.mark.parametrize("method", METHODS)
+@pytest.mark.parametrize("method", BLOCK_METHODS)
 def test_rf_block_bit_exact(gpu, multi_chains, method):
     ch = multi_chains
     with _ctx(gpu, ch) as ctx:

@@ -52,7 +52,7 @@ def test_replay_oracle_only(tmp_path, name):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("method", [0, 1])
+@pytest.mark.parametrize("method", [0, 1, 2])
 @pytest.mark.parametrize("name", list(SCENARIOS))
 def test_replay_stop_decision_identical(gpu, tmp_path, name, method):
     rp = _run(tmp_path, SCENARIOS[name], gpu_mod=gpu, method=method)
