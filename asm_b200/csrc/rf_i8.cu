@@ -769,12 +769,12 @@ rf_i8x2_kernel(const __grid_constant__ CUtensorMap tm, int nkb, const int* __res
 // =====================================================================================================
 constexpr int kTileNF = 240;
 constexpr int kSfaCol = 480, kSfbCol = 496;
-// The MMA needs half the time per tile, so the epilogue gets twice the warps: 16, four per TMEM lane quadrant,
-// each with a quarter of the 15 chunks of 16 columns.
-constexpr int kEpiWarpsF = 16;
+// The MMA needs half the time per tile, so the epilogue gets more warps: 12, three per TMEM lane quadrant,
+// each with five of the 15 chunks of 16 columns.
+constexpr int kEpiWarpsF = 12;
 constexpr int kThreadsF = 128 + kEpiWarpsF * 32;
 constexpr int kSchedConsumersF = 2 + kEpiWarpsF + 1 + kEpiWarpsF;
-constexpr uint32_t kF32Magic = 0x4B400000u;  // bits of 1.5 * 2^23: (x + 1.5*2^23) has the integer x in its low mantissa bits
+constexpr uint32_t kF32Magic = 0x4AC00000u;  // bits of 1.5 * 2^22 (ulp 0.5): see the epilogue
 constexpr uint32_t kIdescF4 = (1u << 7) | (1u << 10) | ((uint32_t)(kTileNF >> 3) << 17) | (1u << 23) | ((uint32_t)(256 >> 4) << 24);
 
 __device__ __forceinline__ void umma_f4_2sm(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
@@ -785,6 +785,14 @@ __device__ __forceinline__ void umma_f4_2sm(uint32_t tmem_c, uint64_t adesc, uin
       "tcgen05.mma.cta_group::2.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n\t}" ::"r"(tmem_c),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(sfa), "r"(sfb)
       : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
@@ -953,14 +961,20 @@ rf_f4x2_kernel(const __grid_constant__ CUtensorMap tm, int nkb, const int* __res
     }
   } else if (warp >= 4) {
     // ===== epilogue (each CTA: its 128 rows x 240 columns) =====
-    // Integer arithmetic on the f32 accumulators without F2I (quarter rate): y = dot + 1.5*2^23 carries dot in its
-    // low mantissa bits, and nb_s holds |b| + 1 + 2*bits(1.5*2^23), so d + 1 = |a| + nb_s - 2*bits(y) (mod 2^32).
+    // Integer arithmetic on the f32 accumulators in three instructions per element and without F2I (quarter rate):
+    // with c = 1.5*2^22 + |a|/2 (ulp 0.5, exact), bits(c - dot) = bits(1.5*2^22) + |a| - 2 dot, and nb_s holds
+    // |b| + 1 - bits(1.5*2^22), so d + 1 = bits(c - dot) + nb_s (mod 2^32).
+    // The accumulator is read into registers in one go and handed back to the MMA warp before the arithmetic
+    // starts, so the tensor core never waits for the epilogue's math, only for its TMEM reads.
     const int ew = warp - 4;
     const int quad = warp & 3;
-    const int slice = ew >> 2;  // chunks [4*slice, 4*slice + 4) of the 15
+    const int slice = ew >> 2;
     const int et = threadIdx.x - 128;
-    const int c_begin = 4 * slice, c_end = min(4 * slice + 4, kTileNF / 16);
+    constexpr int kSlices = kEpiWarpsF / 4, kChunks = kTileNF / 16, kCPW = kChunks / kSlices;
+    static_assert(kCPW * kSlices == kChunks, "chunks must split evenly over the warps of a quadrant");
+    const int c_begin = slice * kCPW;
     // rows 240..255 of a block are padding: they must not count as columns of the statistic in the column sums
+    const bool pad_warp = rank == 1 && quad == 3;
     const uint32_t col_mask = (rank * kTileRows + quad * 32 + lane) < kTileNF ? 0xFFFFFFFFu : 0u;
     uint32_t* nbu = reinterpret_cast<uint32_t*>(nb_s);
     int acc = 0, buf = 0;
@@ -972,57 +986,66 @@ rf_f4x2_kernel(const __grid_constant__ CUtensorMap tm, int nkb, const int* __res
       pair_flags(e.x, e.y, rank, tile_meta, pi);
       const long long col0 = (long long)pi.jb * kBlockRows;
       const long long row = (long long)pi.ib * kBlockRows + rank * kTileRows + quad * 32 + lane;
-      if (et < kTileNF) nbu[buf * kTileN + et] = (uint32_t)(nbits[col0 + et] + 1) + 2u * kF32Magic;
-      const uint32_t na = (uint32_t)nbits[row];
+      if (et < kTileNF) nbu[buf * kTileN + et] = (uint32_t)(nbits[col0 + et] + 1) - kF32Magic;
+      const float cfa = __fadd_rn(__uint_as_float(kF32Magic), __fmul_rn(0.5f, (float)nbits[row]));
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarpsF * 32) : "memory");
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kTileNF);
-      unsigned long long row_sum = 0;
-#pragma unroll 1
-      for (int cc = c_begin; cc < c_end; cc++) {
-        uint32_t r[16];
-        tmem_ld16(taddr + cc * 16, r);
-        if (dbg & 1) {  // tuning aid: accumulator read only
-          row_sum += r[0];
-          continue;
-        }
-        uint32_t nbv[16];
-        {
-          const uint4* nb4 = reinterpret_cast<const uint4*>(nbu + buf * kTileN + cc * 16);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kTileNF + c_begin * 16);
+      uint32_t r[kCPW][16];
 #pragma unroll
-          for (int q = 0; q < 4; q++) {
-            const uint4 t = nb4[q];
-            nbv[4 * q] = t.x, nbv[4 * q + 1] = t.y, nbv[4 * q + 2] = t.z, nbv[4 * q + 3] = t.w;
-          }
-        }
-        uint32_t chunk = 0;
-        if (pi.do_col) {
+      for (int cc = 0; cc < kCPW; cc++) tmem_ld16_nowait(taddr + cc * 16, r[cc]);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-          for (int j = 0; j < 16; j++) {
-            const uint32_t yi = __float_as_uint(__fadd_rn(__uint_as_float(r[j]), __uint_as_float(kF32Magic)));
-            const uint32_t e2 = na + nbv[j] - 2u * yi;
-            chunk += e2 * e2;
-            const uint32_t sred = __reduce_add_sync(0xffffffffu, (e2 & col_mask) * e2);
-            if (lane == 0) colpart[quad * kTileN + cc * 16 + j] = sred;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; j++) {
-            const uint32_t yi = __float_as_uint(__fadd_rn(__uint_as_float(r[j]), __uint_as_float(kF32Magic)));
-            const uint32_t e2 = na + nbv[j] - 2u * yi;
-            chunk += e2 * e2;
-          }
-        }
-        row_sum += chunk;
-      }
+      for (int cc = 0; cc < kCPW; cc++)  // the registers are defined only now: nothing that reads them may move above the wait
+        asm volatile("" : "+r"(r[cc][0]), "+r"(r[cc][1]), "+r"(r[cc][2]), "+r"(r[cc][3]), "+r"(r[cc][4]), "+r"(r[cc][5]),
+                          "+r"(r[cc][6]), "+r"(r[cc][7]), "+r"(r[cc][8]), "+r"(r[cc][9]), "+r"(r[cc][10]), "+r"(r[cc][11]),
+                          "+r"(r[cc][12]), "+r"(r[cc][13]), "+r"(r[cc][14]), "+r"(r[cc][15]));
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) {  // the TMEM reads are complete (tcgen05.wait::ld) and fenced: no memory release needed
+      if (lane == 0) {  // the TMEM reads are complete and fenced: the accumulator goes back before the math
         if (rank == 0)
-          mbar_arrive_relaxed(&tempty[acc], (int)row_sum);
+          mbar_arrive_relaxed(&tempty[acc], (int)r[0][0]);
         else
-          mbar_arrive_rank_relaxed(&tempty[acc], 0, (int)row_sum);
+          mbar_arrive_rank_relaxed(&tempty[acc], 0, (int)r[0][0]);
+      }
+      unsigned long long row_sum = 0;
+      if (!(dbg & 1)) {
+#pragma unroll
+        for (int cc = 0; cc < kCPW; cc++) {
+          uint32_t nbv[16];
+          {
+            const uint4* nb4 = reinterpret_cast<const uint4*>(nbu + buf * kTileN + (c_begin + cc) * 16);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+              const uint4 t = nb4[q];
+              nbv[4 * q] = t.x, nbv[4 * q + 1] = t.y, nbv[4 * q + 2] = t.z, nbv[4 * q + 3] = t.w;
+            }
+          }
+          uint32_t chunk = 0;
+          if (pi.do_col) {
+            uint32_t cs[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+              const uint32_t e2 = __float_as_uint(__fsub_rn(cfa, __uint_as_float(r[cc][j]))) + nbv[j];
+              const uint32_t v = e2 * e2;
+              chunk += v;
+              cs[j] = __reduce_add_sync(0xffffffffu, pad_warp ? (v & col_mask) : v);
+            }
+            if (lane == 0) {
+              uint4* dst = reinterpret_cast<uint4*>(colpart + quad * kTileN + (c_begin + cc) * 16);
+#pragma unroll
+              for (int q = 0; q < 4; q++) dst[q] = make_uint4(cs[4 * q], cs[4 * q + 1], cs[4 * q + 2], cs[4 * q + 3]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+              const uint32_t e2 = __float_as_uint(__fsub_rn(cfa, __uint_as_float(r[cc][j]))) + nbv[j];
+              chunk += e2 * e2;
+            }
+          }
+          row_sum += chunk;
+        }
       }
       if (pi.do_row && !(dbg & 2)) atomicAdd(&S[(size_t)row * C + pi.chain_cols], row_sum);
       if (pi.do_col && !(dbg & 2)) {
