@@ -426,6 +426,36 @@ def bench_psrf(args, rank, world, local, dist):
                        "psrf_mean_01": float(mean[0, 1]), "psrf_mean_10": float(mean[1, 0])},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
             "step_breakdown_ms": fam_ms}
+    # ---- the other ways the north star names (popcount-XOR, int8 tcgen05), same inputs, same step ---------------------
+    if world == 1 and args.workload == "psrf" and not args.no_other_methods:
+        others = {}
+        for name, m in (("i8", L.ASM_RF_I8), ("fp4", L.ASM_RF_FP4), ("popc", L.ASM_RF_POPC)):
+            if m == method:
+                continue
+            n_steps = 3 if m == L.ASM_RF_POPC else 10
+            for _ in range(3):
+                mean_m = ctx.psrf_eval(burnin, 0, n_trees, 1, m)
+            ts = []
+            for _ in range(n_steps):
+                ctx.flush_l2()
+                ctx.timer_mark(0)
+                mean_m = ctx.psrf_eval(burnin, 0, n_trees, 1, m)
+                ctx.timer_mark(1)
+                ts.append(ctx.timer_elapsed_ms(0, 1))
+            ctx.profile_enable(True)
+            ctx.profile_reset()
+            for _ in range(3):
+                ctx.flush_l2()
+                ctx.psrf_eval(burnin, 0, n_trees, 1, m)
+            km, kn = ctx.profile_get(L.K_RF_POPC if m == L.ASM_RF_POPC else L.K_RF_I8)
+            ctx.profile_enable(False)
+            km /= max(kn, 1)
+            ms_m = float(np.mean(ts))
+            others[name] = {"ms_per_step": ms_m, "value": T * T / (ms_m * 1e-3), "unit": "tree-pairs/s", "kernel_ms": km,
+                            "algorithmic_tflops": D * T * (T - 1) / (km * 1e-3) / 1e12 if m != L.ASM_RF_POPC else None,
+                            "xor_popc64_per_s": (D / 64.0) * T * (T - 1) / 2 / (km * 1e-3) if m == L.ASM_RF_POPC else None,
+                            "bit_identical_means": bool(np.array_equal(np.asarray(mean_m), np.asarray(mean), equal_nan=True))}
+        line["other_methods"] = others
     return line, ctx
 
 
@@ -539,10 +569,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="psrf", choices=["psrf", "ess", "cfg5"])
-    ap.add_argument("--method", default=os.environ.get("ASM_BENCH_METHOD", "i8"), choices=["i8", "fp4", "popc"])
+    ap.add_argument("--method", default=os.environ.get("ASM_BENCH_METHOD", "fp4"), choices=["i8", "fp4", "popc"])
     ap.add_argument("--cpu-rows", type=int, default=2048, help="row trees per chain in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ess", action="store_true", help="skip the secondary ESS block of the default run")
+    ap.add_argument("--no-other-methods", action="store_true", help="skip the int8 / popcount comparison runs")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

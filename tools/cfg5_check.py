@@ -25,6 +25,7 @@ ap.add_argument("--popc", action="store_true")
 ap.add_argument("--chains", type=int, default=32)
 ap.add_argument("--trees", type=int, default=50000)
 ap.add_argument("--rows", type=int, default=6)
+ap.add_argument("--method", default="i8", choices=["i8", "fp4"])
 args = ap.parse_args()
 
 cfg = dict(bench.CFG5, n_chains=args.chains, n_trees=args.trees)
@@ -37,16 +38,17 @@ ctx = A.GpuContext(C)
 for c in range(C):
     ctx.trees_set(c, bits[c])
 burnin = [0] * C
+METHOD = L.ASM_RF_FP4 if args.method == "fp4" else L.ASM_RF_I8
 t0 = time.time()
-S = ctx.psrf_sums(burnin, 0, N, 1, L.ASM_RF_I8)
-out["i8_first_eval_s"] = round(time.time() - t0, 2)
+S = ctx.psrf_sums(burnin, 0, N, 1, METHOD)
+out["first_eval_s"] = round(time.time() - t0, 2)
 ctx.timer_mark(0)
-mean = ctx.psrf_eval(burnin, 0, N, 1, L.ASM_RF_I8)
+mean = ctx.psrf_eval(burnin, 0, N, 1, METHOD)
 ctx.timer_mark(1)
 ms = ctx.timer_elapsed_ms(0, 1)
 T = C * N
-out.update({"i8_step_ms": ms, "tree_pairs_per_s": T * T / (ms * 1e-3), "layout": ctx.last_layout(),
-            "algorithmic_int8_tflops": enc.num_clades * T * (T - 1) / (ms * 1e-3) / 1e12,
+out.update({"method": args.method, "step_ms": ms, "tree_pairs_per_s": T * T / (ms * 1e-3), "layout": ctx.last_layout(),
+            "algorithmic_tflops": enc.num_clades * T * (T - 1) / (ms * 1e-3) / 1e12,
             "psrf_mean_range": [float(np.nanmin(mean[~np.eye(C, dtype=bool)])), float(np.nanmax(mean[~np.eye(C, dtype=bool)]))]})
 
 # host recomputation of sampled rows over all columns
@@ -66,9 +68,15 @@ out["host_rows_checked"] = args.rows
 out["host_rows_match"] = ok
 out["host_check_s"] = round(time.time() - t0, 1)
 
-parts = [ctx.psrf_sums(burnin, 0, N, 1, L.ASM_RF_I8, shard=(i, 4)) for i in range(4)]
+parts = [ctx.psrf_sums(burnin, 0, N, 1, METHOD, shard=(i, 4)) for i in range(4)]
 out["shards_add_up"] = bool(np.array_equal(sum(parts), S))
 del parts
+if args.method == "fp4":  # the two tensor-core kernels must agree on the full table
+    t0 = time.time()
+    S1 = ctx.psrf_sums(burnin, 0, N, 1, L.ASM_RF_I8)
+    out["i8_eval_s"] = round(time.time() - t0, 2)
+    out["fp4_equals_i8"] = bool(np.array_equal(S, S1))
+    del S1
 if args.popc:
     t0 = time.time()
     S2 = ctx.psrf_sums(burnin, 0, N, 1, L.ASM_RF_POPC)
