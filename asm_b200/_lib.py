@@ -47,6 +47,8 @@ SIGNATURES = {
     "asm_clade_counts": (_i32, [_p, _i32, _i64, _i64, _p]),
     "asm_psrf_sums": (_i32, [_p, _p, _i32, _i32, _i32, _i32, Shard, _p]),
     "asm_psrf_sums_device": (_i32, [_p, _p, _i32, _i32, _i32, _i32, Shard, _p]),
+    "asm_psrf_sums_device_async": (_i32, [_p, _p, _i32, _i32, _i32, _i32, Shard, _p]),
+    "asm_stream_handle": (_p, [_p]),
     "asm_psrf_finish_device": (_i32, [_p, _p, _i32, _p, _p]),
     "asm_psrf_eval": (_i32, [_p, _p, _i32, _i32, _i32, _i32, _p, _p]),
     "asm_ess_batch": (_i32, [_p, _i32, _i64, _i64, _p, _i32, _p, _p]),
@@ -275,6 +277,15 @@ class GpuContext:
         b = _i32arr(burnin)
         self._check(lib().asm_psrf_sums_device(self._h, _ptr(b), row_start, end, delta, method, Shard(*shard),
                                                C.c_void_p(d_S_ptr)))
+
+    def psrf_sums_device_async(self, burnin, row_start: int, end: int, delta: int, method: int, shard, d_S_ptr: int):
+        """Enqueue only: the caller orders its collective on `stream_handle()`."""
+        b = _i32arr(burnin)
+        self._check(lib().asm_psrf_sums_device_async(self._h, _ptr(b), row_start, end, delta, method, Shard(*shard),
+                                                     C.c_void_p(d_S_ptr)))
+
+    def stream_handle(self) -> int:
+        return int(lib().asm_stream_handle(self._h) or 0)
 
     def psrf_finish_device(self, d_S_ptr: int, n_rows: int, want_rows: bool = False):
         Cn = self.n_chains

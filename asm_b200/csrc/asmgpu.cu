@@ -329,6 +329,15 @@ int32_t asm_psrf_sums_device(asm_ctx* ctx, const int32_t* burnin, int32_t row_st
   return ASM_OK;
 }
 
+int32_t asm_psrf_sums_device_async(asm_ctx* ctx, const int32_t* burnin, int32_t row_start, int32_t end, int32_t delta,
+                                   int32_t method, asm_shard shard, int64_t* d_S) {
+  ASM_ENTER(ctx);
+  if (!burnin || !d_S) return asm_fail(ctx, ASM_E_INVALID, "psrf_sums: null argument");
+  return psrf_sums_impl(ctx, burnin, row_start, end, delta, method, shard, d_S);
+}
+
+void* asm_stream_handle(asm_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
 int32_t asm_psrf_sums(asm_ctx* ctx, const int32_t* burnin, int32_t row_start, int32_t end, int32_t delta,
                       int32_t method, asm_shard shard, int64_t* S) {
   ASM_ENTER(ctx);

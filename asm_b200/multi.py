@@ -40,10 +40,19 @@ def psrf_eval_multi(ctx, dist, burnin: Sequence[int], row_start: int, end: int, 
     n_rows = ctx.n_rows(row_start, end, delta)
     S = torch.zeros((C, max(n_rows, 1), C), dtype=torch.int64, device=device)
     if n_rows > 0:
-        ctx.psrf_sums_device(burnin, row_start, end, delta, method, (rank, world), S.data_ptr())
-        dist.all_reduce(S, op=dist.ReduceOp.SUM)
-        if S.is_cuda:
-            torch.cuda.current_stream(S.device).synchronize()  # the library works on its own stream
+        if S.is_cuda and hasattr(ctx, "psrf_sums_device_async"):
+            # no host round trips: the partial sums, the all-reduce and the finish kernel are ordered on the
+            # library's own stream (NCCL waits for the stream it is called under and makes it wait in turn)
+            torch.cuda.current_stream(S.device).synchronize()  # S was allocated and zeroed on torch's stream
+            lib_stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=S.device)
+            ctx.psrf_sums_device_async(burnin, row_start, end, delta, method, (rank, world), S.data_ptr())
+            with torch.cuda.stream(lib_stream):
+                dist.all_reduce(S, op=dist.ReduceOp.SUM)
+        else:
+            ctx.psrf_sums_device(burnin, row_start, end, delta, method, (rank, world), S.data_ptr())
+            dist.all_reduce(S, op=dist.ReduceOp.SUM)
+            if S.is_cuda:
+                torch.cuda.current_stream(S.device).synchronize()  # the library works on its own stream
     return ctx.psrf_finish_device(S.data_ptr(), n_rows, want_rows=want_rows), S
 
 

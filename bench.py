@@ -281,6 +281,8 @@ def bench_psrf(args, rank, world, local, dist):
     if world > 1:
         import torch
         d_S = torch.zeros((C, n_trees, C), dtype=torch.int64, device=f"cuda:{local}")
+        torch.cuda.synchronize()
+        lib_stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=f"cuda:{local}")
 
     def upload():
         if world == 1:
@@ -293,9 +295,10 @@ def bench_psrf(args, rank, world, local, dist):
     def step_resident():
         if world == 1:
             return ctx.psrf_eval(burnin, 0, n_trees, 1, method)
-        ctx.psrf_sums_device(burnin, 0, n_trees, 1, method, (rank, world), d_S.data_ptr())
-        dist.all_reduce(d_S, op=dist.ReduceOp.SUM)  # exact: int64 partial sums
-        torch.cuda.current_stream().synchronize()
+        # partial sums -> all-reduce -> finish, ordered on the library's stream with no host round trip in between
+        ctx.psrf_sums_device_async(burnin, 0, n_trees, 1, method, (rank, world), d_S.data_ptr())
+        with torch.cuda.stream(lib_stream):
+            dist.all_reduce(d_S, op=dist.ReduceOp.SUM)  # exact: int64 partial sums
         return ctx.psrf_finish_device(d_S.data_ptr(), n_trees)
 
     def barrier():

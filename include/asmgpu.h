@@ -110,6 +110,13 @@ int32_t asm_psrf_sums(asm_ctx* ctx, const int32_t* burnin, int32_t row_start, in
  * tables can be combined with an NCCL all-reduce without a host round trip. */
 int32_t asm_psrf_sums_device(asm_ctx* ctx, const int32_t* burnin, int32_t row_start, int32_t end, int32_t delta,
                              int32_t method, asm_shard shard, int64_t* d_S);
+/* The same without the final host synchronisation: the work is enqueued on the context's stream
+ * (asm_stream_handle), on which the caller orders its collective; asm_psrf_finish_device, enqueued on the same
+ * stream, then follows the collective with no host round trip in between. */
+int32_t asm_psrf_sums_device_async(asm_ctx* ctx, const int32_t* burnin, int32_t row_start, int32_t end, int32_t delta,
+                                   int32_t method, asm_shard shard, int64_t* d_S);
+/* The cudaStream_t (as void*) the context enqueues its PSRF work on. */
+void* asm_stream_handle(asm_ctx* ctx);
 /* From a complete S table on the device: psrf_rows[((a*n_rows)+r)*C + b] = S[a,r][a] != 0 ?
  * sqrt(S[a,r][b] / S[a,r][a]) : sqrt(S[a,r][b]) (TreePSRF.java:287-292) and psrf_mean[a*C + b] =
  * (sequential sum over r ascending) / n_rows (TreePSRF.java:264-271).  psrf_rows may be NULL.
