@@ -386,6 +386,15 @@ constexpr size_t kSmemBytes2 = (size_t)kStages2 * kStageBytes2 + kAuxBytes + 64;
 constexpr uint32_t kIdesc2 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;  // shared::cluster address of the same offset in CTA 0 of the pair
 
+__device__ __forceinline__ bool elect_one() {  // one lane of the (converged) warp
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -927,12 +936,15 @@ rf_f4x2_kernel(const __grid_constant__ CUtensorMap tm, int nkb, const int* __res
     }
   } else if (warp == 1) {
     // ===== MMA issuer (leader CTA only) =====
-    if (rank == 0 && lane == 0) {
+    // The whole warp walks the loop (so that stage, phase and the descriptors are warp-uniform and live in the
+    // uniform datapath: no R2UR per K block) and one elected lane issues.
+    if (rank == 0) {
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       const uint32_t sfa = tmem_base + (uint32_t)kSfaCol, sfb = tmem_base + (uint32_t)kSfbCol;
+      const uint32_t smem_base = smem_u32(smem);
       for (;;) {
-        const int2 e = wq.next(true);
+        const int2 e = wq.next(false);
         if (e.x < 0) break;
         mbar_wait_cluster(&tempty[acc], acc_phase ^ 1);  // both CTAs' epilogues have drained this accumulator
         tc_fence_after();
@@ -940,19 +952,23 @@ rf_f4x2_kernel(const __grid_constant__ CUtensorMap tm, int nkb, const int* __res
         for (int kb = 0; kb < nkb; kb++) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + (size_t)stage * kStageBytes2);
-          const uint64_t adesc = make_desc(a_addr), bdesc = make_desc(a_addr + kABytes);
+          if (elect_one()) {
+            const uint32_t a_addr = smem_base + (uint32_t)stage * kStageBytes2;
+            const uint64_t adesc = make_desc(a_addr), bdesc = make_desc(a_addr + kABytes);
 #pragma unroll
-          for (int kk = 0; kk < kBlockK / 32; kk++)
-            umma_f4_2sm(tmem_c, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), kIdescF4, (uint32_t)((kb | kk) != 0), sfa,
-                        sfb);
-          umma_commit_2sm(&empty[stage]);
+            for (int kk = 0; kk < kBlockK / 32; kk++)
+              umma_f4_2sm(tmem_c, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), kIdescF4, (uint32_t)((kb | kk) != 0),
+                          sfa, sfb);
+            umma_commit_2sm(&empty[stage]);
+          }
+          __syncwarp();
           if (++stage == kStages2) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit_2sm(&tfull[acc]);
+        if (elect_one()) umma_commit_2sm(&tfull[acc]);
+        __syncwarp();
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
