@@ -656,11 +656,14 @@ rf_i8x2_kernel(const __grid_constant__ CUtensorMap tm, int nkb, const int* __res
     }
   } else if (warp == 1) {
     // ===== MMA issuer (leader CTA only) =====
-    if (rank == 0 && lane == 0) {
+    // The whole warp walks the loop (stage, phase and the descriptors stay warp-uniform: no R2UR per K block, no
+    // elect loop around every tcgen05 instruction) and one elected lane issues.
+    if (rank == 0) {
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
+      const uint32_t smem_base = smem_u32(smem);
       for (;;) {
-        const int2 e = wq.next(true);
+        const int2 e = wq.next(false);
         if (e.x < 0) break;
         mbar_wait_cluster(&tempty[acc], acc_phase ^ 1);  // both CTAs' epilogues have drained this accumulator
         tc_fence_after();
@@ -668,18 +671,22 @@ rf_i8x2_kernel(const __grid_constant__ CUtensorMap tm, int nkb, const int* __res
         for (int kb = 0; kb < nkb; kb++) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + (size_t)stage * kStageBytes2);
-          const uint64_t adesc = make_desc(a_addr), bdesc = make_desc(a_addr + kABytes);
+          if (elect_one()) {
+            const uint32_t a_addr = smem_base + (uint32_t)stage * kStageBytes2;
+            const uint64_t adesc = make_desc(a_addr), bdesc = make_desc(a_addr + kABytes);
 #pragma unroll
-          for (int kk = 0; kk < kBlockK / 32; kk++)
-            umma_i8_2sm(tmem_c, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), kIdesc2, (uint32_t)((kb | kk) != 0));
-          umma_commit_2sm(&empty[stage]);
+            for (int kk = 0; kk < kBlockK / 32; kk++)
+              umma_i8_2sm(tmem_c, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), kIdesc2, (uint32_t)((kb | kk) != 0));
+            umma_commit_2sm(&empty[stage]);
+          }
+          __syncwarp();
           if (++stage == kStages2) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit_2sm(&tfull[acc]);
+        if (elect_one()) umma_commit_2sm(&tfull[acc]);
+        __syncwarp();
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
