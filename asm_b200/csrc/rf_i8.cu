@@ -382,7 +382,6 @@ rf_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 // =====================================================================================================
 constexpr int kStages2 = 6;
 constexpr int kStageBytes2 = 2 * kABytes;  // A half + B half: 32 KB
-constexpr size_t kSmemBytes2 = (size_t)kStages2 * kStageBytes2 + kAuxBytes + 64;
 constexpr uint32_t kIdesc2 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;  // shared::cluster address of the same offset in CTA 0 of the pair
 
@@ -424,14 +423,6 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {  // arrives on 
                "h"((uint16_t)3)
                : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_cta0(uint64_t* bar) {  // arrive on CTA 0's copy of `bar`
-  asm volatile(
-      "{\n\t.reg .b32 ra;\n\t"
-      "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar))
-      : "memory");
-}
-
 struct PairInfo {
   int ib, jb;
   bool do_row, do_col;  // for THIS CTA's 128 rows

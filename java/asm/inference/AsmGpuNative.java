@@ -36,7 +36,7 @@ final class AsmGpuNative {
     static final MethodHandle asm_ess_batch = h("asm_ess_batch",
             FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_LONG, JAVA_LONG, ADDRESS, JAVA_INT, ADDRESS, ADDRESS));
 
-    static final int ASM_OK = 0, ASM_RF_POPC = 0, ASM_RF_I8 = 1;
+    static final int ASM_OK = 0, ASM_RF_POPC = 0, ASM_RF_I8 = 1, ASM_RF_FP4 = 2;
 
     /** Throws with the library's message; the criteria catch it exactly where the reference catches Throwable. */
     static void check(MemorySegment ctx, int rc, String what) {

@@ -61,7 +61,8 @@ public class TreePSRFGPU extends TreePSRF {
             try (Arena a = Arena.ofConfined()) {
                 MemorySegment b = a.allocateFrom(JAVA_INT, burnin);
                 MemorySegment mean = a.allocate(JAVA_DOUBLE, 4);
-                int method = "popc".equals(methodInput.get()) ? AsmGpuNative.ASM_RF_POPC : AsmGpuNative.ASM_RF_I8;
+                int method = "popc".equals(methodInput.get()) ? AsmGpuNative.ASM_RF_POPC
+                        : "fp4".equals(methodInput.get()) ? AsmGpuNative.ASM_RF_FP4 : AsmGpuNative.ASM_RF_I8;
                 int rc = (int) AsmGpuNative.asm_psrf_eval.invokeExact(store.ctx, b, start, end, delta, method,
                         MemorySegment.NULL, mean);
                 AsmGpuNative.check(store.ctx, rc, "asm_psrf_eval");
