@@ -801,16 +801,6 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[1
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsF, 1)
 rf_f4x2_kernel(const __grid_constant__ CUtensorMap tm, int nkb, const int* __restrict__ nbits,
                const int2* __restrict__ tile_meta, long long n_slots, const uint32_t* __restrict__ walk_tiles, int nb,

@@ -19,7 +19,7 @@ import static java.lang.foreign.ValueLayout.*;
 @Description("Gelman-Rubin like criterion for convergence based on trees alone, evaluated on a B200 GPU")
 public class TreePSRFGPU extends TreePSRF {
     public Input<Integer> deviceInput = new Input<>("device", "CUDA device index", 0);
-    public Input<String> methodInput = new Input<>("method", "distance kernel: i8 (tcgen05) or popc", "i8");
+    public Input<String> methodInput = new Input<>("method", "distance kernel: i8 (int8 tcgen05), fp4 (block-scaled FP4 tcgen05, same integers, fastest) or popc", "i8");
 
     private GpuTraceStore store;
     private int start0 = -1;
