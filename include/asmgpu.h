@@ -165,7 +165,7 @@ int32_t asm_timer_elapsed_ms(asm_ctx* ctx, int32_t from, int32_t to, float* ms);
  * per kernel family (ASM_K_*), measured with events around every launch when profiling is on. */
 #define ASM_K_GATHER 0
 #define ASM_K_RF_POPC 1
-#define ASM_K_RF_I8 2
+#define ASM_K_RF_I8 2 /* both tensor-core kernels (ASM_RF_I8 and ASM_RF_FP4) */
 #define ASM_K_PSRF_FINISH 3
 #define ASM_K_CLADE_COUNTS 4
 #define ASM_K_ESS_LAG 5
