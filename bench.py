@@ -164,10 +164,7 @@ def pinned_like(a: np.ndarray):
 
 
 # --------------------------------------------------------------------------------------------------
-def cpu_baseline_psrf(cfg, n_trees, sample_rows=2048):
-    """The reference's CPU path for this workload, as restated by the oracle (Java cannot run here):
-    calcPSRF's two column loops (TreePSRF.java:274-286) for `sample_rows` row trees against every
-    column tree of every chain, OpenMP over rows."""
+def oracle_tree_set(cfg, n_trees):
     import oracle as O
     from asm_b200 import _lib as L
     ts = O.TreeSet(cfg["n_chains"], cfg["n_taxa"])
@@ -175,6 +172,16 @@ def cpu_baseline_psrf(cfg, n_trees, sample_rows=2048):
         l, r, root, _ = L.synth_tree_chain(cfg["n_taxa"], n_trees, cfg["start_seed"], cfg["seed0"] + c, cfg["moves"],
                                            cfg["beta"])
         ts.add(c, l, r, root)
+    return ts
+
+
+def cpu_baseline_psrf(cfg, n_trees, sample_rows=2048, ts=None):
+    """The reference's CPU path for this workload, as restated by the oracle (Java cannot run here):
+    calcPSRF's two column loops (TreePSRF.java:274-286) for `sample_rows` row trees against every
+    column tree of every chain, OpenMP over rows."""
+    import oracle as O
+    if ts is None:
+        ts = oracle_tree_set(cfg, n_trees)
     rows = min(sample_rows, n_trees)
     burnin = [0] * cfg["n_chains"]
     T = cfg["n_chains"] * n_trees
@@ -244,8 +251,9 @@ def run_reference(args):
         cfg = CFG5 if args.workload == "cfg5" else CFG2
         n_trees = cfg["n_trees"] if args.workload == "cfg5" else int(round(cfg["n_trees"] * math.sqrt(args.gpus)))
         vals = []
+        ts = oracle_tree_set(cfg, n_trees)  # built once; a step is the calcPSRF loops over a bounded block of rows
         for s in range(warm + steps):
-            r = cpu_baseline_psrf(cfg, n_trees, sample_rows=args.cpu_rows)
+            r = cpu_baseline_psrf(cfg, n_trees, sample_rows=args.ref_rows, ts=ts)
             if s >= warm:
                 vals.append(r)
         v = float(np.mean([r["value"] for r in vals]))
@@ -313,7 +321,7 @@ def bench_psrf(args, rank, world, local, dist):
         ctx.flush_l2()
     # ---- timed: inputs resident in HBM --------------------------------------------------------------
     ctx.profile_enable(False)
-    sampler = ClockSampler(local, period_s=0.004)
+    sampler = ClockSampler(local, period_s=0.001)
     per_step = []
     barrier()
     launches0 = ctx.launch_count()
@@ -574,6 +582,8 @@ def main():
     ap.add_argument("--workload", default="psrf", choices=["psrf", "ess", "cfg5"])
     ap.add_argument("--method", default=os.environ.get("ASM_BENCH_METHOD", "fp4"), choices=["i8", "fp4", "popc"])
     ap.add_argument("--cpu-rows", type=int, default=2048, help="row trees per chain in the CPU-baseline sample")
+    ap.add_argument("--ref-rows", type=int, default=512,
+                    help="row trees per chain per step of --impl reference (about 2 s of CPU work per step at cfg2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ess", action="store_true", help="skip the secondary ESS block of the default run")
     ap.add_argument("--no-other-methods", action="store_true", help="skip the int8 / popcount comparison runs")
