@@ -28,6 +28,12 @@ def test_cfg2_full_size_properties(gpu, cfg2):
         S_i8 = ctx.psrf_sums(b0, 0, N, 1, gpu.ASM_RF_I8)
         S_pc = ctx.psrf_sums(b0, 0, N, 1, gpu.ASM_RF_POPC)
         assert np.array_equal(S_i8, S_pc)                       # tensor-core and popcount kernels agree exactly
+        S_f4 = ctx.psrf_sums(b0, 0, N, 1, gpu.ASM_RF_FP4)
+        assert np.array_equal(S_f4, S_i8)                       # so does the block-scaled fp4 kernel (240-row blocks)
+        parts4 = [ctx.psrf_sums(b0, 0, N, 1, gpu.ASM_RF_FP4, shard=(i, 8)) for i in range(8)]
+        assert np.array_equal(sum(parts4), S_i8)
+        assert np.array_equal(ctx.psrf_sums([1000, 0, 37, 9999], 120, N - 3, 3, gpu.ASM_RF_FP4),
+                              ctx.psrf_sums([1000, 0, 37, 9999], 120, N - 3, 3, gpu.ASM_RF_I8))  # burn-in, thinning, ragged
         tot = S_i8.sum(axis=1)                                  # [a][c] = sum over all (row in a, column in c) pairs
         assert np.array_equal(tot, tot.T)                       # RF(a,b) = RF(b,a)
         assert (S_i8[np.arange(C), :, np.arange(C)] >= 1).all()  # the diagonal term (0+1)^2
