@@ -33,6 +33,50 @@ def test_act_closed_form_equals_literal_java_loop(n, mu):
         assert bits_equal(np.array([O.act_literal(x, 3, n)]), np.array([O.act_final(x, 3, n)]))
 
 
+def py_act(trace, start, end, MAX_LAG=2000):
+    """TraceESS.ACT (TraceESS.java:130-179) once more, line by line in plain Python floats (IEEE doubles, no
+    fused multiply-add in CPython): a third implementation, in another language, of the same Java text."""
+    s = 0.0
+    sls = [0.0] * MAX_LAG
+    ac = [0.0] * MAX_LAG
+    for i in range(end - start):
+        trace_i = trace[i + start]
+        s += trace_i
+        mean = s / (i + 1)
+        sum1 = s
+        sum2 = s
+        for lag in range(min(i + 1, MAX_LAG)):
+            t = trace[i + start - lag]
+            sls[lag] = sls[lag] + t * trace_i
+            ac[lag] = sls[lag] - (sum1 + sum2) * mean + mean * mean * (i + 1 - lag)
+            ac[lag] /= (i + start + 1 - lag)
+            sum1 -= t
+            sum2 -= trace[start + lag]
+    max_lag = min(end - start, MAX_LAG)
+    integral = 0.0
+    for lag in range(max_lag):
+        if lag == 0:
+            integral = ac[0]
+        elif lag % 2 == 0:
+            if ac[lag - 1] + ac[lag] > 0:
+                integral += 2.0 * (ac[lag - 1] + ac[lag])
+            else:
+                break
+    return integral / ac[0] if ac[0] != 0 or integral != 0 else float("nan")  # Java: 0.0/0.0 = NaN
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 64, 301])
+@pytest.mark.parametrize("mu", [0.0, 1.0, -1e4])
+def test_act_c_oracle_equals_plain_python_restatement(n, mu):
+    rng = np.random.default_rng(100 + n)
+    x = (mu + np.cumsum(rng.normal(size=n)) * 0.1 + rng.normal(size=n)).tolist()
+    for start in (0, 2) if n > 4 else (0,):
+        want = py_act(x, start, n)
+        got_lit = O.act_literal(np.array(x), start, n)
+        got_fin = O.act_final(np.array(x), start, n)
+        assert bits_equal(np.array([want]), np.array([got_lit])) and bits_equal(np.array([want]), np.array([got_fin]))
+
+
 def test_act_known_answers():
     assert math.isnan(O.act_final(np.full(100, 2.5)))      # constant: ac[0] = 0 -> 0/0
     assert math.isnan(O.act_literal(np.full(100, 2.5)))
