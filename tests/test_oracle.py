@@ -215,6 +215,46 @@ def test_burnin_detector():
     assert O.burnin([np.stack([y, y])], [1], "Automatic", 0, n)[0] == 300
 
 
+def py_burnin(trace, end, WINDOW_SIZE=10):
+    """BurnInDetector.burnIn(List<Double>, int) (BurnInDetector.java:51-78) line by line in plain Python floats."""
+    m2 = 0.0
+    sq2 = 0.0
+    lb = 3 * end // 4
+    for i in range(lb, end):
+        m2 += trace[i]
+    m2 = m2 / (end - lb) if end - lb != 0 else float("nan")
+    for i in range(lb, end):
+        d = trace[i]
+        sq2 += (d - m2) * (d - m2)
+    den = end - lb - 1
+    q = sq2 / den if den != 0 else (float("nan") if sq2 == 0 or sq2 != sq2 else math.copysign(math.inf, sq2))
+    stdev2 = math.sqrt(q) if q == q and q >= 0 else float("nan")
+    i = 0
+    while i + WINDOW_SIZE < lb:
+        s = 0.0
+        for j in range(WINDOW_SIZE):
+            s += trace[i + j]
+        s /= WINDOW_SIZE
+        if m2 - stdev2 < s and s < m2 + stdev2:
+            return i + WINDOW_SIZE
+        i += 1
+    return lb
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_burnin_c_oracle_equals_plain_python_restatement(seed):
+    rng = np.random.default_rng(seed)
+    n = 600
+    t = np.arange(n)
+    cols = [np.arange(n, dtype=float)]
+    for j in range(3):
+        cols.append(-500.0 * np.exp(-t / rng.uniform(5, 120)) * rng.uniform(0.2, 3) + rng.normal(size=n) * rng.uniform(0.1, 5) + j)
+    logs = [np.stack(cols)]
+    for end in (1, 2, 5, 13, 41, 100, 333, 600):
+        want = max(py_burnin(cols[c].tolist(), end) for c in (1, 2, 3))  # BurnInDetector.java:38-47: max over the map
+        assert O.burnin(logs, [1, 2, 3], "Automatic", 0, end)[0] == want, (seed, end)
+
+
 # ---------------------------------------------------------------- GelmanRubin / CladeDifference
 def test_gelman_rubin_oracle():
     rng = np.random.default_rng(2)
