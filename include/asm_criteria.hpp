@@ -135,7 +135,7 @@ class TreeESS : public MCMCConvergenceCriterion {  // TreeESS.java
   double smoothingInput = 1.0;
   int cacheLimitInput = 1024;
   int ESSSampleSizeInput = 10;  // "sampleSize"
-  // not in the reference: which distance kernel the GPU uses (ASM_RF_POPC / ASM_RF_I8)
+  // not in the reference: which distance kernel the GPU uses (ASM_RF_POPC / ASM_RF_I8 / ASM_RF_FP4; same integers)
   int methodInput = ASM_RF_I8;
 
   void initAndValidate() override;                          // :45-76 (as written: rejects every smoothing >= 0)
