@@ -51,6 +51,26 @@ def test_replay_oracle_only(tmp_path, name):
         assert rp.oracle_psrf.delta == 8  # end/delta > cacheLimit at 129, 258, 516 (TreePSRF.java:120-124)
 
 
+@pytest.mark.parametrize("name", list(SCENARIOS))
+def test_replay_oracle_matches_frozen_expectations(tmp_path, name):
+    """CPU: the oracle's per-check numbers for the replayed runs are frozen in tests/golden/replay_<name>_expected.json
+    (tests/golden/make_replay_expected.py); a change of the oracle, the generators or the harness shows up here.
+    The same files are what a maintainer compares the Java's output with."""
+    import json
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    want = json.load(open(os.path.join(here, "golden", f"replay_{name}_expected.json")))["checks"]
+    rp = _run(tmp_path, SCENARIOS[name])
+    assert len(rp.history) == len(want)
+    hexbits = lambda x: [format(int(v), "016x") for v in np.ascontiguousarray(np.atleast_1d(x), dtype=np.float64).view(np.uint64)]
+    for r, w in zip(rp.history, want):
+        po, eo = r["psrf_oracle"], r["ess_oracle"]
+        assert r["end"] == w["end"] and r["burnin"] == w["burnin"]
+        assert [bool(po[0]), hexbits(po[1]), int(po[2]), int(po[3])] == w["psrf"], f"TreePSRF at check {r['end']}"
+        assert [bool(eo[0]), hexbits(eo[1]), hexbits(eo[2])[0]] == w["ess"], f"TraceESS at check {r['end']}"
+        assert bool(r["converged_oracle"]) == w["converged"]
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("method", [0, 1, 2])
 @pytest.mark.parametrize("name", list(SCENARIOS))
