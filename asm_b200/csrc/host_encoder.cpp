@@ -44,29 +44,62 @@ struct KeyHash {
 
 struct asm_encoder {
   int32_t n_taxa = 0;
+  int32_t set_words = 0;        // words of a leaf-set bitset: ceil(n_taxa / 64)
   std::vector<Key128> zobrist;  // per leaf
-  std::unordered_map<Key128, std::vector<int32_t>, KeyHash> table;  // hash -> candidate ids
-  std::vector<int64_t> leaf_off;   // id -> offset into leaf_pool
-  std::vector<int32_t> leaf_pool;  // concatenated sorted leaf lists
+  // open-addressing table, linear probing: (key, id) with id < 0 = empty.  A node-based std::unordered_map costs
+  // a cache miss or two per lookup, and there is one lookup per internal node of every tree.
+  struct Slot {
+    Key128 key;
+    int32_t id;
+  };
+  std::vector<Slot> slots;
+  size_t mask = 0;
+  // id -> leaf set as a bitset over the taxa (bit v = leaf number v).  Bitsets make a node's set the OR of its
+  // children's (n/64 words) where sorted leaf lists cost a merge of the whole subtree at every node.
+  std::vector<uint64_t> set_pool;
+  std::vector<uint64_t> scratch;
   std::string err;
 
-  int64_t num_clades() const { return (int64_t)leaf_off.size(); }
+  int64_t num_clades() const { return set_words ? (int64_t)(set_pool.size() / (size_t)set_words) : 0; }
+  const uint64_t* clade_set(int64_t id) const { return set_pool.data() + (size_t)id * (size_t)set_words; }
   int32_t clade_size(int64_t id) const {
-    int64_t e = (id + 1 < (int64_t)leaf_off.size()) ? leaf_off[id + 1] : (int64_t)leaf_pool.size();
-    return (int32_t)(e - leaf_off[id]);
+    int32_t c = 0;
+    const uint64_t* p = clade_set(id);
+    for (int w = 0; w < set_words; w++) c += __builtin_popcountll(p[w]);
+    return c;
   }
-  // leaves must be sorted ascending
-  int32_t get_or_add(const Key128& k, const int32_t* leaves, int32_t n) {
-    auto& cand = table[k];
-    for (int32_t id : cand) {
-      if (clade_size(id) == n && std::memcmp(&leaf_pool[leaf_off[id]], leaves, sizeof(int32_t) * (size_t)n) == 0)
-        return id;
+  void grow() {
+    const size_t cap = slots.empty() ? 4096 : slots.size() * 2;
+    std::vector<Slot> old;
+    old.swap(slots);
+    slots.assign(cap, Slot{{0, 0}, -1});
+    mask = cap - 1;
+    for (const Slot& s : old) {
+      if (s.id < 0) continue;
+      size_t h = KeyHash()(s.key) & mask;
+      while (slots[h].id >= 0) h = (h + 1) & mask;
+      slots[h] = s;
     }
-    int32_t id = (int32_t)leaf_off.size();
-    leaf_off.push_back((int64_t)leaf_pool.size());
-    leaf_pool.insert(leaf_pool.end(), leaves, leaves + n);
-    cand.push_back(id);
+  }
+  int32_t get_or_add_set(const Key128& k, const uint64_t* bits) {
+    if ((size_t)(num_clades() + 1) * 2 > slots.size()) grow();  // load factor <= 1/2
+    size_t h = KeyHash()(k) & mask;
+    for (;; h = (h + 1) & mask) {
+      const Slot& s = slots[h];
+      if (s.id < 0) break;
+      // equal keys are confirmed against the stored leaf set: the mapping is exact, not probabilistic
+      if (s.key == k && std::memcmp(clade_set(s.id), bits, sizeof(uint64_t) * (size_t)set_words) == 0) return s.id;
+    }
+    const int32_t id = (int32_t)num_clades();
+    set_pool.insert(set_pool.end(), bits, bits + set_words);
+    slots[h] = Slot{k, id};
     return id;
+  }
+  // the same from a list of leaf numbers (any order)
+  int32_t get_or_add(const Key128& k, const int32_t* leaves, int32_t n) {
+    scratch.assign((size_t)set_words, 0);
+    for (int32_t i = 0; i < n; i++) scratch[(size_t)(leaves[i] >> 6)] |= 1ULL << (leaves[i] & 63);
+    return get_or_add_set(k, scratch.data());
   }
 };
 
@@ -75,63 +108,69 @@ namespace {
 // Post-order walk (left subtree, right subtree, node) without recursion limits: emits one clade id
 // per internal node.  Returns false if the arrays do not describe a binary tree on n_taxa leaves.
 bool encode_tree(asm_encoder* enc, const int32_t* left, const int32_t* right, int32_t root, int32_t* ids_out) {
-  const int n = enc->n_taxa, nn = 2 * n - 1;
+  const int n = enc->n_taxa, nn = 2 * n - 1, W = enc->set_words;
   if (root < 0 || root >= nn) return false;
-  // iterative post-order; each frame owns a slice of `leaves`
   struct Frame {
-    int32_t node, begin, stage;
-    Key128 key;
+    int32_t node, stage;
   };
-  std::vector<Frame> st;
-  std::vector<int32_t> leaves;  // leaf lists of completed subtrees, stacked
-  std::vector<int32_t> sizes;   // sizes of completed subtrees on the value stack
-  std::vector<Key128> keys;
-  std::vector<int32_t> merged;
-  leaves.reserve(n);
+  // scratch kept across calls (one encoder = one caller thread)
+  static thread_local std::vector<Frame> st;
+  static thread_local std::vector<uint64_t> sets;  // leaf sets of completed subtrees, stacked (W words each)
+  static thread_local std::vector<int32_t> sizes;
+  static thread_local std::vector<Key128> keys;
+  st.clear();
+  sets.clear();
+  sizes.clear();
+  keys.clear();
   int n_out = 0, visited = 0;
-  st.push_back({root, 0, 0, {0, 0}});
+  st.push_back({root, 0});
   while (!st.empty()) {
     Frame& f = st.back();
-    int32_t v = f.node;
+    const int32_t v = f.node;
     if (v < 0 || v >= nn || ++visited > 4 * nn) return false;
     if (left[v] < 0) {  // leaf: getNr() == node index, must be < n_taxa
       if (v >= n) return false;
-      leaves.push_back(v);
+      sets.resize(sets.size() + (size_t)W, 0);
+      sets[sets.size() - (size_t)W + (size_t)(v >> 6)] = 1ULL << (v & 63);
       sizes.push_back(1);
-      keys.push_back(enc->zobrist[v]);
+      keys.push_back(enc->zobrist[(size_t)v]);
       st.pop_back();
       continue;
     }
     if (f.stage == 0) {
       f.stage = 1;
-      f.begin = (int32_t)leaves.size();
-      st.push_back({left[v], 0, 0, {0, 0}});
+      const int32_t c = left[v];
+      st.push_back({c, 0});
       continue;
     }
     if (f.stage == 1) {
       f.stage = 2;
-      st.push_back({right[v], 0, 0, {0, 0}});
+      const int32_t c = right[v];
+      st.push_back({c, 0});
       continue;
     }
-    // both children done: merge the two sorted lists on top of the value stack
+    // both children done: the node's leaf set is the union of the two sets on top of the value stack
     if (sizes.size() < 2) return false;
-    int32_t nr = sizes.back();
+    const int32_t nr = sizes.back();
     sizes.pop_back();
-    int32_t nl = sizes.back();
+    const int32_t nl = sizes.back();
     sizes.pop_back();
-    Key128 kr = keys.back();
+    const Key128 kr = keys.back();
     keys.pop_back();
-    Key128 kl = keys.back();
+    const Key128 kl = keys.back();
     keys.pop_back();
-    int32_t* base = leaves.data() + (leaves.size() - (size_t)(nl + nr));
-    merged.resize((size_t)(nl + nr));
-    std::merge(base, base + nl, base + nl, base + nl + nr, merged.begin());
-    std::memcpy(base, merged.data(), sizeof(int32_t) * (size_t)(nl + nr));
-    for (int32_t q = 1; q < nl + nr; q++)
-      if (base[q] == base[q - 1]) return false;  // a leaf reached twice: not a tree
-    Key128 k{kl.a ^ kr.a, kl.b ^ kr.b};
+    uint64_t* l = sets.data() + (sets.size() - 2 * (size_t)W);
+    const uint64_t* r = l + W;
+    uint64_t overlap = 0;
+    for (int w = 0; w < W; w++) {
+      overlap |= l[w] & r[w];
+      l[w] |= r[w];
+    }
+    if (overlap) return false;  // a leaf reached twice: not a tree
+    sets.resize(sets.size() - (size_t)W);
+    const Key128 k{kl.a ^ kr.a, kl.b ^ kr.b};
     if (n_out >= n - 1) return false;
-    ids_out[n_out++] = enc->get_or_add(k, base, nl + nr);
+    ids_out[n_out++] = enc->get_or_add_set(k, sets.data() + (sets.size() - (size_t)W));
     sizes.push_back(nl + nr);
     keys.push_back(k);
     st.pop_back();
@@ -148,6 +187,7 @@ int32_t asm_encoder_create(asm_encoder** out, int32_t n_taxa) {
   auto* e = new (std::nothrow) asm_encoder();
   if (!e) return ASM_E_NOMEM;
   e->n_taxa = n_taxa;
+  e->set_words = (n_taxa + 63) / 64;
   e->zobrist.resize((size_t)n_taxa);
   uint64_t s = 0x5EEDC1ADE5ULL;
   for (auto& z : e->zobrist) {
@@ -246,9 +286,12 @@ int64_t asm_encoder_num_clades(const asm_encoder* enc) { return enc ? enc->num_c
 
 int32_t asm_encoder_clade_leaves(const asm_encoder* enc, int64_t id, int32_t* leaves_out, int32_t cap) {
   if (!enc || id < 0 || id >= enc->num_clades()) return ASM_E_INVALID;
-  int32_t n = enc->clade_size(id);
+  const int32_t n = enc->clade_size(id);
   if (n > cap || !leaves_out) return ASM_E_RANGE;
-  std::memcpy(leaves_out, &enc->leaf_pool[(size_t)enc->leaf_off[(size_t)id]], sizeof(int32_t) * (size_t)n);
+  const uint64_t* p = enc->clade_set(id);
+  int32_t k = 0;
+  for (int w = 0; w < enc->set_words; w++)  // ascending leaf numbers
+    for (uint64_t m = p[w]; m; m &= m - 1) leaves_out[k++] = w * 64 + __builtin_ctzll(m);
   return n;
 }
 
