@@ -277,6 +277,48 @@ def test_gelman_rubin_oracle():
     assert conv and np.isnan(gr).all()
 
 
+def py_gr_stat(n, t1, t2):
+    """GelmanRubin.calcGRStat (GelmanRubin.java:53-96) line by line in plain Python floats."""
+    mean1 = mean2 = sumsq1 = sumsq2 = 0.0
+    for i in range(n):
+        d = t1[i]
+        mean1 += d
+        sumsq1 += d * d
+    mean1 = mean1 / n if n else float("nan")
+    for i in range(n):
+        d = t2[i]
+        mean2 += d
+        sumsq2 += d * d
+    mean2 = mean2 / n if n else float("nan")
+
+    def div(a, b):  # Java double division: x/0 = +-Infinity, 0/0 = NaN
+        if b != 0:
+            return a / b
+        return float("nan") if a == 0 or a != a else math.copysign(math.inf, a) * math.copysign(1.0, b)
+
+    var1 = div(sumsq1 - mean1 * mean1 * n, n - 1)
+    var2 = div(sumsq2 - mean2 * mean2 * n, n - 1)
+    fW = (var1 + var2) / 2
+    if fW == 0:
+        return 1.0
+    total_mean = (mean1 + mean2) / 2
+    total_sq = mean1 * mean1 + mean2 * mean2
+    fB = total_sq - total_mean * total_mean * 2
+    varR = div(n - 1.0, n) + div(fB, fW) * div(1.0, n)
+    return math.sqrt(varR) if varR >= 0 else float("nan")
+
+
+@pytest.mark.parametrize("n", [2, 3, 10, 257, 1000])
+def test_gr_stat_c_oracle_equals_plain_python_restatement(n):
+    import ctypes
+    rng = np.random.default_rng(n)
+    a = rng.normal(size=1000) * 3 - 7000.0
+    b = rng.normal(size=1000) * 2.5 - 7000.5
+    got = O.lib().orc_gr_stat(n, a.ctypes.data_as(ctypes.c_void_p), b.ctypes.data_as(ctypes.c_void_p))
+    want = py_gr_stat(n, a.tolist(), b.tolist())
+    assert bits_equal(np.array([got]), np.array([want]))
+
+
 def test_clade_difference_oracle(multi_chains):
     ch = multi_chains
     n = ch.n_taxa
