@@ -79,3 +79,29 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cpp", ".h", ".hpp", ".cuh")) or f == "Makefile":
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in txt.lower(), f"{f} mentions the oracle"
+
+
+def test_headers_are_plain_c(tmp_path):
+    """include/asmgpu.h and include/asmgpu_host.h compile as C11 (what cgo / JNI / Panama jextract would consume) and a
+    C program calling a no-GPU entry point links against the library."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc") or "/usr/bin/gcc"
+    src = tmp_path / "abi.c"
+    src.write_text(
+        '#include "asmgpu.h"\n#include "asmgpu_host.h"\n#include <stdio.h>\n'
+        'int main(void) { asm_shard s = {0, 1}; (void)s; printf("%s %d\\n", asm_version(), (int)asm_device_count());\n'
+        '  int64_t lines = -1; const char* p[1] = {"/nonexistent"}; int32_t b[1] = {0};\n'
+        '  int32_t rc = asmh_combine_logs(0, 1, p, b, 1, 1, 0, 0, "/dev/null", &lines);\n'
+        '  return rc == ASM_OK ? 1 : 0; }\n')
+    inc = os.path.join(ROOT, "include")
+    r = subprocess.run([gcc, "-std=c11", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-I", inc, str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(L.LIB_PATH)
+    r = subprocess.run([gcc, "-std=c11", "-I", inc, str(src), "-o", str(exe), "-L", libdir, "-l:libasmgpu.so",
+                        f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("asm-b200")  # the missing chain file is an error, not a crash
