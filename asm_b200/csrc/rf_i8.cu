@@ -20,115 +20,9 @@
 // across GPUs, to shards.
 //
 // Bound: tensor pipe.  Algorithmic work D*T*(T-1) int8 flop (unordered pairs); see DESIGN.md.
-#include <cuda.h>
-
-#include <algorithm>
-#include <cstdlib>
-#include <mutex>
-#include <vector>
-
-#include "asm_internal.h"
+#include "tc_common.cuh"
 
 namespace {
-
-constexpr int kStages = 4;
-constexpr int kBlockK = 128;                       // bytes (= int8 elements) per K block, one swizzle atom wide
-constexpr int kTileN = 256;                        // columns per tile
-constexpr int kABytes = kTileRows * kBlockK;       // 16 KB
-constexpr int kBBytes = kTileN * kBlockK;          // 32 KB
-constexpr int kStageBytes = kABytes + kBBytes;     // 48 KB
-constexpr int kThreads = 384;
-constexpr int kEpiWarps = 8;
-constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kAccCols = 256;                      // TMEM columns per accumulator
-constexpr int kTmemCols = 512;
-constexpr size_t kAuxBytes = 128 /*barriers + tmem ptr*/ + 2 * kTileN * 4 /*nb+1, double buffered*/ + 4 * kTileN * 4 /*col partials*/;
-constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + kAuxBytes;
-
-// instruction descriptor for kind::i8 (cute::UMMA::InstrDescriptor): c_format S32 = 2 @ [4,6),
-// a/b_format S8 = 1 @ [7,10)/[10,13), K-major A and B (bits 15,16 = 0), N>>3 @ [17,23), M>>4 @ [24,29)
-constexpr uint32_t kIdesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(kTileRows >> 4) << 24);
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol error traps (the launch fails with an error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 28)) __trap();
-  }
-}
-
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-
-// shared-memory matrix descriptor, K-major, 128B swizzle: start>>4 @ [0,14), LBO>>4 @ [16,30) (unused
-// for swizzled K-major), SBO>>4 = 1024>>4 @ [32,46) (8 rows x 128 B per swizzle atom), version 1 @ [46,48),
-// layout SWIZZLE_128B = 2 @ [61,64)  (cute::UMMA::SmemDescriptor)
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-
-__device__ __forceinline__ void umma_i8(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_c),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
-
 
 // Linear work index -> block pair (ib <= jb) of the upper triangle, walked in G x G supertiles so that the
 // 2G operand blocks a wave of CTAs touches stay resident in L2 (a plain column-major walk streams one
@@ -380,164 +274,6 @@ rf_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 // through L2 by CTAs that use them at the same time (static striding let the clusters drift apart: ncu on
 // a cfg5-shaped run showed 49 % L2 hit rate and 5.9 TB/s of DRAM reads).
 // =====================================================================================================
-constexpr int kStages2 = 6;
-constexpr int kStageBytes2 = 2 * kABytes;  // A half + B half: 32 KB
-constexpr uint32_t kIdesc2 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-constexpr uint32_t kPeerMask = 0xFEFFFFFFu;  // shared::cluster address of the same offset in CTA 0 of the pair
-
-__device__ __forceinline__ bool elect_one() {  // one lane of the (converged) warp
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* leader_bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(map), "r"(smem_u32(leader_bar) & kPeerMask), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void umma_i8_2sm(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_c),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {  // arrives on `bar` in both CTAs of the pair
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                   smem_u32(bar)),
-               "h"((uint16_t)3)
-               : "memory");
-}
-struct PairInfo {
-  int ib, jb;
-  bool do_row, do_col;  // for THIS CTA's 128 rows
-  int chain_rows, chain_cols;
-};
-
-// Work flags of block pair (ib <= jb) for the CTA of rank `rank`; the return value (any work at all) is the
-// same in both CTAs of the pair.
-__device__ __forceinline__ bool pair_flags(int ib, int jb, int rank, const int2* __restrict__ meta, PairInfo& pi) {
-  pi.ib = ib;
-  pi.jb = jb;
-  const int2 mi0 = meta[2 * ib], mi1 = meta[2 * ib + 1], mj0 = meta[2 * jb], mj1 = meta[2 * jb + 1];
-  const bool diag = ib == jb;
-  const bool col_j = (mj0.y & kFlagCol) != 0, col_i = (mi0.y & kFlagCol) != 0;
-  const bool rows_j = ((mj0.y | mj1.y) & kFlagRows) != 0;
-  const int my = rank ? mi1.y : mi0.y;
-  pi.do_row = (my & kFlagRows) && col_j;
-  pi.do_col = !diag && col_i && rows_j;
-  pi.chain_rows = mi0.x;
-  pi.chain_cols = mj0.x;
-  return (((mi0.y | mi1.y) & kFlagRows) && col_j) || pi.do_col;
-}
-
-// even bits of v, compacted (Morton decode)
-__device__ __forceinline__ uint32_t compact_bits(unsigned long long v) {
-  v &= 0x5555555555555555ULL;
-  v = (v | (v >> 1)) & 0x3333333333333333ULL;
-  v = (v | (v >> 2)) & 0x0F0F0F0F0F0F0F0FULL;
-  v = (v | (v >> 4)) & 0x00FF00FF00FF00FFULL;
-  v = (v | (v >> 8)) & 0x0000FFFF0000FFFFULL;
-  v = (v | (v >> 16)) & 0x00000000FFFFFFFFULL;
-  return (uint32_t)v;
-}
-
-__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait_cluster(bar, parity)) {
-    if (++spins > (1u << 28)) __trap();
-  }
-}
-__device__ __forceinline__ void mbar_arrive_rank(uint64_t* bar, uint32_t rank) {  // arrive on CTA `rank`'s copy of `bar`
-  asm volatile(
-      "{\n\t.reg .b32 ra;\n\t"
-      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
-      "r"(rank)
-      : "memory");
-}
-// Arrivals that only hand a buffer back (the data was consumed into registers, `dep` is one of those registers so
-// that the arrive cannot issue before the load has returned): no release fence.  A releasing arrive is a MEMBAR
-// that waits for every outstanding memory operation of the thread, including the fire-and-forget atomics of the
-// previous tile (ncu: a fifth of all stall samples of the fp4 kernel).
-__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar, int dep) {
-  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)), "r"(dep) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_rank_relaxed(uint64_t* bar, uint32_t rank, int dep) {
-  asm volatile(
-      "{\n\t.reg .b32 ra;\n\t"
-      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
-      "r"(rank), "r"(dep)
-      : "memory");
-}
-__device__ __forceinline__ void st_int2_rank(int2* p, uint32_t rank, int a, int b) {  // store into CTA `rank`'s copy of *p
-  asm volatile(
-      "{\n\t.reg .b32 ra;\n\t"
-      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "st.shared::cluster.v2.s32 [ra], {%2, %3};\n\t}" ::"r"(smem_u32(p)),
-      "r"(rank), "r"(a), "r"(b)
-      : "memory");
-}
-
-constexpr int kQ = 4;  // depth of the in-kernel work queue
-constexpr int kSchedConsumers = 2 + kEpiWarps + 1 + kEpiWarps;  // leader: TMA, MMA, 8 epilogue warps; peer: TMA, 8 epilogue warps
-constexpr size_t kAuxBytes2 = 256 /*barriers, tmem ptr, work queue*/ + 2 * kTileN * 4 + 4 * kTileN * 4;
-constexpr size_t kSmemBytes2x = (size_t)kStages2 * kStageBytes2 + kAuxBytes2;
-
-// A role's view of the work queue: wait for entry q, read it, hand the entry back to the scheduler.
-struct WorkQueue {
-  uint64_t* sfull;
-  uint64_t* sempty;
-  const int2* slots;
-  int q = 0;
-  uint32_t ph = 0;
-  int rank;
-  // whole-warp call (every lane returns the entry; lane 0 releases it) or single-thread call (`solo`)
-  __device__ __forceinline__ int2 next(bool solo) {
-    mbar_wait_cluster(&sfull[q], ph);
-    const int2 e = slots[q];
-    if (!solo) __syncwarp();
-    if (solo || (threadIdx.x & 31) == 0) {
-      if (rank == 0)
-        mbar_arrive_relaxed(&sempty[q], e.x);
-      else
-        mbar_arrive_rank_relaxed(&sempty[q], 0, e.x);
-    }
-    if (++q == kQ) {
-      q = 0;
-      ph ^= 1;
-    }
-    return e;
-  }
-};
-
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 rf_i8x2_kernel(const __grid_constant__ CUtensorMap tm, int nkb, const int* __restrict__ nbits,
                const int2* __restrict__ tile_meta, long long n_slots, const uint32_t* __restrict__ walk_tiles, int nb,
@@ -762,352 +498,6 @@ rf_i8x2_kernel(const __grid_constant__ CUtensorMap tm, int nkb, const int* __res
 }
 
 
-// =====================================================================================================
-// K2-fp4: the same contraction on the block-scaled FP4 path of the tensor cores, which issues twice the
-// K per instruction.  A clade indicator is an e2m1 nibble (1.0 = 0x2), every scale factor is 2^0 (UE8M0
-// 0x7F in every byte of the scale-factor columns of TMEM, so their layout does not matter), accumulators are
-// f32: a dot product of two indicator rows is an integer below 2^24 and therefore exact (tools/fp4_probe.cu).
-// Differences from rf_i8x2_kernel:
-//   * TMEM holds two 240-column accumulators + 2 x 16 scale-factor columns (512 in all), so a tile is 256 rows x
-//     240 columns; the operand layout has 240 trees per 256-row block (PsrfLayout::block_real), the 16 padding
-//     rows of the row operand are masked out of the column sums;
-//   * cta_group::2 splits B in halves of N/2 = 120 rows: CTA 1 loads the rows from 120 on;
-//   * one K block is 128 bytes = 256 clades, 4 MMAs of K = 64.
-// =====================================================================================================
-constexpr int kTileNF = 240;
-constexpr int kSfaCol = 480, kSfbCol = 496;
-// The MMA needs half the time per tile, so the epilogue gets more warps: 12, three per TMEM lane quadrant,
-// each with five of the 15 chunks of 16 columns.
-constexpr int kEpiWarpsF = 12;
-constexpr int kThreadsF = 128 + kEpiWarpsF * 32;
-constexpr int kSchedConsumersF = 2 + kEpiWarpsF + 1 + kEpiWarpsF;
-constexpr uint32_t kF32Magic = 0x4AC00000u;  // bits of 1.5 * 2^22 (ulp 0.5): see the epilogue
-constexpr uint32_t kIdescF4 = (1u << 7) | (1u << 10) | ((uint32_t)(kTileNF >> 3) << 17) | (1u << 23) | ((uint32_t)(256 >> 4) << 24);
-
-__device__ __forceinline__ void umma_f4_2sm(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
-                                            uint32_t sfa, uint32_t sfb) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n\t}" ::"r"(tmem_c),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(sfa), "r"(sfb)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsF, 1)
-rf_f4x2_kernel(const __grid_constant__ CUtensorMap tm, int nkb, const int* __restrict__ nbits,
-               const int2* __restrict__ tile_meta, long long n_slots, const uint32_t* __restrict__ walk_tiles, int nb,
-               int shard_index, int shard_count, unsigned long long* __restrict__ slot_counter,
-               unsigned long long* __restrict__ S, int C, int dbg) {
-  extern __shared__ __align__(1024) unsigned char smem[];
-  if ((smem_u32(smem) & 1023u) != 0) __trap();
-  unsigned char* aux = smem + (size_t)kStages2 * kStageBytes2;
-  uint64_t* full = reinterpret_cast<uint64_t*>(aux);  // [kStages2]   (used in CTA 0)
-  uint64_t* empty = full + kStages2;                  // [kStages2]   (each CTA)
-  uint64_t* tfull = empty + kStages2;                 // [2]          (each CTA)
-  uint64_t* tempty = tfull + 2;                       // [2]          (used in CTA 0)
-  uint64_t* sfull = tempty + 2;                       // [kQ]         (each CTA)
-  uint64_t* sempty = sfull + kQ;                      // [kQ]         (used in CTA 0)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sempty + kQ);
-  int2* slots = reinterpret_cast<int2*>(aux + 208);   // [kQ] work queue entries {ib, jb}, {-1,-1} = stop
-  int* nb_s = reinterpret_cast<int*>(aux + 256);
-  uint32_t* colpart = reinterpret_cast<uint32_t*>(aux + 256 + 2 * kTileN * 4);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rank = (int)cluster_ctarank();
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages2; s++) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
-    }
-    for (int a = 0; a < 2; a++) {
-      mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 2 * kEpiWarpsF);
-    }
-    for (int q = 0; q < kQ; q++) {
-      mbar_init(&sfull[q], 1);
-      mbar_init(&sempty[q], kSchedConsumersF);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  cluster_sync_all();  // the peer's barriers exist before anything can arrive on them
-  if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(kTmemCols));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-  if (warp >= 4 && warp < 8) {  // unit scale factors in both CTAs: 32 columns x 128 lanes of 0x7F bytes
-    const uint32_t t = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)kSfaCol;
-    const uint32_t v = 0x7F7F7F7Fu;
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
-        "%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(t),
-        "r"(v)
-        : "memory");
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();  // the peer's scale factors are in place before the leader issues for both CTAs
-  tc_fence_after();
-
-  WorkQueue wq;
-  wq.sfull = sfull;
-  wq.sempty = sempty;
-  wq.slots = slots;
-  wq.rank = rank;
-
-  if (warp == 3) {
-    // ===== scheduler (leader CTA): draws the next block pair of the Morton walk for the whole cluster =====
-    if (rank == 0 && lane == 0) {
-      int q = 0;
-      uint32_t ph = 0;
-      for (;;) {
-        mbar_wait_cluster(&sempty[q], ph ^ 1);
-        int ib = -1, jb = -1;
-        for (;;) {
-          const long long t = (long long)atomicAdd(slot_counter, 1ULL) * shard_count + shard_index;
-          if (t >= n_slots) {
-            ib = jb = -1;
-            break;
-          }
-          const uint32_t tile = walk_tiles[t >> 6];
-          const unsigned long long local = (unsigned long long)(t & 63);
-          ib = (int)(tile & 0xFFFFu) * 8 + (int)compact_bits(local);
-          jb = (int)(tile >> 16) * 8 + (int)compact_bits(local >> 1);
-          PairInfo tmp;
-          if (ib <= jb && jb < nb && pair_flags(ib, jb, 0, tile_meta, tmp)) break;
-        }
-        slots[q] = make_int2(ib, jb);
-        st_int2_rank(&slots[q], 1, ib, jb);
-        mbar_arrive_rank(&sfull[q], 0);
-        mbar_arrive_rank(&sfull[q], 1);
-        if (ib < 0) break;
-        if (++q == kQ) {
-          q = 0;
-          ph ^= 1;
-        }
-      }
-    }
-  } else if (warp == 0) {
-    // ===== TMA producer (both CTAs; completion bytes go to CTA 0's full barrier) =====
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (;;) {
-        const int2 e = wq.next(true);
-        if (e.x < 0) break;
-        for (int kb = 0; kb < nkb; kb++) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          unsigned char* st = smem + (size_t)stage * kStageBytes2;
-          if (rank == 0) mbar_expect_tx(&full[stage], 2 * kStageBytes2);  // bytes of both CTAs
-          tma_load_2d_2sm(st, &tm, kb * kBlockK, e.x * kBlockRows + rank * kTileRows, &full[stage]);
-          // B half of this CTA: columns [rank*120, rank*120 + 120) of the tile (the box brings 8 rows more)
-          tma_load_2d_2sm(st + kABytes, &tm, kb * kBlockK, e.y * kBlockRows + rank * (kTileNF / 2), &full[stage]);
-          if (++stage == kStages2) {
-            stage = 0;
-            phase ^= 1;
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===== MMA issuer (leader CTA only) =====
-    // The whole warp walks the loop (so that stage, phase and the descriptors are warp-uniform and live in the
-    // uniform datapath: no R2UR per K block) and one elected lane issues.
-    if (rank == 0) {
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      const uint32_t sfa = tmem_base + (uint32_t)kSfaCol, sfb = tmem_base + (uint32_t)kSfbCol;
-      const uint32_t smem_base = smem_u32(smem);
-      for (;;) {
-        const int2 e = wq.next(false);
-        if (e.x < 0) break;
-        mbar_wait_cluster(&tempty[acc], acc_phase ^ 1);  // both CTAs' epilogues have drained this accumulator
-        tc_fence_after();
-        const uint32_t tmem_c = tmem_base + (uint32_t)(acc * kTileNF);
-        for (int kb = 0; kb < nkb; kb++) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint32_t a_addr = smem_base + (uint32_t)stage * kStageBytes2;
-            const uint64_t adesc = make_desc(a_addr), bdesc = make_desc(a_addr + kABytes);
-#pragma unroll
-            for (int kk = 0; kk < kBlockK / 32; kk++)
-              umma_f4_2sm(tmem_c, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), kIdescF4, (uint32_t)((kb | kk) != 0),
-                          sfa, sfb);
-            umma_commit_2sm(&empty[stage]);
-          }
-          __syncwarp();
-          if (++stage == kStages2) {
-            stage = 0;
-            phase ^= 1;
-          }
-        }
-        if (elect_one()) umma_commit_2sm(&tfull[acc]);
-        __syncwarp();
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1;
-        }
-      }
-    }
-  } else if (warp >= 4) {
-    // ===== epilogue (each CTA: its 128 rows x 240 columns) =====
-    // Integer arithmetic on the f32 accumulators in three instructions per element and without F2I (quarter rate):
-    // with c = 1.5*2^22 + |a|/2 (ulp 0.5, exact), bits(c - dot) = bits(1.5*2^22) + |a| - 2 dot, and nb_s holds
-    // |b| + 1 - bits(1.5*2^22), so d + 1 = bits(c - dot) + nb_s (mod 2^32).
-    // The accumulator is read into registers in one go and handed back to the MMA warp before the arithmetic
-    // starts, so the tensor core never waits for the epilogue's math, only for its TMEM reads.
-    const int ew = warp - 4;
-    const int quad = warp & 3;
-    const int slice = ew >> 2;
-    const int et = threadIdx.x - 128;
-    constexpr int kSlices = kEpiWarpsF / 4, kChunks = kTileNF / 16, kCPW = kChunks / kSlices;
-    static_assert(kCPW * kSlices == kChunks, "chunks must split evenly over the warps of a quadrant");
-    const int c_begin = slice * kCPW;
-    // rows 240..255 of a block are padding: they must not count as columns of the statistic in the column sums
-    const bool pad_warp = rank == 1 && quad == 3;
-    const uint32_t col_mask = (rank * kTileRows + quad * 32 + lane) < kTileNF ? 0xFFFFFFFFu : 0u;
-    uint32_t* nbu = reinterpret_cast<uint32_t*>(nb_s);
-    int acc = 0, buf = 0;
-    uint32_t acc_phase = 0;
-    for (;;) {
-      const int2 e = wq.next(false);
-      if (e.x < 0) break;
-      PairInfo pi;
-      pair_flags(e.x, e.y, rank, tile_meta, pi);
-      const long long col0 = (long long)pi.jb * kBlockRows;
-      const long long row = (long long)pi.ib * kBlockRows + rank * kTileRows + quad * 32 + lane;
-      if (et < kTileNF) nbu[buf * kTileN + et] = (uint32_t)(nbits[col0 + et] + 1) - kF32Magic;
-      const float cfa = __fadd_rn(__uint_as_float(kF32Magic), __fmul_rn(0.5f, (float)nbits[row]));
-      asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarpsF * 32) : "memory");
-      mbar_wait(&tfull[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kTileNF + c_begin * 16);
-      uint32_t r[kCPW][16];
-#pragma unroll
-      for (int cc = 0; cc < kCPW; cc++) tmem_ld16_nowait(taddr + cc * 16, r[cc]);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-      for (int cc = 0; cc < kCPW; cc++)  // the registers are defined only now: nothing that reads them may move above the wait
-        asm volatile("" : "+r"(r[cc][0]), "+r"(r[cc][1]), "+r"(r[cc][2]), "+r"(r[cc][3]), "+r"(r[cc][4]), "+r"(r[cc][5]),
-                          "+r"(r[cc][6]), "+r"(r[cc][7]), "+r"(r[cc][8]), "+r"(r[cc][9]), "+r"(r[cc][10]), "+r"(r[cc][11]),
-                          "+r"(r[cc][12]), "+r"(r[cc][13]), "+r"(r[cc][14]), "+r"(r[cc][15]));
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {  // the TMEM reads are complete and fenced: the accumulator goes back before the math
-        if (rank == 0)
-          mbar_arrive_relaxed(&tempty[acc], (int)r[0][0]);
-        else
-          mbar_arrive_rank_relaxed(&tempty[acc], 0, (int)r[0][0]);
-      }
-      unsigned long long row_sum = 0;
-      if (!(dbg & 1)) {
-#pragma unroll
-        for (int cc = 0; cc < kCPW; cc++) {
-          uint32_t nbv[16];
-          {
-            const uint4* nb4 = reinterpret_cast<const uint4*>(nbu + buf * kTileN + (c_begin + cc) * 16);
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-              const uint4 t = nb4[q];
-              nbv[4 * q] = t.x, nbv[4 * q + 1] = t.y, nbv[4 * q + 2] = t.z, nbv[4 * q + 3] = t.w;
-            }
-          }
-          uint32_t chunk = 0;
-          if (pi.do_col) {
-            uint32_t cs[16];
-#pragma unroll
-            for (int j = 0; j < 16; j++) {
-              const uint32_t e2 = __float_as_uint(__fsub_rn(cfa, __uint_as_float(r[cc][j]))) + nbv[j];
-              const uint32_t v = e2 * e2;
-              chunk += v;
-              cs[j] = __reduce_add_sync(0xffffffffu, pad_warp ? (v & col_mask) : v);
-            }
-            if (lane == 0) {
-              uint4* dst = reinterpret_cast<uint4*>(colpart + quad * kTileN + (c_begin + cc) * 16);
-#pragma unroll
-              for (int q = 0; q < 4; q++) dst[q] = make_uint4(cs[4 * q], cs[4 * q + 1], cs[4 * q + 2], cs[4 * q + 3]);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; j++) {
-              const uint32_t e2 = __float_as_uint(__fsub_rn(cfa, __uint_as_float(r[cc][j]))) + nbv[j];
-              chunk += e2 * e2;
-            }
-          }
-          row_sum += chunk;
-        }
-      }
-      if (pi.do_row && !(dbg & 2)) atomicAdd(&S[(size_t)row * C + pi.chain_cols], row_sum);
-      if (pi.do_col && !(dbg & 2)) {
-        asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarpsF * 32) : "memory");
-        if (et < kTileNF) {
-          const uint32_t v = colpart[et] + colpart[kTileN + et] + colpart[2 * kTileN + et] + colpart[3 * kTileN + et];
-          atomicAdd(&S[(size_t)(col0 + et) * C + pi.chain_rows], (unsigned long long)v);
-        }
-      }
-      buf ^= 1;
-      if (++acc == 2) {
-        acc = 0;
-        acc_phase ^= 1;
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();  // neither CTA leaves (or frees TMEM) while the other may still signal it
-  if (warp == 2) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
-  }
-}
-
-// ---- host side ------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  });
-  return fn;
-}
-
-// [rows][bytes_per_row] uint8, boxes of 128 rows x 128 bytes, 128B swizzle
-int32_t make_tmap(asm_ctx* ctx, CUtensorMap* m, const void* base, uint64_t rows, uint64_t bytes_per_row) {
-  EncodeTiledFn enc = get_encode_fn();
-  if (!enc) return asm_fail(ctx, ASM_E_CUDA, "cuTensorMapEncodeTiled not available from the driver");
-  cuuint64_t dims[2] = {bytes_per_row, rows};
-  cuuint64_t strides[1] = {bytes_per_row};
-  cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)kTileRows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return asm_fail(ctx, ASM_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
-  return ASM_OK;
-}
-
 template <bool kDump>
 int32_t set_smem_attr(asm_ctx* ctx) {
   const uint32_t bit = kDump ? kAttrI8Dump : kAttrI8;
@@ -1142,38 +532,6 @@ __global__ void __launch_bounds__(256) expand_rows_kernel(const uint64_t* __rest
 }
 
 }  // namespace
-
-
-// The walk: 8x8 tiles of block pairs in Morton order, only the tiles that touch the triangle ib <= jb < nb
-// (built on the host when nb changes; 4 bytes per 64 pairs).  Inside a tile the 64 pairs are again in Morton
-// order, so any ~74 consecutive slots form a compact 2-D patch and almost every slot is a real pair.
-static int32_t ensure_walk(asm_ctx* ctx, long long nb) {
-  if (ctx->walk_nb == nb) return ASM_OK;
-  const long long nt = (nb + 7) / 8;
-  long long Pt = 1;
-  while (Pt < nt) Pt <<= 1;
-  auto compact = [](unsigned long long v) {
-    v &= 0x5555555555555555ULL;
-    v = (v | (v >> 1)) & 0x3333333333333333ULL;
-    v = (v | (v >> 2)) & 0x0F0F0F0F0F0F0F0FULL;
-    v = (v | (v >> 4)) & 0x00FF00FF00FF00FFULL;
-    v = (v | (v >> 8)) & 0x0000FFFF0000FFFFULL;
-    v = (v | (v >> 16)) & 0x00000000FFFFFFFFULL;
-    return (uint32_t)v;
-  };
-  std::vector<uint32_t>& tiles = ctx->walk_host;
-  tiles.clear();
-  for (unsigned long long m = 0; m < (unsigned long long)(Pt * Pt); m++) {
-    const uint32_t ti = compact(m), tj = compact(m >> 1);
-    if (ti <= tj && (long long)tj < nt) tiles.push_back(ti | (tj << 16));
-  }
-  int32_t rc;
-  if ((rc = asm_reserve(ctx, ctx->walk_dev, sizeof(uint32_t) * tiles.size())) != ASM_OK) return rc;
-  ASM_CUDA(ctx, cudaMemcpyAsync(ctx->walk_dev.p, tiles.data(), sizeof(uint32_t) * tiles.size(), cudaMemcpyHostToDevice,
-                                ctx->stream));
-  ctx->walk_nb = nb;
-  return ASM_OK;
-}
 
 static bool use_two_cta() {
   static int v = -1;
@@ -1242,44 +600,6 @@ int32_t rf_i8_sums(asm_ctx* ctx, asm_shard shard) {
         tm, tm, (int)(Dp / kBlockK), (const int*)ctx->nbits.p, (const int*)ctx->nbits.p, (const int2*)ctx->blk_meta.p,
         2 * n_slots, 0, (int)nb, G, shard.shard_index, shard.shard_count, (unsigned long long*)ctx->S_pad.p, L.C, nullptr,
         0);
-  }
-  ASM_CUDA(ctx, cudaGetLastError());
-  return ASM_OK;
-}
-
-int32_t rf_f4_sums(asm_ctx* ctx, asm_shard shard) {
-  PsrfLayout& L = ctx->layout;
-  if (L.block_real != kTileNF) return asm_fail(ctx, ASM_E_INVALID, "rf_f4: layout built for %d live rows per block", L.block_real);
-  const long long nb = L.Tp / kBlockRows;
-  const uint64_t pitch = (uint64_t)L.pitch4;
-  L.bits_used = (int64_t)pitch * 2;
-  if (pitch * 2 >= 5792) {  // same 32-bit epilogue sums as the int8 kernel
-    int32_t rcg = psrf_check_max_bits(ctx, 5791);
-    if (rcg != ASM_OK) return rcg;
-  }
-  CUtensorMap tm;
-  int32_t rc = make_tmap(ctx, &tm, ctx->opnd_f4.p, (uint64_t)L.Tp, pitch);
-  if (rc != ASM_OK) return rc;
-  const long long n_pairs = nb * (nb + 1) / 2;
-  L.tiles_total = n_pairs;
-  L.tiles_done = (n_pairs - shard.shard_index + shard.shard_count - 1) / shard.shard_count;
-  if (!(ctx->func_attr_done & kAttrF4x2)) {
-    ASM_CUDA(ctx, cudaFuncSetAttribute(rf_f4x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes2x));
-    ctx->func_attr_done |= kAttrF4x2;
-  }
-  if ((rc = ensure_walk(ctx, nb)) != ASM_OK) return rc;
-  const long long n_morton = (long long)ctx->walk_host.size() * 64;
-  if ((rc = asm_reserve(ctx, ctx->tile_counter, sizeof(unsigned long long))) != ASM_OK) return rc;
-  ASM_CUDA(ctx, cudaMemsetAsync(ctx->tile_counter.p, 0, sizeof(unsigned long long), ctx->stream));
-  const int clusters = (int)std::min<long long>(L.tiles_done, ctx->sm_count / 2);
-  if (clusters <= 0) return ASM_OK;
-  {
-    LaunchScope ls(ctx, ASM_K_RF_I8);
-    rf_f4x2_kernel<<<2 * clusters, kThreadsF, kSmemBytes2x, ctx->stream>>>(
-        tm, (int)(pitch / kBlockK), (const int*)ctx->nbits.p, (const int2*)ctx->blk_meta.p, n_morton,
-        (const uint32_t*)ctx->walk_dev.p, (int)nb, shard.shard_index, shard.shard_count,
-        (unsigned long long*)ctx->tile_counter.p, (unsigned long long*)ctx->S_pad.p, L.C,
-        getenv("ASM_F4_DEBUG") ? atoi(getenv("ASM_F4_DEBUG")) : 0);
   }
   ASM_CUDA(ctx, cudaGetLastError());
   return ASM_OK;
