@@ -137,7 +137,7 @@ int32_t psrf_finish(asm_ctx* ctx, const int64_t* d_S, int32_t n_rows, double* ps
 int32_t rf_popc_sums(asm_ctx* ctx, asm_shard shard);
 int32_t rf_popc_block(asm_ctx* ctx, int32_t chainA, int64_t r0, int64_t r1, int32_t chainB, int64_t c0, int64_t c1,
                       uint16_t* out_host);
-// rf_i8.cu
+// rf_i8.cu / rf_f4.cu (tc_common.cuh)
 int32_t rf_i8_sums(asm_ctx* ctx, asm_shard shard);
 int32_t rf_f4_sums(asm_ctx* ctx, asm_shard shard);  // block-scaled FP4 variant (layout with 240 live rows per block)
 int32_t rf_i8_block(asm_ctx* ctx, int32_t chainA, int64_t r0, int64_t r1, int32_t chainB, int64_t c0, int64_t c1,
