@@ -76,8 +76,6 @@ SIGNATURES = {
     "asm_encoder_clade_leaves": (_i32, [_p, _i64, _p, _i32]),
     "asm_encoder_words": (_i32, [_p]),
     "asm_encode_bits": (_i32, [_p, _i64, _i32, _i32, _p]),
-    "asm_synth_tree_chain": (_i32, [_i32, _i64, _u64, _u64, _i32, _f64, _p, _p, _p, _p, _p]),
-    "asm_synth_ar1": (_i32, [_p, _i64, _f64, _f64, _u64]),
 }
 
 _lib: Optional[C.CDLL] = None
@@ -174,31 +172,6 @@ class Encoder:
         if rc != ASM_OK:
             raise AsmGpuError(rc, "asm_encode_bits")
         return out
-
-
-def synth_tree_chain(n_taxa: int, n_trees: int, start_seed: int, chain_seed: int, moves_per_sample: int = 2,
-                     beta: float = 7.0, topologies: bool = True, encoder: Optional[Encoder] = None):
-    """asm_synth_tree_chain: returns (left, right, root, clade_ids); entries not requested are None."""
-    nn = 2 * n_taxa - 1
-    left = np.empty((n_trees, nn), dtype=np.int32) if topologies else None
-    right = np.empty((n_trees, nn), dtype=np.int32) if topologies else None
-    root = np.empty(n_trees, dtype=np.int32) if topologies else None
-    ids = np.empty((n_trees, n_taxa - 1), dtype=np.int32) if encoder is not None else None
-    rc = lib().asm_synth_tree_chain(n_taxa, n_trees, start_seed, chain_seed, moves_per_sample, beta, _ptr(left),
-                                    _ptr(right), _ptr(root), encoder.handle if encoder is not None else None, _ptr(ids))
-    if rc != ASM_OK:
-        raise AsmGpuError(rc, "asm_synth_tree_chain")
-    return left, right, root, ids
-
-
-def synth_ar1(n: int, mu: float, phi: float, seed: int, out: Optional[np.ndarray] = None) -> np.ndarray:
-    if out is None:
-        out = np.empty(n, dtype=np.float64)
-    assert out.flags.c_contiguous and out.dtype == np.float64 and out.shape[0] >= n
-    rc = lib().asm_synth_ar1(_ptr(out), n, mu, phi, seed)
-    if rc != ASM_OK:
-        raise AsmGpuError(rc, "asm_synth_ar1")
-    return out
 
 
 class GpuContext:

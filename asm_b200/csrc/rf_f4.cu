@@ -297,8 +297,10 @@ rf_f4x2_kernel(const __grid_constant__ CUtensorMap tm, int nkb, const int* __res
       if (pi.do_col && !(dbg & 2)) {
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarpsF * 32) : "memory");
         if (et < kTileNF) {
-          const uint32_t v = colpart[et] + colpart[kTileN + et] + colpart[2 * kTileN + et] + colpart[3 * kTileN + et];
-          atomicAdd(&S[(size_t)(col0 + et) * C + pi.chain_rows], (unsigned long long)v);
+          // each partial is a sum of 32 squares (< 2^32 by the clade-count guard); their sum of 128 may not be
+          const unsigned long long v = (unsigned long long)colpart[et] + colpart[kTileN + et] + colpart[2 * kTileN + et] +
+                                       colpart[3 * kTileN + et];
+          atomicAdd(&S[(size_t)(col0 + et) * C + pi.chain_rows], v);
         }
       }
       buf ^= 1;

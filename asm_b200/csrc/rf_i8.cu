@@ -239,8 +239,10 @@ rf_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (ti.do_row) atomicAdd(&S[(size_t)row * C + ti.chain_cols], row_sum);
         if (ti.do_col) {
           epi_barrier();
-          const uint32_t v = colpart[et] + colpart[kTileN + et] + colpart[2 * kTileN + et] + colpart[3 * kTileN + et];
-          atomicAdd(&S[(size_t)(col0 + et) * C + ti.chain_rows], (unsigned long long)v);
+          // each partial is a sum of 32 squares (< 2^32 by the clade-count guard); their sum of 128 may not be
+          const unsigned long long v = (unsigned long long)colpart[et] + colpart[kTileN + et] + colpart[2 * kTileN + et] +
+                                       colpart[3 * kTileN + et];
+          atomicAdd(&S[(size_t)(col0 + et) * C + ti.chain_rows], v);
         }
       }
       buf ^= 1;
@@ -478,8 +480,10 @@ rf_i8x2_kernel(const __grid_constant__ CUtensorMap tm, int nkb, const int* __res
       if (pi.do_row) atomicAdd(&S[(size_t)row * C + pi.chain_cols], row_sum);
       if (pi.do_col) {
         epi_barrier();
-        const uint32_t v = colpart[et] + colpart[kTileN + et] + colpart[2 * kTileN + et] + colpart[3 * kTileN + et];
-        atomicAdd(&S[(size_t)(col0 + et) * C + pi.chain_rows], (unsigned long long)v);
+        // each partial is a sum of 32 squares (< 2^32 by the clade-count guard); their sum of 128 may not be
+          const unsigned long long v = (unsigned long long)colpart[et] + colpart[kTileN + et] + colpart[2 * kTileN + et] +
+                                       colpart[3 * kTileN + et];
+        atomicAdd(&S[(size_t)(col0 + et) * C + pi.chain_rows], v);
       }
       buf ^= 1;
       if (++acc == 2) {

@@ -118,13 +118,12 @@ def gen_psrf_input(cfg, n_trees, want_topologies=False):
     Chains longer than cfg["n_trees"] (the weak-scaling runs at N > 1 GPUs) keep the first cfg["n_trees"]
     generated trees and append a seeded resample of them, so the clade dictionary -- the K dimension of the
     contraction, i.e. the work per tree pair -- is the same at every N."""
-    import asm_b200 as A
-    from asm_b200 import _lib as L
-    enc = A.Encoder(cfg["n_taxa"])
+    import synthgen as G
+    enc = G.Encoder(cfg["n_taxa"])  # the generator's own dictionary: input generation uses nothing of libasmgpu.so
     n_base = min(n_trees, cfg["n_trees"])
     ids, topo = [], []
     for c in range(cfg["n_chains"]):
-        l, r, root, i = L.synth_tree_chain(cfg["n_taxa"], n_base, cfg["start_seed"], cfg["seed0"] + c, cfg["moves"],
+        l, r, root, i = G.synth_tree_chain(cfg["n_taxa"], n_base, cfg["start_seed"], cfg["seed0"] + c, cfg["moves"],
                                            cfg["beta"], topologies=want_topologies, encoder=enc)
         if n_trees > n_base:
             pick = np.random.default_rng(cfg["seed0"] + 1000 + c).integers(0, n_base, n_trees - n_base)
@@ -140,12 +139,12 @@ def gen_psrf_input(cfg, n_trees, want_topologies=False):
 
 def gen_traces(n_traces, n_samples, seed0, first=0, out=None):
     from concurrent.futures import ThreadPoolExecutor
-    from asm_b200 import _lib as L
+    import synthgen as G
     x = np.empty((n_traces, n_samples), dtype=np.float64) if out is None else out
 
     def one(j):
         g = first + j
-        L.synth_ar1(n_samples, MUS[g % 3], PHIS[g % 4], seed0 + g, out=x[j])
+        G.synth_ar1(n_samples, MUS[g % 3], PHIS[g % 4], seed0 + g, out=x[j])
 
     with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 1)) as ex:
         list(ex.map(one, range(n_traces)))
@@ -166,10 +165,10 @@ def pinned_like(a: np.ndarray):
 # --------------------------------------------------------------------------------------------------
 def oracle_tree_set(cfg, n_trees):
     import oracle as O
-    from asm_b200 import _lib as L
+    import synthgen as G
     ts = O.TreeSet(cfg["n_chains"], cfg["n_taxa"])
     for c in range(cfg["n_chains"]):
-        l, r, root, _ = L.synth_tree_chain(cfg["n_taxa"], n_trees, cfg["start_seed"], cfg["seed0"] + c, cfg["moves"],
+        l, r, root, _ = G.synth_tree_chain(cfg["n_taxa"], n_trees, cfg["start_seed"], cfg["seed0"] + c, cfg["moves"],
                                            cfg["beta"])
         ts.add(c, l, r, root)
     return ts
@@ -233,6 +232,8 @@ def run_reference(args):
     if rank != 0:
         return
     steps, warm = args.steps, args.warmup
+    import oracle as O
+    O.use_all_cores()  # torchrun exports OMP_NUM_THREADS=1 to its children; the CPU arm uses every host core it may
     if args.workload == "ess":
         n = CFG3["n_samples"]
         vals = []
@@ -264,6 +265,8 @@ def run_reference(args):
                 "config": {"workload": f"{cfg['n_chains']} chains x {n_trees} trees x {cfg['n_taxa']} taxa (bounded row sample per step)"},
                 "cpu_baseline": {k: vals[-1][k] for k in ("kind", "cores", "sample")} | {"value": v, "unit": "tree-pairs/s"},
                 "e2e": {"value": v, "unit": "tree-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    with open("/proc/self/maps") as f:  # evidence: this arm maps the oracle and the input generators, not the product
+        line["native_libs"] = sorted({os.path.relpath(l.split()[-1], ROOT) for l in f if l.rstrip().endswith(".so") and ROOT in l})
     _emit(line)
 
 
@@ -271,6 +274,7 @@ def run_reference(args):
 def bench_psrf(args, rank, world, local, dist):
     import asm_b200 as A
     from asm_b200 import _lib as L
+    import synthgen as G
     peaks = measured_peaks()
     cfg = CFG5 if args.workload == "cfg5" else CFG2
     n_trees = cfg["n_trees"] if args.workload == "cfg5" else int(round(cfg["n_trees"] * math.sqrt(world)))
@@ -473,6 +477,7 @@ def bench_psrf(args, rank, world, local, dist):
 def bench_ess(args, rank, world, local, dist, n_traces=None):
     import asm_b200 as A
     from asm_b200 import _lib as L
+    import synthgen as G
     import torch
     peaks = measured_peaks()
     n_tr = n_traces or CFG3["n_traces"]

@@ -93,6 +93,7 @@ def lib() -> C.CDLL:
         L.orc_clade_difference_converged.restype = _i32
         L.orc_clade_difference_converged.argtypes = [_p, _i32, _i32, _f64, C.POINTER(_f64)]
         L.orc_num_threads.restype = _i32
+        L.orc_set_num_threads.argtypes = [_i32]
         _lib = L
     return _lib
 
@@ -291,6 +292,17 @@ def clade_difference_converged(ts: "TreeSet", available: int, threshold: float =
 
 def num_threads() -> int:
     return int(lib().orc_num_threads())
+
+
+def use_all_cores() -> int:
+    """Make the OpenMP loops use every core this process may run on, whatever OMP_NUM_THREADS says
+    (torchrun exports OMP_NUM_THREADS=1 to its children).  Returns the thread count."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    lib().orc_set_num_threads(max(n, 1))
+    return num_threads()
 
 
 def combine_logs(tree_mode: bool, chain_paths, burnin, last_reported: int, sample_delta: int) -> str:

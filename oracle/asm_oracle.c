@@ -807,6 +807,16 @@ int32_t orc_num_threads(void) {
 #endif
 }
 
+/* Launchers such as torchrun export OMP_NUM_THREADS=1 to their children; the timing harness asks for
+ * the host's cores explicitly. */
+void orc_set_num_threads(int32_t n) {
+#ifdef _OPENMP
+  if (n >= 1) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 /* ------------------------------------------------------------------------------------------
  * GelmanRubin (GelmanRubin.java) and CladeDifference (CladeDifference.java) criteria
  * ---------------------------------------------------------------------------------------- */

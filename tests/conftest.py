@@ -21,6 +21,7 @@ class SynthChains:
     def __init__(self, n_taxa, n_trees, n_chains, beta, moves=2, start_seed=1, seed0=20240001):
         import asm_b200 as A
         from asm_b200 import _lib as L
+        import synthgen as G
         import oracle as O
 
         self.n_taxa, self.n_chains = n_taxa, n_chains
@@ -29,7 +30,7 @@ class SynthChains:
         self.ts = O.TreeSet(n_chains, n_taxa)
         self.topo, self.ids = [], []
         for c in range(n_chains):
-            l, r, root, _ = L.synth_tree_chain(n_taxa, self.n_trees[c], start_seed, seed0 + c, moves, beta)
+            l, r, root, _ = G.synth_tree_chain(n_taxa, self.n_trees[c], start_seed, seed0 + c, moves, beta)
             self.topo.append((l, r, root))
             self.ids.append(self.enc.add_topologies(l, r, root))
             self.ts.add(c, l, r, root)
@@ -62,6 +63,7 @@ def ragged_chains():
 def _have_gpu():
     try:
         from asm_b200 import _lib as L
+        import synthgen as G
         return L.lib().asm_device_count() > 0
     except Exception:
         return False
@@ -70,6 +72,7 @@ def _have_gpu():
 @pytest.fixture()
 def gpu():
     from asm_b200 import _lib as L
+    import synthgen as G
     if L.lib().asm_device_count() == 0:
         pytest.fail("no CUDA device: GPU tests must run on the B200 box (there is no CPU fallback)")
     return L

@@ -19,6 +19,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 import asm_b200 as A  # noqa: E402  (host encoder + generators only; no GPU involved)
 import oracle as O  # noqa: E402
 from asm_b200 import _lib as L  # noqa: E402
+import synthgen as G
 
 
 def psrf_fixture():
@@ -26,7 +27,7 @@ def psrf_fixture():
     enc, ts = A.Encoder(n_taxa), O.TreeSet(C, n_taxa)
     topo, bits = [], []
     for c in range(C):
-        l, r, root, _ = L.synth_tree_chain(n_taxa, n_trees, 7, 500 + c, 2, 1.8)
+        l, r, root, _ = G.synth_tree_chain(n_taxa, n_trees, 7, 500 + c, 2, 1.8)
         ts.add(c, l, r, root)
         topo.append((l, r, root))
         bits.append(enc.add_topologies(l, r, root))
@@ -58,7 +59,7 @@ def ess_fixture():
     lens = [1, 2, 7, 64, 1000, 2003, 5000]
     out = {"lens": np.array(lens)}
     for n in lens:
-        x = np.stack([L.synth_ar1(n, mu, phi, 900 + i) for i, (mu, phi) in
+        x = np.stack([G.synth_ar1(n, mu, phi, 900 + i) for i, (mu, phi) in
                       enumerate([(0.0, 0.0), (1.0, 0.5), (-1e4, 0.9), (0.0, 0.99)])])
         act, ess = O.ess_batch(x, literal=(n <= 2003))
         out[f"x{n}"], out[f"act{n}"], out[f"ess{n}"] = x, act, ess

@@ -252,14 +252,15 @@ class Replay:
 def make_run(tmpdir, n_taxa, n_chains, n_samples, beta, seed, burn_len=40):
     """Synthetic chains -> files on disk.  Traces: AR(1) around a level that relaxes from a bad start."""
     from asm_b200 import _lib as L
+    import synthgen as G
     prefixes = []
     for c in range(n_chains):
-        l, r, root, _ = L.synth_tree_chain(n_taxa, n_samples + 2, 11, seed + c, 2, beta)
+        l, r, root, _ = G.synth_tree_chain(n_taxa, n_samples + 2, 11, seed + c, 2, beta)
         rng = np.random.default_rng(seed + 100 + c)
         t = np.arange(n_samples + 2)
         cols = []
         for j, (mu, phi) in enumerate([(-5000.0, 0.6), (-4800.0, 0.5), (-200.0, 0.3), (0.5, 0.7)]):
-            x = L.synth_ar1(n_samples + 2, 0.0, phi, seed * 7 + c * 13 + j)
+            x = G.synth_ar1(n_samples + 2, 0.0, phi, seed * 7 + c * 13 + j)
             cols.append(mu + x * (1 + j) - 300.0 * np.exp(-t / (burn_len / 3.0)) * (1 + 0.1 * c))
         cols[0] = cols[1] + cols[2]  # posterior = likelihood + prior
         p = os.path.join(str(tmpdir), f"chain{c}-run")

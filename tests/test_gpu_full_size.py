@@ -61,10 +61,11 @@ def test_cfg2_full_size_properties(gpu, cfg2):
 def test_cfg3_sized_ess_properties(gpu):
     import torch
     from asm_b200 import _lib as L
+    import synthgen as G
     n_tr, n = 64, 1_000_000
     x = np.empty((n_tr, n))
     for j in range(n_tr):
-        L.synth_ar1(n, [0.0, 1.0, -1e4][j % 3], [0.0, 0.5, 0.9, 0.99][j % 4], 777 + j, out=x[j])
+        G.synth_ar1(n, [0.0, 1.0, -1e4][j % 3], [0.0, 0.5, 0.9, 0.99][j % 4], 777 + j, out=x[j])
     with gpu.GpuContext(1) as ctx:
         act, ess = ctx.ess_batch(x)
         act4, ess4 = ctx.ess_batch(x * 4.0)                     # exact in binary floating point

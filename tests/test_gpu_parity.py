@@ -191,10 +191,11 @@ def test_streaming_append_and_dictionary_growth(gpu, small_chains):
 # ---------------------------------------------------------------- ESS (TraceESS.java:126-179)
 def _traces(n_tr, n, seed=777):
     from asm_b200 import _lib as L
+    import synthgen as G
     phis, mus = [0.0, 0.5, 0.9, 0.99], [0.0, 1.0, -1e4]
     x = np.empty((n_tr, n))
     for j in range(n_tr):
-        L.synth_ar1(n, mus[j % 3], phis[j % 4], seed + j, out=x[j])
+        G.synth_ar1(n, mus[j % 3], phis[j % 4], seed + j, out=x[j])
     return x
 
 
@@ -214,10 +215,11 @@ def test_ess_staged_equals_all_lags_and_wide_path(gpu):
     """Staged (adaptive) lag evaluation must be bit-identical to evaluating every lag, on both thread shapes
     (R = 4 for few open chains, R = 8 for many)."""
     from asm_b200 import _lib as L
+    import synthgen as G
     n_tr, n = 2200, 2600
     x = np.empty((n_tr, n))
     for j in range(n_tr):
-        L.synth_ar1(n, [0.0, -1e4][j % 2], [0.0, 0.9, 0.99, 0.999][j % 4], 4000 + j, out=x[j])
+        G.synth_ar1(n, [0.0, -1e4][j % 2], [0.0, 0.9, 0.99, 0.999][j % 4], 4000 + j, out=x[j])
     want_act, want_ess = O.ess_batch(x)
     with gpu.GpuContext(1) as ctx:
         act_a, ess_a = ctx.ess_batch(x)
@@ -236,10 +238,11 @@ def test_ess_every_thread_shape(gpu, lags_per_thread, n, monkeypatch):
     """Each lags-per-thread instantiation of the lag kernel (normally picked by the cost model) on its own,
     on a ragged length, staged and unstaged."""
     from asm_b200 import _lib as L
+    import synthgen as G
     n_tr = 37
     x = np.empty((n_tr, n))
     for j in range(n_tr):
-        L.synth_ar1(n, [0.0, 1.0, -1e4][j % 3], [0.0, 0.5, 0.9, 0.99, 0.999][j % 5], 9100 + j, out=x[j])
+        G.synth_ar1(n, [0.0, 1.0, -1e4][j % 3], [0.0, 0.5, 0.9, 0.99, 0.999][j % 5], 9100 + j, out=x[j])
     want_act, want_ess = O.ess_batch(x)
     monkeypatch.setenv("ASM_ESS_R", ",".join([str(lags_per_thread)] * 5))
     with gpu.GpuContext(1) as ctx:
@@ -255,10 +258,11 @@ def test_ess_host_upload_groups_and_stage_plans(gpu, plan, monkeypatch):
     (five / three / two stages or all lags at once), served by a polling host loop.  Normally that engages
     only for gigabyte inputs; ASM_ESS_H2D_PLAN forces it on a small one."""
     from asm_b200 import _lib as L
+    import synthgen as G
     n_tr, n = 42, 5003
     x = np.empty((n_tr, n))
     for j in range(n_tr):
-        L.synth_ar1(n, [0.0, -1e4][j % 2], [0.0, 0.5, 0.9, 0.99, 0.999][j % 5], 8800 + j, out=x[j])
+        G.synth_ar1(n, [0.0, -1e4][j % 2], [0.0, 0.5, 0.9, 0.99, 0.999][j % 5], 8800 + j, out=x[j])
     want_act, want_ess = O.ess_batch(x)
     monkeypatch.setenv("ASM_ESS_H2D_PLAN", plan)
     with gpu.GpuContext(1) as ctx:
@@ -272,10 +276,11 @@ def test_ess_narrowed_stage(gpu):
     """More open traces in a late stage than one wave of warps holds (148 SMs x 4 sub-partitions): the stage is
     narrowed to a single wave and the next one picks up the rest.  Same bits as the oracle and as all lags."""
     from asm_b200 import _lib as L
+    import synthgen as G
     n_tr, n = 130, 2500
     x = np.empty((n_tr, n))
     for j in range(n_tr):
-        L.synth_ar1(n, 0.0, 0.9995 if j < 100 else 0.3, 7300 + j, out=x[j])
+        G.synth_ar1(n, 0.0, 0.9995 if j < 100 else 0.3, 7300 + j, out=x[j])
     want_act, want_ess = O.ess_batch(x)
     with gpu.GpuContext(1) as ctx:
         act, ess = ctx.ess_batch(x)

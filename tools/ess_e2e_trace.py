@@ -4,13 +4,14 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import asm_b200 as A
 from asm_b200 import _lib as L
+import synthgen as G
 import bench
 from concurrent.futures import ThreadPoolExecutor
 n_tr, n = 1000, 1_000_000
 ctx = A.GpuContext(1)
 host = np.empty((n_tr, n))
 def one(j):
-    L.synth_ar1(n, bench.MUS[j % 3], bench.PHIS[j % 4], 777 + j, out=host[j])
+    G.synth_ar1(n, bench.MUS[j % 3], bench.PHIS[j % 4], 777 + j, out=host[j])
 with ThreadPoolExecutor(32) as ex:
     list(ex.map(one, range(n_tr)))
 t, hp = bench.pinned_like(host)

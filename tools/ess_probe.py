@@ -6,6 +6,7 @@ import numpy as np
 import torch
 import asm_b200 as A
 from asm_b200 import _lib as L
+import synthgen as G
 import bench
 
 n_tr, n = 1000, 1_000_000
@@ -15,7 +16,7 @@ res = {}
 for name, phis in {"phi0_only_stage0": [0.0], "phi099_all": [0.99], "mix": bench.PHIS}.items():
     from concurrent.futures import ThreadPoolExecutor
     def one(j):
-        L.synth_ar1(n, 0.0, phis[j % len(phis)], 777 + j, out=host[j])
+        G.synth_ar1(n, 0.0, phis[j % len(phis)], 777 + j, out=host[j])
     with ThreadPoolExecutor(32) as ex:
         list(ex.map(one, range(n_tr)))
     dev = torch.from_numpy(host).cuda()

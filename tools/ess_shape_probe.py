@@ -7,6 +7,7 @@ import numpy as np
 import torch
 import asm_b200 as A
 from asm_b200 import _lib as L
+import synthgen as G
 import bench
 from concurrent.futures import ThreadPoolExecutor
 
@@ -14,7 +15,7 @@ n_tr, n = 1000, 1_000_000
 ctx = A.GpuContext(1)
 host = np.empty((n_tr, n))
 def one(j):
-    L.synth_ar1(n, bench.MUS[j % 3], bench.PHIS[j % 4], 777 + j, out=host[j])
+    G.synth_ar1(n, bench.MUS[j % 3], bench.PHIS[j % 4], 777 + j, out=host[j])
 with ThreadPoolExecutor(32) as ex:
     list(ex.map(one, range(n_tr)))
 dev = torch.from_numpy(host).cuda()

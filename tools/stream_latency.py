@@ -6,6 +6,7 @@ import numpy as np
 import asm_b200 as A
 import oracle as O
 from asm_b200 import _lib as L
+import synthgen as G
 
 n_taxa, C = 35, 2
 res = []
@@ -13,12 +14,12 @@ for m in (100, 200, 1000, 5000, 20000, 50000):
     enc, ts = A.Encoder(n_taxa), O.TreeSet(C, n_taxa)
     bits = []
     for c in range(C):
-        l, r, root, _ = L.synth_tree_chain(n_taxa, m, 1, 50 + c, 2, 2.4)
+        l, r, root, _ = G.synth_tree_chain(n_taxa, m, 1, 50 + c, 2, 2.4)
         ids = enc.add_topologies(l, r, root)
         ts.add(c, l, r, root)
         bits.append(ids)
     bits = [enc.bits(b) for b in bits]
-    x = np.stack([np.stack([L.synth_ar1(m, 0.0, 0.9, 10 * c + j) for j in range(4)]) for c in range(C)])
+    x = np.stack([np.stack([G.synth_ar1(m, 0.0, 0.9, 10 * c + j) for j in range(4)]) for c in range(C)])
     with A.GpuContext(C) as ctx:
         for c in range(C):
             ctx.trees_set(c, bits[c])
