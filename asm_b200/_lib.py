@@ -38,6 +38,12 @@ SIGNATURES = {
     "asm_device_count": (_i32, []),
     "asm_create": (_i32, [C.POINTER(_p), _i32, _i32]),
     "asm_destroy": (_i32, [_p]),
+    "asm_create_multi": (_i32, [C.POINTER(_p), _p, _i32, _i32]),
+    "asm_comm_unique_id": (_i32, [_p]),
+    "asm_comm_init_rank": (_i32, [_p, _p, _i32, _i32]),
+    "asm_comm_info": (_i32, [_p, _i32p, _i32p, _i32p]),
+    "asm_comm_nccl_version": (_i32, []),
+    "asm_comm_all_gather_f64": (_i32, [_p, _p, _i64, _p]),
     "asm_last_error": (C.c_char_p, [_p]),
     "asm_trees_set": (_i32, [_p, _i32, _i64, _i32, _p]),
     "asm_trees_append": (_i32, [_p, _i32, _i64, _i32, _p]),
@@ -53,6 +59,9 @@ SIGNATURES = {
     "asm_psrf_eval": (_i32, [_p, _p, _i32, _i32, _i32, _i32, _p, _p]),
     "asm_ess_batch": (_i32, [_p, _i32, _i64, _i64, _p, _i32, _p, _p]),
     "asm_ess_batch_device": (_i32, [_p, _i32, _i64, _i64, _p, _i32, _p, _p]),
+    "asm_ess_traces_put": (_i32, [_p, _i32, _i64, _i64, _p]),
+    "asm_ess_traces_count": (_i32, [_p, _i32p, _i64p]),
+    "asm_ess_traces_eval": (_i32, [_p, _i32, _p, _p]),
     "asm_traces_append": (_i32, [_p, _i32, _i32, _i64, _p]),
     "asm_traces_count": (_i32, [_p, _i32, _i64p, _i32p]),
     "asm_ess_eval": (_i32, [_p, _p, _i32, _p, _i32, _p]),
@@ -81,6 +90,24 @@ SIGNATURES = {
 _lib: Optional[C.CDLL] = None
 
 
+def _prefer_bundled_nccl():
+    """libasmgpu.so dlopens NCCL by soname on first multi-GPU use.  If this process later imports torch, torch needs
+    ITS OWN libnccl.so.2 (a newer one than the system's) under the same soname; point the library at that file now,
+    without importing torch, so that whichever loads first the process ends up with one NCCL that suits both."""
+    if os.environ.get("ASM_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for loc in (spec.submodule_search_locations or []) if spec else []:
+            cand = os.path.join(loc, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["ASM_NCCL_LIB"] = cand
+                return
+    except Exception:  # noqa: BLE001 -- no bundled NCCL: the library falls back to the system's libnccl.so.2
+        pass
+
+
 def load_library(path: str = LIB_PATH) -> C.CDLL:
     """Load libasmgpu.so and bind every symbol of the header.  Raises if the library is missing:
     there is no fallback implementation."""
@@ -89,6 +116,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
         return _lib
     if not os.path.exists(path):
         raise ImportError(f"{path} not found: build it with `make -C asm_b200/csrc` (or __graft_entry__.build())")
+    _prefer_bundled_nccl()
     lib_ = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib_, name)  # AttributeError if the ABI lost a symbol
@@ -174,16 +202,53 @@ class Encoder:
         return out
 
 
-class GpuContext:
-    """One asm_ctx = one GPU.  Mirrors the C ABI one to one; numpy arrays in, numpy arrays out."""
+ASM_COMM_ID_BYTES = 128
 
-    def __init__(self, n_chains: int, device: int = 0):
+
+def comm_unique_id() -> bytes:
+    """asm_comm_unique_id: the bytes rank 0 hands to the other ranks (over the launcher's own channel)."""
+    buf = (C.c_uint8 * ASM_COMM_ID_BYTES)()
+    rc = lib().asm_comm_unique_id(buf)
+    if rc != ASM_OK:
+        raise AsmGpuError(rc, (lib().asm_last_error(None) or b"").decode())
+    return bytes(buf)
+
+
+class GpuContext:
+    """One asm_ctx: one GPU (`device`) or several GPUs of one box driven from this process (`devices`,
+    asm_create_multi).  Mirrors the C ABI one to one; numpy arrays in, numpy arrays out."""
+
+    def __init__(self, n_chains: int, device: int = 0, devices: Optional[Sequence[int]] = None):
         self._h = C.c_void_p()
-        rc = lib().asm_create(C.byref(self._h), device, n_chains)
+        if devices is not None:
+            d = _i32arr(devices)
+            rc = lib().asm_create_multi(C.byref(self._h), _ptr(d), d.shape[0], n_chains)
+            device = int(d[0]) if d.shape[0] else 0
+        else:
+            rc = lib().asm_create(C.byref(self._h), device, n_chains)
         if rc != ASM_OK:
             raise AsmGpuError(rc, (lib().asm_last_error(None) or b"").decode())
         self.n_chains = n_chains
         self.device = device
+        self.devices = list(devices) if devices is not None else [device]
+
+    # ---- communicator (one process per GPU)
+    def comm_init_rank(self, comm_id: bytes, rank: int, n_ranks: int):
+        assert len(comm_id) == ASM_COMM_ID_BYTES
+        buf = (C.c_uint8 * ASM_COMM_ID_BYTES).from_buffer_copy(comm_id)
+        self._check(lib().asm_comm_init_rank(self._h, buf, rank, n_ranks))
+
+    def comm_info(self):
+        r, n, l = C.c_int32(), C.c_int32(), C.c_int32()
+        self._check(lib().asm_comm_info(self._h, C.byref(r), C.byref(n), C.byref(l)))
+        return {"rank": r.value, "n_ranks": n.value, "n_local_devices": l.value}
+
+    def all_gather_f64(self, local: np.ndarray) -> np.ndarray:
+        local = np.ascontiguousarray(local, dtype=np.float64)
+        n_ranks = self.comm_info()["n_ranks"] if len(self.devices) == 1 else 1
+        out = np.empty(local.shape[0] * n_ranks, dtype=np.float64)
+        self._check(lib().asm_comm_all_gather_f64(self._h, _ptr(local), local.shape[0], _ptr(out)))
+        return out
 
     def close(self):
         if getattr(self, "_h", None) and _lib is not None:
@@ -295,6 +360,21 @@ class GpuContext:
         ess = np.empty(n_traces, dtype=np.float64)
         self._check(lib().asm_ess_batch_device(self._h, n_traces, n_samples, stride, C.c_void_p(d_ptr), max_lag,
                                                _ptr(act), _ptr(ess)))
+        return act, ess
+
+    def ess_traces_put(self, traces: np.ndarray):
+        traces = np.asarray(traces, dtype=np.float64)
+        assert traces.ndim == 2 and (traces.strides[1] == 8 or traces.shape[1] <= 1)
+        n_tr, n = traces.shape
+        stride = traces.strides[0] // 8 if n_tr > 1 else max(n, 1)
+        self._check(lib().asm_ess_traces_put(self._h, n_tr, n, max(stride, n), _ptr(traces)))
+
+    def ess_traces_eval(self, max_lag: int = ASM_MAX_LAG):
+        n = C.c_int32()
+        self._check(lib().asm_ess_traces_count(self._h, C.byref(n), None))
+        act = np.empty(n.value, dtype=np.float64)
+        ess = np.empty(n.value, dtype=np.float64)
+        self._check(lib().asm_ess_traces_eval(self._h, max_lag, _ptr(act), _ptr(ess)))
         return act, ess
 
     def traces_append(self, chain: int, values: np.ndarray):

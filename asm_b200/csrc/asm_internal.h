@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -98,6 +99,19 @@ struct asm_ctx {
   int64_t launches = 0;
   bool ess_adaptive = true;     // staged lag evaluation (ess.cu)
   long long ess_lag_slots = 0;  // (trace, lag) chains evaluated by the last ESS call
+  // resident batch traces (asm_ess_traces_put): [ess_res_n][ess_res_stride] doubles
+  DevBuf ess_res;
+  int32_t ess_res_n = 0;
+  int64_t ess_res_samples = 0, ess_res_stride = 0;
+  // ---- multi-GPU (comm.cu) ------------------------------------------------------------------------------
+  // A context is a single GPU (rank 0 of 1), one rank of an NCCL communicator shared with other processes
+  // (asm_comm_init_rank), a member of a one-process group (asm_create_multi), or the parent of such a group
+  // (members non-empty; the parent owns no device state and forwards every call to its members' threads).
+  void* comm = nullptr;  // ncclComm_t
+  int rank = 0, world = 1;
+  asm_ctx* parent = nullptr;
+  std::vector<asm_ctx*> members;
+  struct WorkerPool* pool = nullptr;
   std::string err;
 };
 
@@ -142,8 +156,20 @@ int32_t rf_i8_sums(asm_ctx* ctx, asm_shard shard);
 int32_t rf_f4_sums(asm_ctx* ctx, asm_shard shard);  // block-scaled FP4 variant (layout with 240 live rows per block)
 int32_t rf_i8_block(asm_ctx* ctx, int32_t chainA, int64_t r0, int64_t r1, int32_t chainB, int64_t c0, int64_t c1,
                     uint16_t* out_host);
-// clade.cu
+// clade.cu (with a communicator: this rank counts its share of [from, to), an int32 all-reduce adds the shares;
+// out_host may be NULL)
 int32_t clade_counts(asm_ctx* ctx, int32_t chain, int64_t from, int64_t to, int32_t* out_host);
+// comm.cu -- collectives on the context's own stream (NCCL, loaded on first use); no-ops when world == 1
+int32_t comm_all_reduce_i64(asm_ctx* ctx, int64_t* d_buf, size_t count);
+int32_t comm_all_reduce_i32(asm_ctx* ctx, int32_t* d_buf, size_t count);
+int32_t comm_all_gather_u64_inplace(asm_ctx* ctx, uint64_t* d_buf, size_t count_per_rank);  // rank r's part at d_buf + r*count
+int32_t comm_broadcast_u64(asm_ctx* ctx, uint64_t* d_buf, size_t count, int root);
+int32_t comm_all_gather_f64(asm_ctx* ctx, const double* d_send, double* d_recv, size_t count_per_rank);
+void comm_destroy(asm_ctx* ctx);
+// run fn(member, index) on every member's thread and wait; returns the first failure (message copied to the parent)
+int32_t group_run(asm_ctx* parent, const std::function<int32_t(asm_ctx*, int)>& fn);
+int32_t group_run_one(asm_ctx* parent, int index, const std::function<int32_t(asm_ctx*)>& fn);
+void group_destroy(asm_ctx* parent);
 // moments.cu
 int32_t trace_moments(asm_ctx* ctx, int32_t end, double* sums_host, double* sumsq_host);
 // ess.cu

@@ -41,13 +41,18 @@ int32_t clade_counts(asm_ctx* ctx, int32_t chain, int64_t from, int64_t to, int3
   int32_t rc = asm_reserve(ctx, ctx->misc, bytes);
   if (rc != ASM_OK) return rc;
   ASM_CUDA(ctx, cudaMemsetAsync(ctx->misc.p, 0, bytes, ctx->stream));
-  if (to > from) {
+  // one rank of N counts its contiguous share of the trees (every rank holds every tree); the int32 all-reduce
+  // below adds the shares
+  const int64_t per = (to - from + ctx->world - 1) / ctx->world;
+  const int64_t lo = std::min<int64_t>(from + (int64_t)ctx->rank * per, to), hi = std::min<int64_t>(lo + per, to);
+  if (hi > lo) {
     LaunchScope ls(ctx, ASM_K_CLADE_COUNTS);
-    dim3 grid((unsigned)((words + 127) / 128), (unsigned)((to - from + kSlab - 1) / kSlab));
-    clade_counts_kernel<<<grid, 128, 0, ctx->stream>>>(ctx->trees[chain].d_bits, words, from, to, (int*)ctx->misc.p);
+    dim3 grid((unsigned)((words + 127) / 128), (unsigned)((hi - lo + kSlab - 1) / kSlab));
+    clade_counts_kernel<<<grid, 128, 0, ctx->stream>>>(ctx->trees[chain].d_bits, words, lo, hi, (int*)ctx->misc.p);
   }
   ASM_CUDA(ctx, cudaGetLastError());
-  ASM_CUDA(ctx, cudaMemcpyAsync(out_host, ctx->misc.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  if ((rc = comm_all_reduce_i32(ctx, (int32_t*)ctx->misc.p, (size_t)words * 64)) != ASM_OK) return rc;
+  if (out_host) ASM_CUDA(ctx, cudaMemcpyAsync(out_host, ctx->misc.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   ASM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return ASM_OK;
 }

@@ -448,6 +448,7 @@ int32_t psrf_compact(asm_ctx* ctx, asm_shard shard, int64_t* d_S_out) {
 int32_t psrf_finish(asm_ctx* ctx, const int64_t* d_S, int32_t n_rows, double* psrf_rows_host, double* psrf_mean_host) {
   const int C = ctx->n_chains;
   int32_t rc;
+  if (!psrf_mean_host) return asm_fail(ctx, ASM_E_INVALID, "psrf_finish: null output");
   const size_t rows_bytes = sizeof(double) * (size_t)C * (size_t)n_rows * (size_t)C;
   if ((rc = asm_reserve(ctx, ctx->psrf_mean, sizeof(double) * (size_t)C * C)) != ASM_OK) return rc;
   double* d_rows = nullptr;

@@ -2,24 +2,31 @@
 """bench.py -- throughput of the ASM convergence-diagnostic hot path on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload psrf|ess|cfg5] [--method i8|popc]
+                    [--workload psrf|ess|cfg5] [--method fp4|i8|popc]
 
-Prints ONE JSON line (rank 0).  A "step" is one full pass of the hot path over one batch of
-synthetic input:
+Prints ONE JSON line (rank 0).  A "step" is one full pass of the hot path over one batch of synthetic input:
 
-  psrf (default; BASELINE.json configs[1], "cfg2"): 4 chains x 10,000 trees x 100 taxa, all-pairs
-      RF + the (d+1)^2 within/between-chain sums + per-row PSRF + per-pair means, i.e. everything
-      TreePSRF.converged2sided (TreePSRF.java:141-158) asks of the device for every ordered chain
-      pair.  metric = tree-pairs/sec, counting the ordered (row tree, column tree) pairs whose
-      distance enters the sums (T*T per step; the GPU evaluates each unordered pair once).
-      With N > 1 ranks the tile pairs are dealt round-robin to the ranks, partial S tables are
-      combined with one NCCL all-reduce, and per-GPU work is held fixed (trees per chain scale with
-      sqrt(N)): "scaling": "weak".
-  ess  (configs[2], "cfg3"): 1,000 traces x 1,000,000 samples, TraceESS.ACT/calcESS per trace.
-      metric = trace-samples/sec.  Traces shard over ranks (weak: 1,000 traces per rank).
+  psrf (default; BASELINE.json configs[1], "cfg2"): 4 chains x 10,000 trees x 100 taxa, all-pairs RF + the (d+1)^2
+      within/between-chain sums + per-row PSRF + per-pair means, i.e. everything TreePSRF.converged2sided
+      (TreePSRF.java:141-158) asks of the device for every ordered chain pair.  metric = tree-pairs/sec, counting the
+      ordered (row tree, column tree) pairs whose distance enters the sums (T*T per step; the GPU evaluates each
+      unordered pair once).  At N > 1 GPUs per-GPU work is held fixed (trees per chain scale with sqrt(N)):
+      "scaling": "weak".
+  The same line carries, at every N, two sub-objects for the other shapes the north star names:
+      "ess"  (configs[2], "cfg3"): 1,000 traces x 1,000,000 samples per GPU, TraceESS.ACT/calcESS per trace (weak);
+      "cfg5" (configs[4]): 32 chains x 50,000 trees x 500 taxa, the SAME input at every N (strong scaling), with an
+             `S_checksum` of the full int64 table that must be equal across N.
 
-`value` is measured with the inputs resident in HBM; `e2e` goes through the C ABI with host
-buffers (pinned), host->device and device->host copies inside the timed region.
+How the N GPUs are driven (both inside libasmgpu.so, asm_b200/csrc/comm.cu; no data-path collective in Python):
+  * under torchrun (one process per GPU): every rank creates a one-GPU context and joins an in-library NCCL
+    communicator (asm_comm_init_rank; torch.distributed/gloo only carries the 128-byte id, barriers and the
+    max-over-ranks of the timings);
+  * plain `python bench.py --gpus N` (no torchrun): ONE process drives the N GPUs through asm_create_multi, the way
+    the reference's single caller thread would.
+The timer is the same at every N: CUDA events on the library's stream(s), max over GPUs.
+
+`value` is measured with the inputs resident in HBM; `e2e` goes through the C ABI with host buffers (pinned),
+host->device and device->host copies inside the timed region.
 """
 from __future__ import annotations
 
@@ -57,8 +64,38 @@ def measured_peaks():
         with open(p) as f:
             d = json.load(f)
         return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
-                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
-    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "MEASURED_PEAKS.json"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def live_peaks(device_index):
+    """Denominators measured in THIS run (tools/peaks.py): vendor-library GEMM throughput for the tensor-core kernels,
+    pipe issue rates for the CUDA-core kernels."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import peaks as P
+    out = {}
+    try:
+        out["gemm"] = P.gemm_peaks(f"cuda:{device_index}", sustain_s=1.0)
+    except Exception as e:  # noqa: BLE001
+        out["gemm"] = {"error": repr(e)[:300]}
+    out["pipes"] = P.pipe_peaks()
+    return out
+
+
+def tensor_peak(live, peaks, kind, sustained):
+    """(peak TFLOP/s, description) for the roofline of a tensor-core kernel: the vendor library's GEMM of the same
+    operand type measured in this run; MEASURED_PEAKS.json's bf16 times the datapath ratio only if that failed."""
+    which = "sustained" if sustained else "burst"
+    g = (live or {}).get("gemm", {})
+    keys = {"fp4": ("fp4_mx_e8m0_block32", "fp4_nv_e4m3_block16"), "i8": ("int8",)}[kind]
+    cands = [(g[k][which], k) for k in keys if isinstance(g.get(k), dict)]
+    if cands:
+        v, k = max(cands)
+        return v, f"cuBLASLt {k} GEMM 8192^3 through torch, {which}, measured in this run (tools/peaks.py)"
+    mult = 4.0 if kind == "fp4" else 2.0
+    base = peaks["bf16_tflops_sustained"] if sustained else peaks["bf16_tflops"]
+    return mult * base, (f"{mult:g} x bf16 {which} of {peaks['source']} (DERIVED: the {kind} GEMM could not be measured here: "
+                         f"{[g.get(k + '_error') for k in keys]})")
 
 
 # --------------------------------------------------------------------------------------------------
@@ -179,17 +216,18 @@ def cpu_baseline_psrf(cfg, n_trees, sample_rows=2048, ts=None):
     calcPSRF's two column loops (TreePSRF.java:274-286) for `sample_rows` row trees against every
     column tree of every chain, OpenMP over rows."""
     import oracle as O
+    cores = O.use_all_cores()
     if ts is None:
         ts = oracle_tree_set(cfg, n_trees)
     rows = min(sample_rows, n_trees)
     burnin = [0] * cfg["n_chains"]
     T = cfg["n_chains"] * n_trees
     t0 = time.perf_counter()
-    # rows [n_trees-rows, n_trees) of chain 0 against all columns of all chains
+    # rows [n_trees-rows, n_trees) of every chain against all columns of all chains
     S = ts.psrf_sums(burnin, n_trees - rows, n_trees, 1)
-    dt_all = time.perf_counter() - t0  # this evaluated C chains x rows rows
+    dt_all = time.perf_counter() - t0
     pairs = cfg["n_chains"] * rows * T
-    return {"value": pairs / dt_all, "unit": "tree-pairs/s", "cores": O.num_threads(), "kind": "port",
+    return {"value": pairs / dt_all, "unit": "tree-pairs/s", "cores": cores, "kind": "port",
             "sample": f"{cfg['n_chains']}x{rows} row trees x {T} column trees ({pairs:.3g} ordered pairs) in {dt_all:.2f}s; "
                       f"C restatement of TreePSRF.calcPSRF with set-intersection RF, OpenMP", "seconds": dt_all,
             "checksum": float(S.sum())}
@@ -197,7 +235,7 @@ def cpu_baseline_psrf(cfg, n_trees, sample_rows=2048, ts=None):
 
 def cpu_baseline_ess(n_samples, seed0, budget_traces=None):
     import oracle as O
-    cores = O.num_threads()
+    cores = O.use_all_cores()
     n_tr = budget_traces or max(cores, 4)
     x = gen_traces(n_tr, n_samples, seed0)
     t0 = time.perf_counter()
@@ -211,18 +249,79 @@ def cpu_baseline_ess(n_samples, seed0, budget_traces=None):
 
 
 # --------------------------------------------------------------------------------------------------
-def dist_setup(n_gpus):
-    """One process per GPU under torchrun; single process otherwise."""
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
+class Job:
+    """How this process takes part in the N-GPU job (see the module docstring)."""
+
+    def __init__(self, n_gpus: int):
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        self.dist = None
+        self.group_devices = None
+        if self.world > 1:
+            import torch
+            import torch.distributed as dist
+            torch.cuda.set_device(self.local)
+            dist.init_process_group("gloo")  # ids, barriers, maxima of timings; the data path is NCCL inside the library
+            self.dist = dist
+            self.n_gpus = self.world
+            self.launch = "torchrun: one process per GPU, in-library NCCL communicator (asm_comm_init_rank)"
+        elif n_gpus > 1:
+            self.group_devices = list(range(n_gpus))
+            self.n_gpus = n_gpus
+            self.launch = "one process drives all GPUs (asm_create_multi: ncclCommInitAll + one host thread per GPU)"
+        else:
+            self.n_gpus = 1
+            self.launch = "one process, one GPU"
+
+    def make_ctx(self, n_chains):
+        import asm_b200 as A
+        if self.group_devices is not None:
+            return A.GpuContext(n_chains, devices=self.group_devices)
+        ctx = A.GpuContext(n_chains, device=self.local)
+        if self.world > 1:
+            from asm_b200 import multi
+            multi.init_comm(ctx, self.dist)
+        return ctx
+
+    def barrier(self, ctx=None):
+        if ctx is not None:
+            ctx.sync()
+        if self.dist is not None:
+            self.dist.barrier()
+
+    def reduce(self, x: float, op: str = "max") -> float:
+        if self.dist is None:
+            return float(x)
         import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        return rank, world, local, dist
-    return 0, 1, 0, None
+        t = torch.tensor([float(x)], dtype=torch.float64)
+        self.dist.all_reduce(t, op={"max": self.dist.ReduceOp.MAX, "sum": self.dist.ReduceOp.SUM}[op])
+        return float(t.item())
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.destroy_process_group()
+
+
+def timed_steps(job, ctx, step, steps, flush=True):
+    """`steps` device-timed steps: CUDA events on the library's stream(s) around each step (max over the GPUs of a
+    group inside the library), barrier + sync before each, mean over steps, then the max over ranks."""
+    per = []
+    out = None
+    for _ in range(steps):
+        if flush:
+            ctx.flush_l2()  # outside the timed bracket
+        job.barrier(ctx)
+        ctx.timer_mark(0)
+        out = step()
+        ctx.timer_mark(1)
+        per.append(max(ctx.timer_elapsed_ms(0, 1), 0.0))
+    return job.reduce(float(np.mean(per)), "max"), out
+
+
+def s_checksum(S: np.ndarray) -> str:
+    """Sum of the int64 table modulo 2^64: equal across GPU counts iff (up to collisions) the tables are."""
+    return format(int(np.ascontiguousarray(S).view(np.uint64).sum(dtype=np.uint64)), "016x")
 
 
 def run_reference(args):
@@ -262,7 +361,8 @@ def run_reference(args):
                 "steps": steps, "warmup": warm, "ms_per_step": 1e3 * float(np.mean([r["seconds"] for r in vals])),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64/int64", "data": "synthetic",
                 "impl": "reference",
-                "config": {"workload": f"{cfg['n_chains']} chains x {n_trees} trees x {cfg['n_taxa']} taxa (bounded row sample per step)"},
+                "config": {"workload": f"{'cfg5' if args.workload == 'cfg5' else 'cfg2'}: {cfg['n_chains']} chains x {n_trees} trees x "
+                                       f"{cfg['n_taxa']} taxa (bounded row sample per step)"},
                 "cpu_baseline": {k: vals[-1][k] for k in ("kind", "cores", "sample")} | {"value": v, "unit": "tree-pairs/s"},
                 "e2e": {"value": v, "unit": "tree-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     with open("/proc/self/maps") as f:  # evidence: this arm maps the oracle and the input generators, not the product
@@ -271,179 +371,131 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------------
-def bench_psrf(args, rank, world, local, dist):
-    import asm_b200 as A
+def bench_psrf(job, args, which, method_name, steps, warmup, live, others=False):
+    """One PSRF workload (`which`: "cfg2" weak-scaled, or "cfg5" strong) -> the dict of its bench line."""
     from asm_b200 import _lib as L
-    import synthgen as G
     peaks = measured_peaks()
-    cfg = CFG5 if args.workload == "cfg5" else CFG2
-    n_trees = cfg["n_trees"] if args.workload == "cfg5" else int(round(cfg["n_trees"] * math.sqrt(world)))
-    method = {"i8": L.ASM_RF_I8, "fp4": L.ASM_RF_FP4, "popc": L.ASM_RF_POPC}[args.method]
+    world = job.n_gpus
+    cfg = CFG5 if which == "cfg5" else CFG2
+    n_trees = cfg["n_trees"] if which == "cfg5" else int(round(cfg["n_trees"] * math.sqrt(world)))
+    method = {"i8": L.ASM_RF_I8, "fp4": L.ASM_RF_FP4, "popc": L.ASM_RF_POPC}[method_name]
     C = cfg["n_chains"]
     T = C * n_trees
     enc, bits, _ = gen_psrf_input(cfg, n_trees)
-    words = enc.words
+    D = enc.num_clades
     burnin = [0] * C
-    ctx = A.GpuContext(C, device=local)
+    ctx = job.make_ctx(C)
     pinned = [pinned_like(b) for b in bits]
-    h2d_bytes = sum(b.nbytes for b in bits)
+    del bits
+    h2d_bytes = sum(p[1].nbytes for p in pinned)
 
-    torch = None
-    d_S = None
-    if world > 1:
-        import torch
-        d_S = torch.zeros((C, n_trees, C), dtype=torch.int64, device=f"cuda:{local}")
-        torch.cuda.synchronize()
-        lib_stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=f"cuda:{local}")
+    def upload():  # at N > 1 every row crosses PCIe once per job: GPU r uploads the r-th slice, one all-gather replicates it
+        for c in range(C):
+            ctx.trees_set(c, pinned[c][1])
 
-    def upload():
-        if world == 1:
-            for c in range(C):
-                ctx.trees_set(c, pinned[c][1])
-        else:  # every row crosses PCIe once per job: rank r uploads the r-th slice, one all-gather replicates it
-            from asm_b200 import multi
-            multi.trees_set_sharded(ctx, dist, [p[0] for p in pinned], f"cuda:{local}")
-
-    def step_resident():
-        if world == 1:
-            return ctx.psrf_eval(burnin, 0, n_trees, 1, method)
-        # partial sums -> all-reduce -> finish, ordered on the library's stream with no host round trip in between
-        ctx.psrf_sums_device_async(burnin, 0, n_trees, 1, method, (rank, world), d_S.data_ptr())
-        with torch.cuda.stream(lib_stream):
-            dist.all_reduce(d_S, op=dist.ReduceOp.SUM)  # exact: int64 partial sums
-        return ctx.psrf_finish_device(d_S.data_ptr(), n_trees)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-        ctx.sync()
+    def step():  # sums on every GPU's share of the tile pairs, ONE int64 all-reduce inside the library, finish
+        return ctx.psrf_eval(burnin, 0, n_trees, 1, method)
 
     upload()
-    for _ in range(args.warmup):
-        mean = step_resident()
+    for _ in range(warmup):
+        mean = step()
         ctx.flush_l2()
     # ---- timed: inputs resident in HBM --------------------------------------------------------------
     ctx.profile_enable(False)
-    sampler = ClockSampler(local, period_s=0.001)
-    per_step = []
-    barrier()
+    sampler = ClockSampler(job.local, period_s=0.001 if which == "cfg2" else 0.02)
+    job.barrier(ctx)
     launches0 = ctx.launch_count()
     sampler.start()
-    for _ in range(args.steps):
-        ctx.flush_l2()  # L2 flushed between timed steps, outside the timed bracket
-        barrier()
-        t0 = time.perf_counter()
-        ctx.timer_mark(0)
-        mean = step_resident()
-        ctx.timer_mark(1)
-        dev_ms = ctx.timer_elapsed_ms(0, 1)
-        wall_ms = (time.perf_counter() - t0) * 1e3
-        per_step.append(max(dev_ms, 0.0) if world == 1 else wall_ms)
+    ms, mean = timed_steps(job, ctx, step, steps)
     clocks = sampler.stop()
-    launches = (ctx.launch_count() - launches0 - args.steps) // max(args.steps, 1)  # minus the flush kernel
-    ms = float(np.mean(per_step))
-    if world > 1:
-        t = torch.tensor([ms], device=f"cuda:{local}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    n_local = max(1, len(ctx.devices))
+    launches = job.reduce((ctx.launch_count() - launches0 - steps * n_local) / max(steps, 1), "sum")  # minus the flush kernels
     value = T * T / (ms * 1e-3)
 
-    # ---- kernel-only time for the roofline (CUDA events around the dominant kernel, same stream) ------
+    # ---- kernel-only time for the roofline (CUDA events around every launch, same stream) --------------
     ctx.profile_enable(True)
     ctx.profile_reset()
-    for _ in range(1 if args.workload == "cfg5" else max(3, min(args.steps, 10))):
+    n_prof = 1 if which == "cfg5" else max(3, min(steps, 10))
+    for _ in range(n_prof):
         ctx.flush_l2()
-        step_resident()
+        step()
     fam = L.K_RF_POPC if method == L.ASM_RF_POPC else L.K_RF_I8  # both tensor-core kernels report under K_RF_I8
-    k_ms, k_n = ctx.profile_get(fam)
-    fam_ms = {name: ctx.profile_get(f)[0] / max(k_n, 1) for name, f in
+    # profile_get: time of the slowest GPU of a group; one distance-kernel launch per GPU and step
+    fam_ms = {name: job.reduce(ctx.profile_get(f)[0] / n_prof, "max") for name, f in
               [("gather", L.K_GATHER), ("rf", fam), ("finish", L.K_PSRF_FINISH)]}
     ctx.profile_enable(False)
-    k_ms /= max(k_n, 1)
+    k_ms = fam_ms["rf"]
     lay = ctx.last_layout()
     Dp, Tp = lay["padded_bits"], lay["padded_rows"]
-    D = enc.num_clades
-    if method == L.ASM_RF_I8:
-        # algorithmic int8 flops: D * T * (T-1) over unordered pairs, per launch / shards
-        alg = D * T * (T - 1) / world
+    sustained = which == "cfg5"  # a seconds-long kernel runs at the sustained clock, a 0.6 ms one at the burst clock
+    if method in (L.ASM_RF_I8, L.ASM_RF_FP4):
+        kind = "fp4" if method == L.ASM_RF_FP4 else "i8"
+        alg = D * T * (T - 1) / world  # per GPU: its share of the unordered pairs, 2 flop per MAC
         achieved = alg / (k_ms * 1e-3) / 1e12
-        peak = 2.0 * peaks["bf16_tflops"]  # int8 dense = 2 x bf16 dense on B200; bf16 is the measured figure
+        peak, src = tensor_peak(live, peaks, kind, sustained)
+        nominal = 9000.0 if kind == "fp4" else 4500.0
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": measured_traffic("rf_i8x2_kernel@cfg2") if (world == 1 and args.workload == "psrf") else None,
-                "kernel": "rf_i8x2_kernel", "kernel_ms": k_ms,
-                "peak_source": f"2 x bf16_tflops ({peaks['source']}); int8 dense is 2x bf16 dense on B200. cuBLAS bf16 reaches "
-                               f"~72% of nominal on this pool, this kernel ~86-93% of nominal int8, hence frac > 1",
-                "frac_of_nominal_int8_4500": achieved / 4500.0, "frac_of_cublaslt_int8_3626": achieved / 3626.0,
-                "algorithmic": "D*T*(T-1) int8 flop per launch (unordered pairs, 2 flop per MAC)"}
-    elif method == L.ASM_RF_FP4:
-        alg = D * T * (T - 1) / world
-        achieved = alg / (k_ms * 1e-3) / 1e12
-        peak = 4.0 * peaks["bf16_tflops"]  # fp4 dense = 4 x bf16 dense on B200; bf16 is the measured figure
-        roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": measured_traffic("rf_f4x2_kernel@cfg2") if (world == 1 and args.workload == "psrf") else None,
-                "kernel": "rf_f4x2_kernel", "kernel_ms": k_ms,
-                "peak_source": f"4 x bf16_tflops ({peaks['source']}); block-scaled fp4 dense is 4x bf16 dense on B200 (9 PFLOP/s nominal)",
-                "frac_of_nominal_fp4_9000": achieved / 9000.0,
-                "algorithmic": "D*T*(T-1) flop per launch (unordered pairs, 2 flop per MAC); e2m1 indicators, unit UE8M0 "
-                               "scales, f32 accumulators: exact"}
+                "traffic": measured_traffic(("rf_f4x2_kernel" if kind == "fp4" else "rf_i8x2_kernel") + "@cfg2")
+                if (world == 1 and which == "cfg2") else None,
+                "kernel": "rf_f4x2_kernel" if kind == "fp4" else "rf_i8x2_kernel", "kernel_ms": k_ms, "peak_source": src,
+                "frac_of_nominal": achieved / nominal, "nominal_tflops": nominal,
+                "executed_over_algorithmic": (Tp * (Tp + 256) / 2.0 * 2 * Dp) / (D * T * (T - 1.0)),
+                "algorithmic": "D*T*(T-1)/N flop per launch and GPU (unordered pairs, 2 flop per MAC)" +
+                               ("; e2m1 indicators, unit UE8M0 scales, f32 accumulators: exact" if kind == "fp4" else "")}
     else:
-        # popcount variant: integer-pipe bound; HBM algorithmic bytes = operand read once + S written
-        alg_bytes = (Tp * Dp / 8 + 8 * Tp * C) / world
-        achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+        pipes = (live or {}).get("pipes", {})
         words_pairs = (D / 64.0) * T * (T - 1) / 2 / world
-        roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"],
-                "traffic": measured_traffic("rf_popc_psrf_kernel@cfg2") if (world == 1 and args.workload == "psrf") else None,
+        achieved = words_pairs * 2 / (k_ms * 1e-3)  # POPC lane-ops/s: one 64-bit popcount = 2 POPC
+        peak = pipes.get("popc", {}).get("ops_per_s")
+        roof = {"bound": "int", "achieved": achieved / 1e12, "peak": (peak or 4.45e12) / 1e12, "unit": "Tpopc32/s",
+                "frac": achieved / (peak or 4.45e12), "traffic": measured_traffic("rf_popc_psrf_kernel@cfg2") if world == 1 else None,
                 "kernel": "rf_popc_psrf_kernel", "kernel_ms": k_ms,
-                "peak_source": f"hbm_gbs ({peaks['source']})",
-                "algorithmic": "T*D/8 operand bytes + 8*T*C S bytes per launch",
-                "note": "integer-pipe (LOP3+POPC) bound, not HBM bound: see int_pipe",
-                "int_pipe": {"xor_popc64_per_s": words_pairs / (k_ms * 1e-3), "unit": "64-bit XOR-popcounts/s"}}
+                "peak_source": "POPC issue rate, tools/microbench measured in this run" if peak else "POPC issue rate of profiles/r01_microbench_pipes.json",
+                "algorithmic": "(D/64)*T*(T-1)/2 64-bit XOR-popcounts (2 POPC each) per launch; integer-pipe bound, not HBM",
+                "hbm_gbs": (Tp * Dp / 8 + 8 * Tp * C) / world / (k_ms * 1e-3) / 1e9}
 
     # ---- e2e: host buffers through the C ABI, H2D + D2H inside the timed region ------------------------
     e2e_steps = []
-    e2e_warm = 0 if args.workload == "cfg5" else args.warmup
-    for i in range(e2e_warm + (1 if args.workload == "cfg5" else args.steps)):
+    e2e_warm = 0 if which == "cfg5" else warmup
+    for i in range(e2e_warm + (1 if which == "cfg5" else steps)):
         ctx.flush_l2()
-        barrier()
+        job.barrier(ctx)
         t0 = time.perf_counter()
         upload()
-        mean_e = step_resident()
+        mean_e = step()
         dt = (time.perf_counter() - t0) * 1e3
         if i >= e2e_warm:
             e2e_steps.append(dt)
-    e_ms = float(np.mean(e2e_steps))
-    if world > 1:
-        t = torch.tensor([e_ms], device=f"cuda:{local}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e_ms = float(t.item())
+    e_ms = job.reduce(float(np.mean(e2e_steps)), "max")
     e2e = {"value": T * T / (e_ms * 1e-3), "unit": "tree-pairs/s", "h2d_bytes_per_step": int(h2d_bytes),
            "d2h_bytes_per_step": int(C * C * 8), "ms_per_step": e_ms,
+           "timer": "host clock around asm_trees_set x C + asm_psrf_eval, max over ranks",
            "bit_identical_to_resident": bool(np.array_equal(np.asarray(mean_e), np.asarray(mean), equal_nan=True))}
-
+    S = ctx.psrf_sums(burnin, 0, n_trees, 1, method)  # the complete int64 table (all-reduced at N > 1)
+    checksum = s_checksum(S)
+    del S
     line = {"metric": "tree-pairs/sec (RF+PSRF)", "value": value, "unit": "tree-pairs/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "strong" if args.workload == "cfg5" else "weak",
+            "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong" if which == "cfg5" else "weak",
             "vs_baseline": None, "dtype": {L.ASM_RF_I8: "int8->s32 (tcgen05), int64 sums, f64 psrf", L.ASM_RF_FP4: "e2m1->f32 (tcgen05 mxf4, exact on 0/1), int64 sums, f64 psrf", L.ASM_RF_POPC: "u64 popc, int64 sums, f64 psrf"}[method],
             "data": "synthetic",
-            "config": {"workload": f"{'cfg5' if args.workload == 'cfg5' else 'cfg2'}: {C} chains x {n_trees} trees x {cfg['n_taxa']} taxa, "
-                                   f"burnin=0 smoothing=1 delta=1", "method": args.method, "clades_D": int(D),
-                       "padded_bits": int(Dp), "padded_rows": int(Tp), "trees_T": int(T),
+            "config": {"workload": f"{which}: {C} chains x {n_trees} trees x {cfg['n_taxa']} taxa, burnin=0 smoothing=1 delta=1",
+                       "method": method_name, "clades_D": int(D), "padded_bits": int(Dp), "padded_rows": int(Tp), "trees_T": int(T),
+                       "launch": job.launch,
                        "l2": "L2 flushed (256 MiB write) between timed steps, outside the timed bracket",
-                       "timing": "CUDA events on the library stream per step" if world == 1 else "host bracket after device sync, max over ranks",
+                       "timing": "CUDA events on the library stream(s) per step, max over GPUs (the same timer at every N)",
                        "generator": {k: cfg[k] for k in ("beta", "moves", "start_seed", "seed0")},
-                       "weak_scaling": "trees per chain = 10000*sqrt(N); trees beyond the first 10000 are a seeded resample "
-                                       "of them, so D (work per pair) is the same at every N",
-                       "e2e_upload": "asm_trees_set from pinned host rows" if world == 1 else
-                                     "rank r uploads the r-th slice of every chain, one NCCL all-gather replicates it "
-                                     "(h2d_bytes_per_step is the whole job's)",
+                       "weak_scaling": ("trees per chain = 10000*sqrt(N); trees beyond the first 10000 are a seeded resample of them, so D "
+                                        "(work per pair) is the same at every N") if which == "cfg2" else None,
+                       "e2e_upload": "asm_trees_set from pinned host rows" + ("" if world == 1 else
+                                     ": GPU r uploads the r-th slice of every chain, one in-library ncclAllGather replicates it "
+                                     "(h2d_bytes_per_step is the whole job's)"),
                        "psrf_mean_01": float(mean[0, 1]), "psrf_mean_10": float(mean[1, 0])},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
-            "step_breakdown_ms": fam_ms}
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(round(launches)), "roofline": roof,
+            "step_breakdown_ms": fam_ms, "S_checksum": checksum}
     # ---- the other ways the north star names (popcount-XOR, int8 tcgen05), same inputs, same step ---------------------
-    if world == 1 and args.workload == "psrf" and not args.no_other_methods:
-        others = {}
+    if others:
+        res = {}
         for name, m in (("i8", L.ASM_RF_I8), ("fp4", L.ASM_RF_FP4), ("popc", L.ASM_RF_POPC)):
             if m == method:
                 continue
@@ -466,116 +518,124 @@ def bench_psrf(args, rank, world, local, dist):
             ctx.profile_enable(False)
             km /= max(kn, 1)
             ms_m = float(np.mean(ts))
-            others[name] = {"ms_per_step": ms_m, "value": T * T / (ms_m * 1e-3), "unit": "tree-pairs/s", "kernel_ms": km,
-                            "algorithmic_tflops": D * T * (T - 1) / (km * 1e-3) / 1e12 if m != L.ASM_RF_POPC else None,
-                            "xor_popc64_per_s": (D / 64.0) * T * (T - 1) / 2 / (km * 1e-3) if m == L.ASM_RF_POPC else None,
-                            "bit_identical_means": bool(np.array_equal(np.asarray(mean_m), np.asarray(mean), equal_nan=True))}
-        line["other_methods"] = others
-    return line, ctx
+            entry = {"ms_per_step": ms_m, "value": T * T / (ms_m * 1e-3), "unit": "tree-pairs/s", "kernel_ms": km,
+                     "bit_identical_means": bool(np.array_equal(np.asarray(mean_m), np.asarray(mean), equal_nan=True))}
+            if m == L.ASM_RF_POPC:
+                pk = (live or {}).get("pipes", {}).get("popc", {}).get("ops_per_s")
+                entry["xor_popc64_per_s"] = (D / 64.0) * T * (T - 1) / 2 / (km * 1e-3)
+                entry["frac_of_popc_issue_rate"] = 2 * entry["xor_popc64_per_s"] / pk if pk else None
+            else:
+                pk, src = tensor_peak(live, peaks, name, False)
+                entry["algorithmic_tflops"] = D * T * (T - 1) / (km * 1e-3) / 1e12
+                entry["frac"] = entry["algorithmic_tflops"] / pk
+                entry["peak"], entry["peak_source"] = pk, src
+            res[name] = entry
+        line["other_methods"] = res
+    ctx.close()
+    return line
 
 
-def bench_ess(args, rank, world, local, dist, n_traces=None):
-    import asm_b200 as A
+def bench_ess(job, args, steps, warmup, live):
     from asm_b200 import _lib as L
-    import synthgen as G
     import torch
-    peaks = measured_peaks()
-    n_tr = n_traces or CFG3["n_traces"]
+    world = job.n_gpus
+    n_tr = args.ess_traces or CFG3["n_traces"]  # per GPU
     n = CFG3["n_samples"]
-    ctx = A.GpuContext(1, device=local)
-    host_t = torch.empty((n_tr, n), dtype=torch.float64)
+    # traces this PROCESS holds: its own GPU's (torchrun) or every GPU's (one process drives them all)
+    n_here = n_tr * (len(job.group_devices) if job.group_devices else 1)
+    first = job.rank * n_tr
+    ctx = job.make_ctx(1)
+    host_t = torch.empty((n_here, n), dtype=torch.float64)
     try:
         host_t = host_t.pin_memory()
     except Exception:
         pass
     host = host_t.numpy()
-    gen_traces(n_tr, n, CFG3["seed0"], first=rank * n_tr, out=host)
-    dev = torch.empty((n_tr, n), dtype=torch.float64, device=f"cuda:{local}")
-    dev.copy_(host_t)
-    torch.cuda.synchronize()
+    gen_traces(n_here, n, CFG3["seed0"], first=first, out=host)
+    ctx.ess_traces_put(host)  # resident: a group deals the traces to its GPUs in contiguous blocks
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        ctx.sync()
+    def step():  # per-GPU evaluation + the ESS vector of the whole job on every rank (in-library all-gather)
+        act, ess = ctx.ess_traces_eval()
+        return act, (ctx.all_gather_f64(ess) if job.dist is not None else ess)
 
-    for _ in range(args.warmup):
-        act, ess = ctx.ess_batch_device(dev.data_ptr(), n_tr, n, n)
-    sampler = ClockSampler(local, period_s=0.05)
-    per = []
-    barrier()
+    for _ in range(warmup):
+        step()
+    sampler = ClockSampler(job.local, period_s=0.05)
+    job.barrier(ctx)
     l0 = ctx.launch_count()
     sampler.start()
-    for _ in range(args.steps):  # 8 GB of traces per step: inputs larger than L2, no flush needed
-        barrier()
-        ctx.timer_mark(0)
-        act, ess = ctx.ess_batch_device(dev.data_ptr(), n_tr, n, n)
-        ctx.timer_mark(1)
-        per.append(ctx.timer_elapsed_ms(0, 1))
+    ms, (act, ess_all) = timed_steps(job, ctx, step, steps, flush=False)  # 8 GB of traces per GPU and step: larger than L2
     clocks = sampler.stop()
-    launches = (ctx.launch_count() - l0) // max(args.steps, 1)
-    ms = float(np.mean(per))
-    if world > 1:
-        t = torch.tensor([ms], device=f"cuda:{local}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-        g = [torch.zeros(n_tr, dtype=torch.float64, device=f"cuda:{local}") for _ in range(world)]
-        dist.all_gather(g, torch.from_numpy(ess).to(f"cuda:{local}"))  # ESS vector gather; min on host (Java NaN rules)
+    launches = job.reduce((ctx.launch_count() - l0) / max(steps, 1), "sum")
     value = world * n_tr * n / (ms * 1e-3)
 
     def profiled():
         ctx.profile_enable(True)
         ctx.profile_reset()
-        ctx.ess_batch_device(dev.data_ptr(), n_tr, n, n)
+        ctx.ess_traces_eval()
         k, kn = ctx.profile_get(L.K_ESS_LAG)
         f, _ = ctx.profile_get(L.K_ESS_FINISH)
         ctx.profile_enable(False)
-        return k, f, ctx.ess_last_lag_count()
+        return job.reduce(k, "max"), job.reduce(f, "max"), job.reduce(ctx.ess_last_lag_count(), "sum")
 
     k_ms, f_ms, slots = profiled()          # as shipped: staged lag evaluation
     ctx.ess_set_adaptive(False)
+    job.barrier(ctx)
     ctx.timer_mark(2)
-    act_full, ess_full = ctx.ess_batch_device(dev.data_ptr(), n_tr, n, n)
+    act_full, ess_full = ctx.ess_traces_eval()
     ctx.timer_mark(3)
-    full_step_ms = ctx.timer_elapsed_ms(2, 3)
+    full_step_ms = job.reduce(ctx.timer_elapsed_ms(2, 3), "max")
     kf_ms, ff_ms, slots_full = profiled()   # every lag of every trace (what the reference evaluates)
     ctx.ess_set_adaptive(True)
     lmax = min(n, 2000)
-    flops_full = 2.0 * (lmax * n - lmax * (lmax - 1) / 2) * n_tr
+    flops_full = 2.0 * (lmax * n - lmax * (lmax - 1) / 2) * n_tr * world
     flops = 2.0 * slots * n  # (trace, lag) chains evaluated x n mul+add pairs (upper bound: ignores the i < lag head)
-    roof = {"bound": "hbm", "achieved": 8.0 * n_tr * n / (k_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-            "frac": 8.0 * n_tr * n / (k_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+    pipes = (live or {}).get("pipes", {})
+    fp64_peak = pipes.get("fp64_issue_tflops")
+    peak_src = "DMUL+DADD issue rate, tools/microbench.cu measured in this run" if fp64_peak else \
+        "DMUL+DADD issue rate of profiles/r01_microbench_pipes.json (tools/microbench not runnable here)"
+    fp64_peak = fp64_peak or 18.38
+    ach = flops / world / (k_ms * 1e-3) / 1e12
+    ach_full = flops_full / world / (kf_ms * 1e-3) / 1e12
+    mine = ess_all[first:first + n_here] if job.dist is not None else ess_all
+    roof = {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
             "traffic": measured_traffic("ess_lag_kernel@cfg3_staged_5_launches") if world == 1 else None,
-            "traffic_note": "sum over the five staged launches of one step (each stage re-reads its open traces)",
-            "kernel": "ess_lag_kernel",
-            "kernel_ms": k_ms, "finish_ms": f_ms,
-            "note": "FP64-pipe bound (~500 flop/byte), not HBM bound: see fp64",
-            "fp64": {"achieved_tflops": flops / (k_ms * 1e-3) / 1e12, "unit": "TFLOP/s (separate DMUL+DADD, no FMA)",
-                     "lag_chains_evaluated": int(slots), "lag_chains_all": int(n_tr) * 2048,
-                     "algorithmic": "2 * n flop per evaluated (trace, lag) chain; staged evaluation stops a trace once the "
-                                    "integral loop of TraceESS.java:161-172 has stopped"},
-            "all_lags": {"step_ms": full_step_ms, "kernel_ms": kf_ms, "achieved_tflops": flops_full / (kf_ms * 1e-3) / 1e12,
+            "traffic_note": "sum over the staged launches of one step (each stage re-reads its open traces); the HBM floor of 8 B/sample is not binding",
+            "kernel": "ess_lag_kernel", "kernel_ms": k_ms, "finish_ms": f_ms, "peak_source": peak_src,
+            "algorithmic": "2*n flop per evaluated (trace, lag) chain, i.e. EXECUTED work: separate DMUL and DADD (bit-exact, no FMA), so "
+                           "the ceiling is the FP64 issue rate (half the DFMA rating); the staged evaluation stops a trace once the "
+                           "integral loop of TraceESS.java:161-172 has stopped",
+            "lag_chains_evaluated": int(slots), "lag_chains_all": int(n_tr) * 2048 * world,
+            "hbm_gbs": 8.0 * n_tr * n / (k_ms * 1e-3) / 1e9,
+            "all_lags": {"step_ms": full_step_ms, "kernel_ms": kf_ms, "achieved": ach_full, "frac": ach_full / fp64_peak,
                          "value": world * n_tr * n / (full_step_ms * 1e-3),
-                         "bit_identical_to_staged": bool(np.array_equal(ess, ess_full, equal_nan=True)),
-                         "algorithmic": "2*(L*n - L(L-1)/2) flop per trace, L = 2000"}}
+                         "bit_identical_to_staged": bool(np.array_equal(ess_full, mine, equal_nan=True)),
+                         "algorithmic": "2*(L*n - L(L-1)/2) flop per trace, L = 2000: every lag, what the reference evaluates"}}
     e2e_ms = []
     for i in range(2):
-        barrier()
+        job.barrier(ctx)
         t0 = time.perf_counter()
         act2, ess2 = ctx.ess_batch(host)
+        if job.dist is not None:
+            ess2 = ctx.all_gather_f64(ess2)
         e2e_ms.append((time.perf_counter() - t0) * 1e3)
-    e_ms = float(min(e2e_ms))
+    e_ms = job.reduce(float(min(e2e_ms)), "max")
+    from asm_b200.multi import java_min
     line = {"metric": "trace-samples/sec (ESS)", "value": value, "unit": "trace-samples/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"cfg3: {n_tr} traces x {n} samples per GPU, AR(1) phi in {PHIS}, mu in {MUS}, max_lag 2000",
-                       "l2": "inputs (8 GB per step) larger than L2"},
-            "clocks": clocks, "gpu_launches": int(launches), "roofline": roof,
-            "e2e": {"value": world * n_tr * n / (e_ms * 1e-3), "unit": "trace-samples/s", "h2d_bytes_per_step": int(host.nbytes),
-                    "d2h_bytes_per_step": int(16 * n_tr), "ms_per_step": e_ms},
-            "min_ess": float(np.nanmin(ess)), "bit_identical_e2e_vs_resident": bool(np.array_equal(ess, ess2, equal_nan=True))}
-    return line, ctx
+                       "l2": "inputs (8 GB per GPU and step) larger than L2", "launch": job.launch,
+                       "timing": "CUDA events on the library stream(s) per step, max over GPUs"},
+            "clocks": clocks, "gpu_launches": int(round(launches)), "roofline": roof,
+            "e2e": {"value": world * n_tr * n / (e_ms * 1e-3), "unit": "trace-samples/s",
+                    "h2d_bytes_per_step": int(host.nbytes) * (job.world if job.dist is not None else 1),
+                    "d2h_bytes_per_step": int(16 * n_tr * world), "ms_per_step": e_ms},
+            "min_ess": java_min(ess_all),
+            "ess_checksum": format(int(np.ascontiguousarray(ess_all).view(np.uint64).sum(dtype=np.uint64)), "016x"),
+            "bit_identical_e2e_vs_resident": bool(np.array_equal(ess_all, ess2, equal_nan=True))}
+    ctx.close()
+    return line
 
 
 def main():
@@ -589,9 +649,12 @@ def main():
     ap.add_argument("--cpu-rows", type=int, default=2048, help="row trees per chain in the CPU-baseline sample")
     ap.add_argument("--ref-rows", type=int, default=512,
                     help="row trees per chain per step of --impl reference (about 2 s of CPU work per step at cfg2)")
+    ap.add_argument("--ess-traces", type=int, default=0, help="traces per GPU of the ESS block (default 1000 = cfg3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-ess", action="store_true", help="skip the secondary ESS block of the default run")
+    ap.add_argument("--no-ess", action="store_true", help="skip the ESS (cfg3) block")
+    ap.add_argument("--no-cfg5", action="store_true", help="skip the cfg5 strong-scaling block")
     ap.add_argument("--no-other-methods", action="store_true", help="skip the int8 / popcount comparison runs")
+    ap.add_argument("--no-live-peaks", action="store_true", help="skip the in-run GEMM / pipe peak measurements")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -609,28 +672,38 @@ def main():
     if args.impl == "reference":
         run_reference(args)
         return
-    rank, world, local, dist = dist_setup(args.gpus)
+    job = Job(args.gpus)
+    t_start = time.time()
+    # roofline denominators measured in this lease, on this process's GPU, before the workload (every rank measures its
+    # own GPU so that all GPUs are in the same thermal state; rank 0's numbers are reported)
+    live = None if args.no_live_peaks else live_peaks(job.local)
+    job.barrier()
     if args.workload == "ess":
-        line, _ = bench_ess(args, rank, world, local, dist)
-        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line = bench_ess(job, args, args.steps, args.warmup, live)
+        if job.rank == 0 and job.n_gpus == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_ess(CFG3["n_samples"], CFG3["seed0"])
+    elif args.workload == "cfg5":
+        line = bench_psrf(job, args, "cfg5", args.method, min(args.steps, 2), 1, live)
     else:
-        line, ctx = bench_psrf(args, rank, world, local, dist)
-        if rank == 0 and world == 1:
-            if not args.no_cpu_baseline and args.workload != "cfg5":  # cfg5's CPU sample: tools/cfg5_check.py
-                line["cpu_baseline"] = cpu_baseline_psrf(CFG2, CFG2["n_trees"], sample_rows=args.cpu_rows)
-            if not args.no_ess and args.workload == "psrf":
-                ctx.close()
-                ess_args = argparse.Namespace(**vars(args))
-                ess_args.steps, ess_args.warmup = min(args.steps, 5), 3
-                ess_line, _ = bench_ess(ess_args, rank, world, local, dist)
-                if not args.no_cpu_baseline:
-                    ess_line["cpu_baseline"] = cpu_baseline_ess(CFG3["n_samples"], CFG3["seed0"])
-                line["ess"] = ess_line
-    if rank == 0:
+        line = bench_psrf(job, args, "cfg2", args.method, args.steps, args.warmup, live,
+                          others=job.n_gpus == 1 and not args.no_other_methods)
+        if job.rank == 0 and job.n_gpus == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_psrf(CFG2, CFG2["n_trees"], sample_rows=args.cpu_rows)
+        if not args.no_ess:
+            ess_line = bench_ess(job, args, min(args.steps, 5), 3, live)
+            if job.rank == 0 and job.n_gpus == 1 and not args.no_cpu_baseline:
+                ess_line["cpu_baseline"] = cpu_baseline_ess(CFG3["n_samples"], CFG3["seed0"])
+            line["ess"] = ess_line
+        if not args.no_cfg5:
+            # strong scaling of the north star's largest shape: the same 1.6M trees at every N; a step is seconds long,
+            # so one warm-up and at most two timed steps
+            line["cfg5"] = bench_psrf(job, args, "cfg5", args.method, min(args.steps, 2), 1, live)
+    if live is not None:
+        line["live_peaks"] = live
+    line["wall_s"] = round(time.time() - t_start, 1)
+    if job.rank == 0:
         _emit(line)
-    if dist is not None:
-        dist.destroy_process_group()
+    job.close()
 
 
 if __name__ == "__main__":

@@ -12,9 +12,9 @@
  *   - plain C: pointers and sizes only; every function returns int32_t, 0 = ASM_OK, < 0 = ASM_E_*;
  *     nothing throws or aborts.  asm_last_error(ctx) gives the message of the last failure.
  *   - the caller owns every host buffer and may free it on return (the library copies).
- *   - one asm_ctx = one GPU.  A context may be used from any thread, one call at a time
- *     (the reference calls criteria from the single LogWatcherThread, AutoStopMCMC.java:214,
- *     397-409); the library selects its device on every call.
+ *   - one asm_ctx = one GPU (asm_create) or several GPUs of one box (asm_create_multi).  A context may be
+ *     used from any thread, one call at a time (the reference calls criteria from the single
+ *     LogWatcherThread, AutoStopMCMC.java:214, 397-409); the library selects its device on every call.
  *   - there is no CPU fallback: without a usable sm_100 device asm_create fails with
  *     ASM_E_NO_DEVICE and every compute entry point fails with it as well.
  *
@@ -61,6 +61,40 @@ int32_t asm_device_count(void);
  * TraceInfo.java:31-41; criteria setup(nChains, traceInfo), MCMCConvergenceCriterion.java:20). */
 int32_t asm_create(asm_ctx** out, int32_t device, int32_t n_chains);
 int32_t asm_destroy(asm_ctx* ctx);
+
+/* ---- more than one GPU ---------------------------------------------------------------------------------------
+ * The reference calls its criteria from ONE thread of ONE process (LogWatcherThread, AutoStopMCMC.java:214,
+ * 397-409), so the multi-GPU form is one context over several devices: asm_create_multi builds one per-device
+ * context per entry of `devices` inside the calling process, joins them in an NCCL communicator
+ * (ncclCommInitAll) and gives each a host thread.  EVERY entry point below takes such a context with unchanged
+ * signature and meaning:
+ *   - trees: asm_trees_set sends each row over PCIe once (device r uploads the r-th slice of the chain) and one
+ *     in-place ncclAllGather over NVLink replicates it; asm_trees_append / asm_traces_append go to every device;
+ *   - PSRF: tile pairs t of the symmetric pair matrix go to device t % N, the int64 partial tables are combined with
+ *     ONE ncclAllReduce on the library's streams (exact in any order: sums of squares of small integers), the
+ *     finish runs on the first device; results are bit-identical to one GPU;
+ *   - ESS: traces (asm_ess_batch, asm_ess_traces_put) and selected columns (asm_ess_eval) are dealt to the devices
+ *     in contiguous blocks; every device writes its slice of the caller's output arrays;
+ *   - clade counts: every device counts its slice of [from, to), one ncclAllReduce(int32) adds the slices;
+ *   - device pointers handed in (asm_trees_set_device, asm_psrf_sums_device, asm_ess_batch_device, ...) are on the
+ *     FIRST device of the list.
+ * NCCL (libnccl.so.2) is loaded on first use; one GPU needs none.  n_devices == 1 is allowed. */
+int32_t asm_create_multi(asm_ctx** out, const int32_t* devices, int32_t n_devices, int32_t n_chains);
+/* The same collectives for a launcher that runs one PROCESS per GPU (torchrun): rank 0 draws an id, the launcher's
+ * own channel carries its ASM_COMM_ID_BYTES bytes to the other ranks, every rank joins with its plain asm_create
+ * context.  From then on asm_trees_set, asm_psrf_sums*, asm_psrf_eval and asm_clade_counts on that context are
+ * collective calls (every rank calls them with the same arguments and receives the complete result); ESS calls stay
+ * local to the traces the rank was given and asm_comm_all_gather_f64 combines the per-rank result vectors. */
+#define ASM_COMM_ID_BYTES 128
+int32_t asm_comm_unique_id(uint8_t* id_out /* [ASM_COMM_ID_BYTES] */);
+int32_t asm_comm_init_rank(asm_ctx* ctx, const uint8_t* id, int32_t rank, int32_t n_ranks);
+/* rank / number of ranks of the context's communicator (0 / 1 without one; a multi-GPU context reports rank 0 of
+ * n_devices) and the number of devices this context drives itself. */
+int32_t asm_comm_info(const asm_ctx* ctx, int32_t* rank, int32_t* n_ranks, int32_t* n_local_devices);
+/* NCCL_VERSION_CODE of the NCCL the library loaded, 0 if none could be loaded. */
+int32_t asm_comm_nccl_version(void);
+/* all[r * n_local + i] = rank r's local[i] (host buffers; the same n_local on every rank). */
+int32_t asm_comm_all_gather_f64(asm_ctx* ctx, const double* local, int64_t n_local, double* all);
 /* Message of the last failure on this context ("" if none).  ctx may be NULL: then the message
  * of the last failed asm_create on this thread. */
 const char* asm_last_error(const asm_ctx* ctx);
@@ -140,6 +174,12 @@ int32_t asm_ess_batch(asm_ctx* ctx, int32_t n_traces, int64_t n_samples, int64_t
 /* Same with `d_traces` on the device; outputs are host buffers. */
 int32_t asm_ess_batch_device(asm_ctx* ctx, int32_t n_traces, int64_t n_samples, int64_t stride,
                              const double* d_traces, int32_t max_lag, double* act_out, double* ess_out);
+/* Resident form of the batch (the benchmark's "inputs already in HBM" leg; a multi-GPU context deals the traces
+ * to its devices here): asm_ess_traces_put uploads and keeps [n_traces][n_samples], asm_ess_traces_eval evaluates
+ * what is resident, outputs as asm_ess_batch. */
+int32_t asm_ess_traces_put(asm_ctx* ctx, int32_t n_traces, int64_t n_samples, int64_t stride, const double* traces);
+int32_t asm_ess_traces_count(const asm_ctx* ctx, int32_t* n_traces, int64_t* n_samples);
+int32_t asm_ess_traces_eval(asm_ctx* ctx, int32_t max_lag, double* act_out, double* ess_out);
 /* Streaming form.  Append n_new log lines of n_cols columns for `chain`, row-major
  * [n_new][n_cols] (readLogLines, AutoStopMCMC.java:459-466). */
 int32_t asm_traces_append(asm_ctx* ctx, int32_t chain, int32_t n_cols, int64_t n_new, const double* values);

@@ -1,14 +1,12 @@
-"""World-size-2 test of the multi-GPU host logic on CPU (gloo).  The device side is replaced by a
-stand-in that produces each rank's partial S table from the oracle, split the way asm_shard splits
-tile pairs (any disjoint cover works: the sums are exact integers); what is under test is the
-orchestration in asm_b200/multi.py -- shard arguments, the int64 all-reduce, the finish step, the
-ESS gather and the NaN-propagating min."""
-import ctypes
+"""World-size-2 test of the launcher-side multi-GPU logic on CPU (gloo): what asm_b200/multi.py adds around the
+library for the one-process-per-GPU mode -- carrying the communicator id from rank 0 to the other ranks, the
+contiguous block dealing of ESS traces, reassembling the per-rank ESS vectors, the NaN-propagating min.  The device
+side (NCCL inside libasmgpu.so) is replaced by a stand-in whose all-gather runs over gloo; the collectives
+themselves are tested on hardware by tests/test_gpu_multi.py and tests/c/multi_gpu_check.c."""
 import os
 import sys
 
 import numpy as np
-import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -17,94 +15,67 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 class StandInCtx:
-    """Mimics GpuContext's device-pointer entry points on host memory."""
+    """GpuContext's communicator-facing calls on host memory (ESS through the oracle, all-gather over gloo)."""
 
-    def __init__(self, ts, n_chains):
-        self.ts, self.n_chains = ts, n_chains
-        self.calls = []
+    def __init__(self):
+        self.joined = None
 
-    def n_rows(self, row_start, end, delta):
-        return (end - row_start + delta - 1) // delta if end > row_start else 0
+    def comm_init_rank(self, comm_id, rank, n_ranks):
+        self.joined = (bytes(comm_id), rank, n_ranks)
 
-    def _view(self, ptr, shape, dtype):
-        n = int(np.prod(shape))
-        buf = (ctypes.c_byte * (n * np.dtype(dtype).itemsize)).from_address(ptr)
-        return np.frombuffer(buf, dtype=dtype).reshape(shape)
+    def ess_batch(self, traces):
+        import oracle as O
+        t = np.ascontiguousarray(traces, dtype=np.float64)
+        if t.shape[0] == 0:
+            return np.empty(0), np.empty(0)
+        return O.ess_batch(t)
 
-    def psrf_sums_device(self, burnin, row_start, end, delta, method, shard, d_S_ptr):
-        idx, cnt = shard
-        self.calls.append(shard)
-        C, n = self.n_chains, self.n_rows(row_start, end, delta)
-        full = self.ts.psrf_sums(burnin, row_start, end, delta).astype(np.int64)
-        part = np.zeros_like(full)
-        # deal (row, chain) cells round-robin, like tile pairs t % shard_count == shard_index
-        cells = np.arange(full.size).reshape(full.shape)
-        mask = (cells % cnt) == idx
-        part[mask] = full[mask]
-        self._view(d_S_ptr, (C, n, C), np.int64)[...] = part
-
-    def trees_set_device(self, chain, d_ptr, n_trees, words):
-        self.trees = getattr(self, "trees", {})
-        self.trees[chain] = self._view(d_ptr, (n_trees, words), np.uint64).copy()
-
-    def psrf_finish_device(self, d_S_ptr, n_rows, want_rows=False):
-        C = self.n_chains
-        S = self._view(d_S_ptr, (C, max(n_rows, 1), C), np.int64)[:, :n_rows, :].astype(np.float64)
-        mean = np.empty((C, C))
-        for a in range(C):
-            for b in range(C):
-                s = 0.0
-                for r in range(n_rows):  # TreePSRF.java:264-271, :287-292
-                    s += np.sqrt(S[a, r, b] / S[a, r, a]) if S[a, r, a] != 0 else np.sqrt(S[a, r, b])
-                mean[a, b] = s / n_rows if n_rows else float("nan")
-        return mean
+    def all_gather_f64(self, local):
+        world = dist.get_world_size()
+        out = [torch.empty(len(local), dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(out, torch.from_numpy(np.ascontiguousarray(local, dtype=np.float64)))
+        return torch.cat(out).numpy()
 
 
 def _worker(rank, world, port, q):
     sys.path.insert(0, ROOT)
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         import oracle as O
         from asm_b200 import multi
-        from conftest import SynthChains
-        ch = SynthChains(14, 60, 3, beta=1.5)
-        ctx = StandInCtx(ch.ts, 3)
-        burnin, start, end, delta = [4, 0, 9], 4, 60, 2
-        mean, S = multi.psrf_eval_multi(ctx, dist, burnin, start, end, delta, 0, "cpu")
-        want_S = ch.ts.psrf_sums(burnin, start, end, delta)
-        ok = np.array_equal(S.numpy().astype(np.float64), want_S) and ctx.calls == [(rank, world)]
-        for a in range(3):
-            for b in range(3):
-                if a != b:
-                    ok &= mean[a, b] == ch.ts.psrf_rows_mean(a, b, start, burnin, end, delta)
-        # sharded upload: ragged row counts (odd, smaller than the world, empty), bit patterns with the top bit set
-        rng = np.random.default_rng(5)
-        bits = [rng.integers(0, 2**64, size=(n, 3), dtype=np.uint64) for n in (7, 1, 0)]
-        multi.trees_set_sharded(ctx, dist, bits, "cpu")
-        ok &= all(np.array_equal(ctx.trees[c], bits[c]) for c in range(3))
-        pinned = [torch.from_numpy(b.copy()) for b in bits]  # uint64 tensors, as bench.py passes them
-        full = multi.gather_tree_shards(dist, pinned, "cpu")
-        ok &= all(np.array_equal(full[c].numpy().view(np.uint64), bits[c]) for c in range(3))
-        # ESS: 5 traces over 2 ranks, one of them constant (NaN)
+        ctx = StandInCtx()
+        cid = multi.init_comm(ctx, dist, make_id=lambda: bytes(range(128)))
+        ok = ctx.joined == (bytes(range(128)), rank, world) and cid == bytes(range(128))
+        # ESS: 5 traces over 2 ranks (blocks of 3 and 2), one of them constant (NaN)
         rng = np.random.default_rng(0)
         x = rng.normal(size=(5, 400))
         x[3] = 1.0
-        mine = multi.my_traces(5, rank, world)
-        ess, mn = multi.ess_multi(None, dist, x[mine], 5, "cpu", ess_fn=lambda t: O.ess_batch(np.ascontiguousarray(t)))
+        lo, hi = multi.block_of(5, world, rank)
+        ess, mn = multi.ess_sharded(ctx, x[lo:hi], 5, rank, world)
         want = O.ess_batch(x)[1]
         ok &= np.array_equal(ess, want, equal_nan=True) and np.isnan(mn)
-        ess2, mn2 = multi.ess_multi(None, dist, x[[i for i in mine if i != 3]][: len(multi.my_traces(4, rank, world))], 4,
-                                    "cpu", ess_fn=lambda t: O.ess_batch(np.ascontiguousarray(t)))
-        q.put((rank, bool(ok), float(mn2)))
+        # fewer traces than ranks would leave a rank empty: 1 trace over 2 ranks
+        lo1, hi1 = multi.block_of(1, world, rank)
+        ess1, mn1 = multi.ess_sharded(ctx, x[lo1:hi1], 1, rank, world)
+        ok &= np.array_equal(ess1, want[:1]) and mn1 == want[0]
+        q.put((rank, bool(ok), float(mn1)))
     finally:
         dist.destroy_process_group()
 
 
-def test_two_rank_gloo():
-    from asm_b200.multi import java_min
+def test_block_dealing_covers_everything_once():
+    from asm_b200.multi import block_of, java_min
+    for n in (0, 1, 5, 7, 8, 1000, 1001):
+        for world in (1, 2, 3, 4, 8):
+            blocks = [block_of(n, world, r) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(blocks[r][1] == blocks[r + 1][0] for r in range(world - 1))
+            assert max(hi - lo for lo, hi in blocks) == (n + world - 1) // world
     assert np.isnan(java_min([3.0, float("nan"), 1.0])) and java_min([3.0, 1.0]) == 1.0 and java_min([]) == float("inf")
+
+
+def test_two_rank_gloo():
     ctxm = mp.get_context("spawn")
     q = ctxm.Queue()
     port = 29500 + os.getpid() % 2000
@@ -115,4 +86,4 @@ def test_two_rank_gloo():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    assert sorted(r[0] for r in res) == [0, 1] and all(r[1] for r in res)
+    assert sorted(r[0] for r in res) == [0, 1] and all(r[1] for r in res) and res[0][2] == res[1][2]
