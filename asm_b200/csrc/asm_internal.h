@@ -37,14 +37,18 @@ struct PsrfLayout {
   int32_t Wp = 0;                 // padded words per row, multiple of 16 (popcount operand)
   int32_t pitch8 = 0;             // bytes per row of the int8 operand, multiple of 128
   int32_t pitch4 = 0;             // bytes per row of the fp4 operand (two clades per byte), multiple of 128
-  int32_t block_real = 256;       // live rows per 256-row block: 256, or 240 for the fp4 kernel (N = 240 tiles)
-  // padded position of output row r of chain a: r < rowsA[a] ? phys(segA_off[a], rowA0[a] + r)
-  //                                                          : phys(segB_off[a], rowB0[a] + r - rowsA[a]),
-  // phys(off, k) = off + (k / block_real) * 256 + k % block_real
+  int32_t block_real = 256;       // live rows per 256-row block (always 256 since round 2: segments are dense)
+  int32_t col_block = 256;        // trees per column block: 256, or 240 for the fp4 kernel (N = 240 tiles over the SAME
+                                  // dense rows: a column block starts at any row, TMA boxes need no alignment)
+  // padded position of output row r of chain a: r < rowsA[a] ? segA_off[a] + rowA0[a] + r
+  //                                                          : segB_off[a] + rowB0[a] + r - rowsA[a]
   int64_t segA_off[ASM_MAX_CHAINS], segB_off[ASM_MAX_CHAINS];
   int64_t rowA0[ASM_MAX_CHAINS], rowB0[ASM_MAX_CHAINS];
   int32_t rowsA[ASM_MAX_CHAINS];
-  int64_t padB[ASM_MAX_CHAINS];   // zero-padding rows inside the column segment of chain c
+  // zero rows that the kernels see beside the column trees of chain c: padC[c] when those trees are the columns of a
+  // tile (column blocks of col_block trees), padR[c] when they are its rows (256-row blocks) and the sums reach the
+  // other operand through the symmetric half.  Removed in closed form by the compaction kernel.
+  int64_t padC[ASM_MAX_CHAINS], padR[ASM_MAX_CHAINS];
   int64_t tiles_total = 0, tiles_done = 0;
   int64_t bits_used = 0;          // operand width (bits) of the kernel that ran last
 };
@@ -89,6 +93,13 @@ struct asm_ctx {
   std::vector<uint32_t> walk_host;  // Morton tile walk of the int8 kernel (rebuilt when the block count changes)
   DevBuf walk_dev;
   long long walk_nb = -1;
+  // fp4 kernel: row blocks (256 trees) and column blocks (240 trees) over the same dense operand rows
+  std::vector<int2> f4_blk_host;   // [nR row blocks][nC column blocks]: {first padded row, chain | flags << 8}
+  DevBuf f4_blk_dev;
+  int32_t f4_nR = 0, f4_nC = 0;
+  std::vector<uint32_t> f4_walk_host;
+  std::vector<long long> f4_walk_key;  // first padded rows of the blocks the cached walk was built for
+  DevBuf f4_walk_dev;
   uint32_t func_attr_done = 0;  // bit per kernel whose max-dynamic-smem attribute is set on this device
   // measurement
   cudaEvent_t timer[16] = {};
@@ -140,10 +151,10 @@ struct LaunchScope {
 // ---- kernels (launchers live next to their kernels) ---------------------------------------------------
 // psrf_layout.cu
 int32_t psrf_build_layout(asm_ctx* ctx, const int32_t* burnin, int32_t row_start, int32_t end, int32_t delta,
-                          int32_t block_real = kBlockRows);
+                          int32_t col_block = kBlockRows);
 int32_t psrf_gather_bits(asm_ctx* ctx);  // layout -> opnd_bits [Tp][Wp], nbits [Tp], blk_meta
 int32_t psrf_gather_i8(asm_ctx* ctx);    // layout -> opnd_i8 [Tp][pitch8] directly, nbits [Tp], blk_meta
-int32_t psrf_gather_f4(asm_ctx* ctx);    // layout (block_real = 240) -> opnd_f4 [Tp][pitch4] e2m1 nibbles, nbits, blk_meta
+int32_t psrf_gather_f4(asm_ctx* ctx);    // layout (col_block = 240) -> opnd_f4 [Tp][pitch4] e2m1 nibbles, nbits, f4 block tables
 int32_t psrf_check_max_bits(asm_ctx* ctx, int32_t limit);  // ASM_E_UNSUPPORTED if a gathered row has more set bits
 int32_t psrf_compact(asm_ctx* ctx, asm_shard shard, int64_t* d_S_out);  // S_pad -> [C][n_rows][C], pad-corrected
 int32_t psrf_finish(asm_ctx* ctx, const int64_t* d_S, int32_t n_rows, double* psrf_rows_host, double* psrf_mean_host);

@@ -159,9 +159,8 @@ __global__ void __launch_bounds__(256) max_bits_kernel(const int32_t* __restrict
 
 struct CompactParams {
   int32_t C, n_rows, subtract_pad;
-  int32_t block_real;
   int64_t segA_off[ASM_MAX_CHAINS], segB_off[ASM_MAX_CHAINS], rowA0[ASM_MAX_CHAINS], rowB0[ASM_MAX_CHAINS];
-  int64_t padB[ASM_MAX_CHAINS];
+  int64_t padC[ASM_MAX_CHAINS], padR[ASM_MAX_CHAINS];
   int32_t rowsA[ASM_MAX_CHAINS];
 };
 
@@ -178,11 +177,14 @@ __global__ void __launch_bounds__(256) compact_kernel(const __grid_constant__ Co
     int a = (int)(ar / n_rows);
     const bool inA = r < prm->rowsA[a];
     const int64_t k = inA ? prm->rowA0[a] + r : prm->rowB0[a] + (r - prm->rowsA[a]);
-    const int64_t p = (inA ? prm->segA_off[a] : prm->segB_off[a]) + (k / prm->block_real) * kBlockRows + k % prm->block_real;
+    const int64_t p = (inA ? prm->segA_off[a] : prm->segB_off[a]) + k;
     long long v = S_pad[p * C + c];
     if (prm->subtract_pad) {
+      // Every pair of (padded) rows is evaluated once, as (row = the earlier one, column = the later one).  The zero
+      // rows behind chain c's column trees come after this tree when a <= c (they were columns of its tiles: padC of
+      // them) and before it when a > c (they were rows, and reached it through the column sums: padR of them).
       long long e = (long long)nbits[p] + 1;  // RF(tree, empty row) + 1
-      v -= prm->padB[c] * e * e;
+      v -= (a <= c ? prm->padC[c] : prm->padR[c]) * e * e;
     }
     out[i] = v;
   }
@@ -253,7 +255,7 @@ inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 }  // namespace
 
 int32_t psrf_build_layout(asm_ctx* ctx, const int32_t* burnin, int32_t row_start, int32_t end, int32_t delta,
-                          int32_t block_real) {
+                          int32_t col_block) {
   PsrfLayout& L = ctx->layout;
   const int C = ctx->n_chains;
   if (delta < 1) return asm_fail(ctx, ASM_E_INVALID, "psrf: delta must be >= 1, not %d", delta);
@@ -274,8 +276,15 @@ int32_t psrf_build_layout(asm_ctx* ctx, const int32_t* burnin, int32_t row_start
   L.Wp = (int32_t)round_up(ctx->words > 0 ? ctx->words : 1, kBitsPad / 64);
   L.pitch8 = (int32_t)round_up((int64_t)(ctx->words > 0 ? ctx->words : 1) * 64, 128);  // int8 operand row pitch: whole 128-byte K blocks
   L.pitch4 = (int32_t)round_up((int64_t)(ctx->words > 0 ? ctx->words : 1) * 32, 128);  // fp4: two clades per byte
-  L.block_real = block_real;
-  auto padded = [&](int64_t n) { return (n + block_real - 1) / block_real * kBlockRows; };  // rows a segment occupies
+  L.block_real = kBlockRows;
+  L.col_block = col_block;
+  // rows a segment occupies: whole 256-row blocks, and (fp4) room for the last 240-tree column block, whose second
+  // 128-row TMA box starts at row 120 of the block
+  auto padded = [&](int64_t n) {
+    int64_t ext = round_up(n, kBlockRows);
+    if (col_block != kBlockRows) ext = std::max(ext, round_up(round_up(n, col_block) + (kTileRows - col_block / 2), kBlockRows));
+    return ext;
+  };
   if (L.n_rows == 0) return ASM_OK;
   int64_t off = 0;
   for (int c = 0; c < C; c++) {
@@ -294,9 +303,10 @@ int32_t psrf_build_layout(asm_ctx* ctx, const int32_t* burnin, int32_t row_start
     if (nB > 0) {
       L.seg[L.n_seg++] = Segment{off, nB, u + kq * delta, c, 1};
       off += padded(nB);
-      L.padB[c] = padded(nB) / kBlockRows * block_real - nB;  // zero rows among the rows the kernels use as columns
+      L.padC[c] = round_up(nB, col_block) - nB;   // zero rows among the rows the kernels use as columns ...
+      L.padR[c] = round_up(nB, kBlockRows) - nB;  // ... and as rows
     } else {
-      L.padB[c] = 0;
+      L.padC[c] = L.padR[c] = 0;
     }
     L.rowsA[c] = (int32_t)std::max<int64_t>(0, kq - kr);
     L.segA_off[c] = offA;
@@ -326,7 +336,7 @@ static int32_t psrf_prepare(asm_ctx* ctx, SegTableDev& tab) {
 
   // per-tile metadata {chain, flags}
   std::vector<int2>& meta = ctx->meta_host;
-  meta.resize((size_t)n_tiles);
+  meta.assign((size_t)n_tiles, make_int2(0, 0));
   for (int s = 0; s < L.n_seg; s++) {
     const Segment& g = L.seg[s];
     const int64_t n_tiles_seg = (g.n + L.block_real - 1) / L.block_real * (kBlockRows / kTileRows);
@@ -387,12 +397,57 @@ int32_t psrf_gather_i8(asm_ctx* ctx) {
   return ASM_OK;
 }
 
+// Block tables of the fp4 kernel: the dense rows of every segment cut into row blocks of 256 trees (operand A of a
+// tile, one half per CTA of the pair) and, independently, into column blocks of col_block = 240 trees (operand B:
+// TMEM has room for two 240-column accumulators beside the scale factors).  Entry = {first padded row,
+// chain | flags << 8}; flags: kFlagCol (the segment's trees are columns of the statistic), bit 1 / bit 2 = the first /
+// second 128 rows of a row block hold output rows, bit 1 = a column block holds output rows.
+static int32_t psrf_build_f4_blocks(asm_ctx* ctx) {
+  PsrfLayout& L = ctx->layout;
+  std::vector<int2>& blk = ctx->f4_blk_host;
+  blk.clear();
+  std::vector<int2> cols;
+  for (int s = 0; s < L.n_seg; s++) {
+    const Segment& g = L.seg[s];
+    int64_t first_row;  // first tree (index within the segment) that is an output row
+    if (!g.is_col) {
+      first_row = (L.rowsA[g.chain] > 0) ? L.rowA0[g.chain] : g.n;
+    } else {
+      first_row = L.rowB0[g.chain];
+      if (L.n_rows - L.rowsA[g.chain] <= 0) first_row = g.n;
+    }
+    auto has_rows = [&](int64_t lo, int64_t hi) { return std::min<int64_t>(hi, g.n) > std::max<int64_t>(lo, first_row); };
+    const uint32_t base_flags = g.is_col ? kFlagCol : 0;
+    for (int64_t k = 0; k < g.n; k += kBlockRows) {
+      uint32_t f = base_flags;
+      if (has_rows(k, k + kTileRows)) f |= 2;
+      if (has_rows(k + kTileRows, k + kBlockRows)) f |= 4;
+      blk.push_back(make_int2((int)(g.dst_off + k), (int)((uint32_t)g.chain | (f << 8))));
+    }
+    for (int64_t k = 0; k < g.n; k += L.col_block) {
+      uint32_t f = base_flags;
+      if (has_rows(k, k + L.col_block)) f |= 2;
+      cols.push_back(make_int2((int)(g.dst_off + k), (int)((uint32_t)g.chain | (f << 8))));
+    }
+  }
+  ctx->f4_nR = (int32_t)blk.size();
+  ctx->f4_nC = (int32_t)cols.size();
+  blk.insert(blk.end(), cols.begin(), cols.end());
+  int32_t rc;
+  if ((rc = asm_reserve(ctx, ctx->f4_blk_dev, sizeof(int2) * std::max<size_t>(blk.size(), 1))) != ASM_OK) return rc;
+  if (!blk.empty())  // pageable source: staged by the runtime before the call returns
+    ASM_CUDA(ctx, cudaMemcpyAsync(ctx->f4_blk_dev.p, blk.data(), sizeof(int2) * blk.size(), cudaMemcpyHostToDevice, ctx->stream));
+  return ASM_OK;
+}
+
 int32_t psrf_gather_f4(asm_ctx* ctx) {
   PsrfLayout& L = ctx->layout;
   int32_t rc;
+  if (L.Tp >= (int64_t)1 << 31) return asm_fail(ctx, ASM_E_UNSUPPORTED, "psrf: %lld padded rows exceed the fp4 kernel's 32-bit row index", (long long)L.Tp);
   if ((rc = asm_reserve(ctx, ctx->opnd_f4, (size_t)L.Tp * L.pitch4)) != ASM_OK) return rc;
   SegTableDev tab;
   if ((rc = psrf_prepare(ctx, tab)) != ASM_OK) return rc;
+  if ((rc = psrf_build_f4_blocks(ctx)) != ASM_OK) return rc;
   {
     LaunchScope ls(ctx, ASM_K_GATHER);
     int blocks = (int)std::min<int64_t>((L.Tp + 7) / 8, (int64_t)ctx->sm_count * 16);
@@ -424,14 +479,14 @@ int32_t psrf_compact(asm_ctx* ctx, asm_shard shard, int64_t* d_S_out) {
   CompactParams prm;
   prm.C = L.C;
   prm.n_rows = L.n_rows;
-  prm.block_real = L.block_real;
   prm.subtract_pad = shard.shard_index == 0 ? 1 : 0;  // the closed-form pad term is removed exactly once
   for (int c = 0; c < L.C; c++) {
     prm.segA_off[c] = L.segA_off[c];
     prm.segB_off[c] = L.segB_off[c];
     prm.rowA0[c] = L.rowA0[c];
     prm.rowB0[c] = L.rowB0[c];
-    prm.padB[c] = L.padB[c];
+    prm.padC[c] = L.padC[c];
+    prm.padR[c] = L.padR[c];
     prm.rowsA[c] = L.rowsA[c];
   }
   {

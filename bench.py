@@ -78,7 +78,7 @@ def live_peaks(device_index):
         out["gemm"] = P.gemm_peaks(f"cuda:{device_index}", sustain_s=1.0)
     except Exception as e:  # noqa: BLE001
         out["gemm"] = {"error": repr(e)[:300]}
-    out["pipes"] = P.pipe_peaks()
+    out["pipes"] = P.pipe_peaks(device_index)
     return out
 
 

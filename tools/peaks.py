@@ -55,14 +55,14 @@ def gemm_peaks(device="cuda:0", n=8192, sustain_s=2.0):
             res["bf16"] = _time_gemm(torch, lambda: a @ b, flops, sustain_s)
             del a, b
         except Exception as e:  # noqa: BLE001
-            res["bf16_error"] = repr(e)[:300]
+            res["bf16_error"] = repr(e)[:900]
         try:
             a = torch.randint(0, 2, (n, n), device=device, dtype=torch.int8)
             b = torch.randint(0, 2, (n, n), device=device, dtype=torch.int8).t().contiguous().t()
             res["int8"] = _time_gemm(torch, lambda: torch._int_mm(a, b), flops, sustain_s)
             del a, b
         except Exception as e:  # noqa: BLE001
-            res["int8_error"] = repr(e)[:300]
+            res["int8_error"] = repr(e)[:900]
         # block-scaled fp4: packed e2m1 pairs, A [M][K/2] row-major, B [K/2][N] column-major, unit scales
         for name, sdt, blk, sval in (("fp4_mx_e8m0_block32", "float8_e8m0fnu", 32, 127), ("fp4_nv_e4m3_block16", "float8_e4m3fn", 16, 0x38)):
             try:
@@ -78,23 +78,26 @@ def gemm_peaks(device="cuda:0", n=8192, sustain_s=2.0):
                 res[name] = _time_gemm(torch, fn, flops, sustain_s)
                 del a, b, sa, sb
             except Exception as e:  # noqa: BLE001
-                res[name + "_error"] = repr(e)[:300]
+                res[name + "_error"] = repr(e)[:900]
         torch.cuda.empty_cache()
     return res
 
 
-def pipe_peaks():
+def pipe_peaks(device_index=0):
     exe = os.path.join(ROOT, "tools", "microbench")
     if not os.path.exists(exe):
         return {"error": "tools/microbench not built (__graft_entry__.build() compiles it)"}
     try:
-        r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+        env = dict(os.environ)  # the binary measures device 0 of what it sees: show it this process's GPU only
+        vis = [v for v in env.get("CUDA_VISIBLE_DEVICES", "").split(",") if v]
+        env["CUDA_VISIBLE_DEVICES"] = vis[device_index] if device_index < len(vis) else str(device_index)
+        r = subprocess.run([exe], capture_output=True, text=True, timeout=120, env=env)
         d = json.loads(r.stdout)
         keep = {k: d[k] for k in ("gpu", "sms", "clock_khz", "popc", "dadd", "dmul", "dfma", "dmul_dadd_pair_instrs") if k in d}
         keep["fp64_issue_tflops"] = d["dmul_dadd_pair_instrs"]["ops_per_s"] / 1e12  # one DMUL or DADD per issue slot = one flop
         return keep
     except Exception as e:  # noqa: BLE001
-        return {"error": repr(e)[:300]}
+        return {"error": repr(e)[:900]}
 
 
 if __name__ == "__main__":
