@@ -323,6 +323,38 @@ __global__ void __launch_bounds__(256) concat_kernel(const __grid_constant__ Con
   }
 }
 
+// Pilot of the staged evaluation: one warp per trace estimates the autocorrelation at lag `lag` from the first P
+// samples and files the trace under "long" (slowly decaying: its integral loop will run far past the first stages)
+// or "short".  Only the schedule depends on it -- which lags are evaluated in one launch -- never a result.
+__global__ void __launch_bounds__(256) ess_pilot_kernel(const double* __restrict__ traces, long long stride, int n_traces,
+                                                         int P, int lag, double threshold, int* __restrict__ ids_short,
+                                                         int* __restrict__ ids_long, int* __restrict__ counts) {
+  const int lane = threadIdx.x & 31;
+  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= n_traces) return;
+  const double* __restrict__ x = traces + (long long)t * stride;
+  double m = 0.0;
+  for (int i = lane; i < P; i += 32) m += x[i];
+  for (int o = 16; o > 0; o >>= 1) m += __shfl_xor_sync(0xffffffffu, m, o);
+  m /= (double)P;
+  double v = 0.0, c = 0.0;
+  for (int i = lane; i < P; i += 32) {
+    const double d = x[i] - m;
+    v += d * d;
+    if (i + lag < P) c += d * (x[i + lag] - m);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    v += __shfl_xor_sync(0xffffffffu, v, o);
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+  }
+  if (lane == 0) {
+    const bool is_long = v > 0.0 && c > threshold * v;
+    if (is_long)
+      ids_long[atomicAdd(&counts[1], 1)] = t;
+    else
+      ids_short[atomicAdd(&counts[0], 1)] = t;
+  }
+}
 
 }  // namespace
 
@@ -339,6 +371,14 @@ struct EssGroup {
   int stage = 0, n_open = 0;
   const int* ids_in = nullptr;
   bool done = false;
+  // A group may be a SUBSET of its trace range (the "short" / "long" halves the pilot makes of one range): ids0 lists
+  // its n0 traces (relative to t0); `slot` selects its private work-list buffers and counter; the state of the range is
+  // cleared and the outputs are copied by the caller, once, for both halves.
+  const int* ids0 = nullptr;
+  int n0 = 0;
+  int slot = -1;
+  bool subset = false;
+  int peer_ctas = 0;  // CTAs of the other groups' first stages launched beside this one (for the CTA spreading)
   int bounds[12] = {0, 2048};  // stage s evaluates the lags [bounds[s], bounds[s+1]); a stage may be narrowed
   int n_stage = 1;
   void plan(std::initializer_list<int> b) {
@@ -350,7 +390,9 @@ struct EssGroup {
 struct EssScratch {
   double *act, *ess, *sums, *sls;
   EssState* state;
-  int *used, *ids[2], *counter;
+  int *used, *ids_base, *counter;
+  size_t nd;
+  int* ids(int slot, int k) const { return ids_base + ((size_t)slot * 2 + (size_t)k) * nd; }
   int* h_counter;  // pinned
 };
 
@@ -442,7 +484,7 @@ int32_t ess_launch_stage(asm_ctx* ctx, EssGroup& g, const EssScratch& sc, const 
   double* sls = sc.sls + (size_t)g.t0 * lags_stride;
   if (s == 0) {
     if (g.ready) ASM_CUDA(ctx, cudaStreamWaitEvent(g.st, g.ready, 0));
-    ASM_CUDA(ctx, cudaMemsetAsync(sc.state + g.t0, 0, sizeof(EssState) * (size_t)g.nt, g.st));
+    if (!g.subset) ASM_CUDA(ctx, cudaMemsetAsync(sc.state + g.t0, 0, sizeof(EssState) * (size_t)g.nt, g.st));
   }
   (void)L;
   if (n_samples > 0) {
@@ -463,7 +505,7 @@ int32_t ess_launch_stage(asm_ctx* ctx, EssGroup& g, const EssScratch& sc, const 
     // A CTA stays where it is placed for the whole walk over the samples, and the block scheduler is free to
     // stack the CTAs of a small grid on few SMs when other groups' kernels are resident.  Asking for just too
     // much shared memory for one more CTA than an even spread needs keeps them apart.
-    const int per_sm = ((int)(grid.x * grid.y) + ctx->sm_count - 1) / ctx->sm_count;
+    const int per_sm = ((int)(grid.x * grid.y) + (s == 0 ? g.peer_ctas : 0) + ctx->sm_count - 1) / ctx->sm_count;
     const size_t smem_spread = std::min<size_t>((size_t)ctx->smem_optin, (size_t)ctx->smem_optin / (per_sm + 1) + 1024);
     LaunchScope ls(ctx, ASM_K_ESS_LAG, g.st);
 #define ASM_ESS_LAUNCH(RR)                                                                                     \
@@ -486,6 +528,27 @@ int32_t ess_launch_stage(asm_ctx* ctx, EssGroup& g, const EssScratch& sc, const 
 
 }  // namespace
 
+// Scratch of one batch: [act n][ess n][sums n][state n][used n (int)][work lists: 2 slots x 2 buffers x n (int)]
+// [pilot lists: 2 x n (int)][counters 32 (int)]
+static int32_t ess_scratch(asm_ctx* ctx, int32_t n_traces, EssScratch& sc) {
+  const size_t nd = (size_t)n_traces;
+  const size_t bytes = sizeof(double) * 3 * nd + sizeof(EssState) * nd + sizeof(int) * (7 * nd + 32);
+  int32_t rc;
+  if ((rc = asm_reserve(ctx, ctx->ess_out, bytes)) != ASM_OK) return rc;
+  sc.nd = nd;
+  sc.act = (double*)ctx->ess_out.p;
+  sc.ess = sc.act + nd;
+  sc.sums = sc.ess + nd;
+  sc.state = (EssState*)(sc.sums + nd);
+  sc.used = (int*)(sc.state + nd);
+  sc.ids_base = sc.used + nd;
+  sc.counter = sc.used + 7 * nd;
+  sc.sls = (double*)ctx->ess_sls.p;
+  if (!ctx->h_pinned) ASM_CUDA(ctx, cudaMallocHost(&ctx->h_pinned, 256));
+  sc.h_counter = (int*)ctx->h_pinned;
+  return ASM_OK;
+}
+
 // Runs `n_groups` groups (each a trace range with its own stream) through the staged evaluation.
 static int32_t ess_run_groups(asm_ctx* ctx, EssGroup* groups, int n_groups, int32_t n_traces, int64_t n_samples,
                               int64_t stride, const double* d_traces, int32_t max_lag, double* act_out_host,
@@ -494,22 +557,8 @@ static int32_t ess_run_groups(asm_ctx* ctx, EssGroup* groups, int n_groups, int3
   const int lags_stride = 2048;  // >= ASM_MAX_LAG rounded up to the widest stage
   int32_t rc;
   if ((rc = asm_reserve(ctx, ctx->ess_sls, sizeof(double) * (size_t)n_traces * lags_stride)) != ASM_OK) return rc;
-  // [act n][ess n][sums n][state n][used n (int)][ids_a n (int)][ids_b n (int)][counters 16 (int)]
-  const size_t nd = (size_t)n_traces;
-  const size_t bytes = sizeof(double) * 3 * nd + sizeof(EssState) * nd + sizeof(int) * (3 * nd + 16);
-  if ((rc = asm_reserve(ctx, ctx->ess_out, bytes)) != ASM_OK) return rc;
   EssScratch sc;
-  sc.act = (double*)ctx->ess_out.p;
-  sc.ess = sc.act + nd;
-  sc.sums = sc.ess + nd;
-  sc.state = (EssState*)(sc.sums + nd);
-  sc.used = (int*)(sc.state + nd);
-  sc.ids[0] = sc.used + nd;
-  sc.ids[1] = sc.used + 2 * nd;
-  sc.counter = sc.used + 3 * nd;
-  sc.sls = (double*)ctx->ess_sls.p;
-  if (!ctx->h_pinned) ASM_CUDA(ctx, cudaMallocHost(&ctx->h_pinned, 64));
-  sc.h_counter = (int*)ctx->h_pinned;
+  if ((rc = ess_scratch(ctx, n_traces, sc)) != ASM_OK) return rc;
 
   if (!(ctx->func_attr_done & kAttrEss)) {
     const int optin = ctx->smem_optin;
@@ -532,7 +581,7 @@ static int32_t ess_run_groups(asm_ctx* ctx, EssGroup* groups, int n_groups, int3
       ess_scan_kernel<<<(g.n_open + 127) / 128, 128, 0, g.st>>>(
           d_traces + (size_t)g.t0 * stride, stride, n_samples, g.n_open, g.ids_in, max_lag, e, lags_stride,
           sc.sls + (size_t)g.t0 * lags_stride, sc.sums + g.t0, sc.state + g.t0, sc.act + g.t0, sc.ess + g.t0,
-          sc.used + g.t0, sc.ids[g.stage & 1] + g.t0, sc.counter + gi);
+          sc.used + g.t0, sc.ids(g.slot, g.stage & 1) + g.t0, sc.counter + gi);
     }
     ASM_CUDA(ctx, cudaGetLastError());
     ASM_CUDA(ctx, cudaMemcpyAsync(sc.h_counter + gi, sc.counter + gi, sizeof(int), cudaMemcpyDeviceToHost, g.st));
@@ -542,9 +591,10 @@ static int32_t ess_run_groups(asm_ctx* ctx, EssGroup* groups, int n_groups, int3
   int remaining = 0;
   for (int gi = 0; gi < n_groups; gi++) {
     groups[gi].stage = 0;
-    groups[gi].n_open = groups[gi].nt;
-    groups[gi].ids_in = nullptr;
-    groups[gi].done = groups[gi].nt == 0;
+    if (groups[gi].slot < 0) groups[gi].slot = 0;
+    groups[gi].n_open = groups[gi].subset ? groups[gi].n0 : groups[gi].nt;
+    groups[gi].ids_in = groups[gi].subset ? groups[gi].ids0 : nullptr;
+    groups[gi].done = groups[gi].n_open == 0;
     if (!groups[gi].done) {
       if ((rc = launch(gi)) != ASM_OK) return rc;
       remaining++;
@@ -556,7 +606,7 @@ static int32_t ess_run_groups(asm_ctx* ctx, EssGroup* groups, int n_groups, int3
   const bool trace_on = getenv("ASM_ESS_TRACE") != nullptr;  // tuning aid: host-side timeline on stderr
   const auto t_begin = std::chrono::steady_clock::now();
   auto now_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
-  bool seen_ready[asm_ctx::kMaxGroups] = {};
+  bool seen_ready[2 * asm_ctx::kMaxGroups] = {};
   while (remaining > 0) {
     bool progressed = false;
     for (int gi = 0; gi < n_groups; gi++) {
@@ -580,13 +630,14 @@ static int32_t ess_run_groups(asm_ctx* ctx, EssGroup* groups, int n_groups, int3
                 g.bounds[g.stage], g.bounds[g.stage + 1], cnt, g.n_open);
       const int next = g.stage + 1;
       if (next < g.n_stage && cnt > 0 && g.bounds[next] < L) {
-        g.ids_in = sc.ids[g.stage & 1] + g.t0;
+        g.ids_in = sc.ids(g.slot, g.stage & 1) + g.t0;
         g.n_open = cnt;
         g.stage = next;
         if ((rc = launch(gi)) != ASM_OK) return rc;
       } else {
         g.done = true;
         remaining--;
+        if (g.subset) continue;  // the two halves of a range: the caller copies the range out once both are done
         if (act_out_host)
           ASM_CUDA(ctx, cudaMemcpyAsync(act_out_host + g.t0, sc.act + g.t0, sizeof(double) * (size_t)g.nt,
                                         cudaMemcpyDeviceToHost, g.st));
@@ -601,26 +652,95 @@ static int32_t ess_run_groups(asm_ctx* ctx, EssGroup* groups, int n_groups, int3
   return ASM_OK;
 }
 
+static void ess_env_bounds(const char* name, EssGroup& g) {  // tuning aid: "0,128,256,...,2048"
+  const char* env = getenv(name);
+  if (!env) return;
+  int k = 0;
+  for (const char* q = env; q && *q && k < 10; k++) {
+    g.bounds[k] = atoi(q);
+    q = strchr(q, ',');
+    if (q) q++;
+  }
+  if (k >= 2 && g.bounds[0] == 0 && g.bounds[k - 1] == 2048) g.n_stage = k - 1;
+}
+
+// CTAs of the first stage of a group of `n_open` traces whose plan starts with `lags` lags (shape as ess_pick_shape
+// would choose it on an empty GPU)
+static int ess_first_stage_ctas(const asm_ctx* ctx, int n_open, int lags) {
+  if (n_open <= 0) return 0;
+  int e = lags;
+  const EssShape sh = ess_pick_shape(ctx, n_open, 0, &e, 0, false, false);
+  return ((n_open + sh.groups - 1) / sh.groups) * sh.blocks_y;
+}
+
 int32_t ess_batch_device(asm_ctx* ctx, int32_t n_traces, int64_t n_samples, int64_t stride, const double* d_traces,
                          int32_t max_lag, double* act_out_host, double* ess_out_host) {
-  EssGroup g;
-  g.t0 = 0;
-  g.nt = n_traces;
-  g.st = ctx->stream;
-  g.st2 = ctx->stream2;
-  g.fork = ctx->ev_fork;
-  g.join = ctx->ev_join;
-  if (ctx->ess_adaptive) g.plan({0, 128, 256, 768, 1792, 2048});
-  if (const char* env = getenv("ASM_ESS_BOUNDS")) {  // tuning aid: "0,128,256,...,2048"
-    int k = 0;
-    for (const char* q = env; q && *q && k < 10; k++) {
-      g.bounds[k] = atoi(q);
-      q = strchr(q, ',');
-      if (q) q++;
-    }
-    if (k >= 2 && g.bounds[0] == 0 && g.bounds[k - 1] == 2048) g.n_stage = k - 1;
+  EssGroup g[2];
+  g[0].t0 = 0;
+  g[0].nt = n_traces;
+  g[0].st = ctx->stream;
+  g[0].st2 = ctx->stream2;
+  g[0].fork = ctx->ev_fork;
+  g[0].join = ctx->ev_join;
+  if (ctx->ess_adaptive) g[0].plan({0, 128, 256, 768, 1792, 2048});
+  ess_env_bounds("ASM_ESS_BOUNDS", g[0]);
+  // Pilot split.  With the staged plan a slowly decaying trace walks through every stage, each of which costs at
+  // least one latency-bound pass of its slowest warp over all samples while most of the GPU idles.  A cheap estimate
+  // of the lag-128 autocorrelation (first 128k samples) picks those traces out beforehand; they form a second group
+  // whose first stage covers [0, 768) at once and runs BESIDE the first stage of the others, so the early stages keep
+  // every sub-partition busy.  A wrong guess only costs time: a "short" trace that is still open after a stage simply
+  // goes on to the next one, a "long" one that stops early has computed lags it did not need.
+  const char* pe = getenv("ASM_ESS_PILOT");
+  const bool pilot = ctx->ess_adaptive && (pe && pe[0] == '1') && n_traces >= 8 && n_samples >= 65536 &&
+                     std::min<int64_t>(n_samples, max_lag) >= 1024 && !getenv("ASM_ESS_BOUNDS");
+  if (!pilot) return ess_run_groups(ctx, g, 1, n_traces, n_samples, stride, d_traces, max_lag, act_out_host, ess_out_host);
+
+  int32_t rc;
+  const int lags_stride = 2048;
+  if ((rc = asm_reserve(ctx, ctx->ess_sls, sizeof(double) * (size_t)n_traces * lags_stride)) != ASM_OK) return rc;
+  EssScratch sc;
+  if ((rc = ess_scratch(ctx, n_traces, sc)) != ASM_OK) return rc;
+  int* ids_short = sc.ids_base + 4 * sc.nd;
+  int* ids_long = sc.ids_base + 5 * sc.nd;
+  int* counts = sc.counter + 16;
+  ASM_CUDA(ctx, cudaMemsetAsync(counts, 0, 2 * sizeof(int), ctx->stream));
+  {
+    LaunchScope ls(ctx, ASM_K_ESS_FINISH);
+    const int P = (int)std::min<int64_t>(n_samples, 131072);
+    const double thr = getenv("ASM_ESS_PILOT_THRESHOLD") ? atof(getenv("ASM_ESS_PILOT_THRESHOLD")) : 0.15;
+    ess_pilot_kernel<<<(n_traces + 7) / 8, 256, 0, ctx->stream>>>(d_traces, stride, n_traces, P, 128, thr, ids_short, ids_long, counts);
   }
-  return ess_run_groups(ctx, &g, 1, n_traces, n_samples, stride, d_traces, max_lag, act_out_host, ess_out_host);
+  ASM_CUDA(ctx, cudaGetLastError());
+  ASM_CUDA(ctx, cudaMemsetAsync(sc.state, 0, sizeof(EssState) * (size_t)n_traces, ctx->stream));  // once, for both halves
+  ASM_CUDA(ctx, cudaMemcpyAsync(sc.h_counter + 16, counts, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  ASM_CUDA(ctx, cudaEventRecord(ctx->group_event[0], ctx->stream));
+  ASM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const int n_short = sc.h_counter[16], n_long = sc.h_counter[17];
+  if (getenv("ASM_ESS_TRACE")) fprintf(stderr, "[ess] pilot: %d short, %d long traces\n", n_short, n_long);
+  g[0].subset = true;
+  g[0].ids0 = ids_short;
+  g[0].n0 = n_short;
+  g[0].slot = 0;
+  g[1] = g[0];
+  g[1].ids0 = ids_long;
+  g[1].n0 = n_long;
+  g[1].slot = 1;
+  g[1].st = ctx->group_stream[0];
+  g[1].st2 = ctx->group_stream2[0];
+  g[1].fork = ctx->group_fork[0];
+  g[1].join = ctx->group_join[0];
+  g[1].ready = ctx->group_event[0];  // the cleared state is in place
+  g[1].plan({0, 768, 1792, 2048});
+  ess_env_bounds("ASM_ESS_LONG_BOUNDS", g[1]);
+  g[0].peer_ctas = ess_first_stage_ctas(ctx, n_long, g[1].bounds[1]);
+  g[1].peer_ctas = ess_first_stage_ctas(ctx, n_short, g[0].bounds[1]);
+  if ((rc = ess_run_groups(ctx, g, 2, n_traces, n_samples, stride, d_traces, max_lag, nullptr, nullptr)) != ASM_OK) return rc;
+  if (act_out_host)
+    ASM_CUDA(ctx, cudaMemcpyAsync(act_out_host, sc.act, sizeof(double) * (size_t)n_traces, cudaMemcpyDeviceToHost, ctx->stream));
+  if (ess_out_host)
+    ASM_CUDA(ctx, cudaMemcpyAsync(ess_out_host, sc.ess, sizeof(double) * (size_t)n_traces, cudaMemcpyDeviceToHost, ctx->stream));
+  ASM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return ASM_OK;
 }
 
 // Host-pointer entry: the traces are uploaded in up to four chunks on the copy stream, each chunk is a group on
