@@ -81,6 +81,7 @@ SIGNATURES = {
     "asm_encoder_destroy": (_i32, [_p]),
     "asm_encoder_add_topologies": (_i32, [_p, _i64, _p, _p, _p, _p]),
     "asm_encoder_add_newick": (_i32, [_p, C.c_char_p, _i32, _p]),
+    "asm_encoder_add_newick_batch": (_i32, [_p, _i64, _p, _i32, _p]),
     "asm_encoder_num_clades": (_i64, [_p]),
     "asm_encoder_clade_leaves": (_i32, [_p, _i64, _p, _i32]),
     "asm_encoder_words": (_i32, [_p]),
@@ -173,6 +174,15 @@ class Encoder:
         rc = lib().asm_encoder_add_newick(self._h, newick.encode(), label_offset, _ptr(ids))
         if rc != ASM_OK:
             raise AsmGpuError(rc, "asm_encoder_add_newick")
+        return ids
+
+    def add_newick_batch(self, newicks: Sequence[str], label_offset: int = 1) -> np.ndarray:
+        n = len(newicks)
+        ids = np.empty((n, self.n_taxa - 1), dtype=np.int32)
+        arr = (C.c_char_p * max(n, 1))(*[s.encode() for s in newicks])
+        rc = lib().asm_encoder_add_newick_batch(self._h, n, arr, label_offset, _ptr(ids))
+        if rc != ASM_OK:
+            raise AsmGpuError(rc, "asm_encoder_add_newick_batch")
         return ids
 
     @property

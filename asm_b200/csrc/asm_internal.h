@@ -114,7 +114,7 @@ struct asm_ctx {
   bool ess_adaptive = true;     // staged lag evaluation (ess.cu)
   long long ess_lag_slots = 0;  // (trace, lag) chains evaluated by the last ESS call
   // resident batch traces (asm_ess_traces_put): [ess_res_n][ess_res_stride] doubles
-  DevBuf ess_res;
+  DevBuf ess_res, ess_park;
   int32_t ess_res_n = 0;
   int64_t ess_res_samples = 0, ess_res_stride = 0;
   // ---- multi-GPU (comm.cu) ------------------------------------------------------------------------------
@@ -129,7 +129,7 @@ struct asm_ctx {
   std::string err;
 };
 
-constexpr uint32_t kAttrPopc = 1, kAttrI8 = 2, kAttrI8Dump = 4, kAttrI8x2 = 8, kAttrEss = 16, kAttrF4x2 = 32;
+constexpr uint32_t kAttrPopc = 1, kAttrI8 = 2, kAttrI8Dump = 4, kAttrI8x2 = 8, kAttrEss = 16, kAttrF4x2 = 32, kAttrEssTicket = 64;
 
 // ---- error plumbing ---------------------------------------------------------------------------------
 int32_t asm_fail(asm_ctx* ctx, int32_t code, const char* fmt, ...);

@@ -303,7 +303,7 @@ int32_t asm_destroy(asm_ctx* ctx) {
     if (t.d_vals) cudaFree(t.d_vals);
   DevBuf* bufs[] = {&ctx->opnd_bits, &ctx->opnd_i8, &ctx->opnd_f4, &ctx->nbits, &ctx->S_pad, &ctx->blk_meta,
                     &ctx->S_compact, &ctx->psrf_rows, &ctx->psrf_mean, &ctx->misc, &ctx->flush, &ctx->ess_tr,
-                    &ctx->ess_sls, &ctx->ess_out, &ctx->tile_counter, &ctx->rf_out, &ctx->walk_dev, &ctx->ess_res, &ctx->f4_blk_dev, &ctx->f4_walk_dev, &ctx->top_word_dev};
+                    &ctx->ess_sls, &ctx->ess_out, &ctx->tile_counter, &ctx->rf_out, &ctx->walk_dev, &ctx->ess_res, &ctx->f4_blk_dev, &ctx->f4_walk_dev, &ctx->top_word_dev, &ctx->ess_park};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   for (auto& ev : ctx->timer)

@@ -220,6 +220,231 @@ __global__ void __launch_bounds__(256) ess_lag_kernel(const double* __restrict__
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// K5t ess_ticket_kernel<R>: the same chains, cut into tickets.
+//
+// ess_lag_kernel gives a group of threads one (trace, lag block) for the whole trace: a launch with 1.7 warps per SM
+// sub-partition takes as long as one with 2, and nothing else can use the slots a short group leaves behind.  Here a
+// JOB is one lag block (gthreads*R lags) of one trace and a TICKET is one segment of `seg_len` samples of a job.
+// Workers (groups of `gthreads` threads of a persistent grid, each with its own shared-memory ring) draw tickets from
+// one atomic counter, segment-major: every segment 0 first, then every segment 1, ...  A chain's additions stay in
+// their Java order because segment k of a job starts from the accumulators segment k-1 parked in global memory (an
+// acquire/release flag per job orders the two; a ticket only ever waits for a lower-numbered one, which a running
+// worker has already drawn, so the wait is short and cannot deadlock whatever else occupies the GPU).  The ring is
+// re-primed per ticket with the `lag_hi + R` samples before the segment (zeros before sample 0).  The jobs of two
+// trace lists with different lag ranges (the "short" and "long" halves of the pilot split) share one launch, so the
+// early stages keep every sub-partition busy and finish together.  Results are bit-identical to ess_lag_kernel's.
+// ---------------------------------------------------------------------------------------------------------------
+struct EssJobSet {
+  const int* ids;  // trace ids (nullptr: 0..n-1)
+  int n;           // traces
+  int lag_begin;
+  int n_blocks;    // lag blocks of gthreads*R lags per trace
+  int first_job;   // jobs [first_job, first_job + n*n_blocks): job j -> trace ids[(j-first_job) % n], lag block (j-first_job) / n
+  int with_sum;    // the job of lag block 0 carries the trace's sequential sum (first stage of its group)
+  int R;           // lags per thread of this set's jobs (the sets of a launch share `gthreads`, not R)
+  size_t park_off; // this set's slice of `park`, in doubles: [n*n_blocks][gthreads*R + 1]
+};
+struct EssTicketParams {
+  const double* traces;
+  long long stride, n;
+  EssJobSet set[2];  // the trace lists of up to two groups (the "short" and "long" halves of the pilot split) share a launch
+  int n_sets, n_jobs;
+  int seg_len, n_seg;  // samples per ticket (a multiple of `chunk`), tickets per job
+  int lags_stride;
+  double* sls;
+  double* sums;
+  double* park;        // accumulators (+ the running sum) between the segments of a job (EssJobSet::park_off)
+  size_t ring_stride;  // bytes between the rings of the workers of a CTA
+  int* progress;       // [n_jobs]: segments completed
+  unsigned long long* ticket_counter;
+  int gthreads, ring_size, chunk;
+};
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// One ticket: segment k of job j of set `js`, R lags per thread.
+template <int R>
+__device__ __forceinline__ void ess_ticket_body(const EssTicketParams& prm, const EssJobSet& js, int k, int j, char* ring, int NT,
+                                                int group, int tid) {
+  const int ring_size = prm.ring_size, chunk = prm.chunk;
+  const long long mask = ring_size - 1;
+  const uint32_t mirror_off = Ring<R>::off((uint32_t)ring_size);
+  const long long n = prm.n;
+  constexpr int kRound = R >= 4 ? R : 8;  // samples per inner-loop step
+  constexpr int SB = kRound;
+  constexpr bool kWinAligned = R >= 2;
+  constexpr uint32_t kStep = Ring<R>::off(SB);
+  const long long nR = (n + 7) / 8 * 8;
+  auto group_sync = [&]() {
+    if (NT == 32)
+      __syncwarp();
+    else
+      asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(NT) : "memory");
+  };
+  const int jj = j - js.first_job;
+  const int blk = jj / js.n;
+  const int ti = jj - blk * js.n;
+  const long long trace = js.ids ? js.ids[ti] : ti;
+  const double* __restrict__ x = prm.traces + trace * prm.stride;
+  const int l0 = js.lag_begin + blk * NT * R + tid * R;
+  const int lag_hi = js.lag_begin + (blk + 1) * NT * R;  // exclusive
+  const bool do_sum = js.with_sum && blk == 0 && tid < 32;
+  const long long i0 = (long long)k * prm.seg_len;
+  const long long i1 = min(nR, i0 + (long long)prm.seg_len);
+
+  auto load_chunk = [&](long long c) {
+    const long long base = c * chunk;
+    const uint32_t e0 = (uint32_t)(base & mask);  // the chunk occupies [e0, e0 + chunk), no wrap
+    const bool mirror = e0 == 0;
+    for (int e = tid; e < chunk; e += NT) {
+      const long long i = base + e;
+      char* dst = ring + Ring<R>::off(e0 + (uint32_t)e);
+      if (i >= 0 && i < n) {
+        cp_async8(dst, x + i);
+        if (mirror) cp_async8(dst + mirror_off, x + i);
+      } else {  // x[i] = 0 before the trace; behind it the padding adds +-0.0, which leaves every accumulator unchanged
+        *reinterpret_cast<double*>(dst) = 0.0;
+        if (mirror) *reinterpret_cast<double*>(dst + mirror_off) = 0.0;
+      }
+    }
+    cp_async_commit();
+  };
+
+  double acc[R];
+  double w[R - 1 + SB];
+  double sum = 0.0;
+  double* park = prm.park + js.park_off + (size_t)jj * ((size_t)NT * R + 1);
+  if (k == 0) {
+#pragma unroll
+    for (int r = 0; r < R; r++) acc[r] = 0.0;
+  } else {
+    if (tid == 0) {
+      uint32_t spins = 0;
+      while (ld_acquire(prm.progress + j) < k) {
+        if (++spins > (1u << 30)) __trap();  // a protocol error fails the launch instead of hanging the GPU
+      }
+    }
+    group_sync();
+#pragma unroll
+    for (int r = 0; r < R; r++) acc[r] = __ldcg(park + tid * R + r);
+    if (do_sum) sum = __ldcg(park + NT * R);
+  }
+
+  auto compute_chunk = [&](long long c, auto with_sum) {
+    const long long i_begin = c * chunk;
+    const int n_blocks = (int)((min(i_begin + (long long)chunk, i1) - i_begin) / SB);
+    uint32_t xo = Ring<R>::off((uint32_t)(i_begin & mask));
+    uint32_t wo = Ring<R>::off((uint32_t)((i_begin - l0) & mask));
+    double xi[SB], wn[SB], xi_n[SB], wn_n[SB];
+    load_block<SB, true>(ring, xo, xi);
+    load_block<SB, kWinAligned>(ring, wo, wn);
+#pragma unroll 2
+    for (int kb = 0; kb < n_blocks; kb++) {
+      xo += kStep;
+      wo += kStep;
+      load_block<SB, true>(ring, xo, xi_n);
+      load_block<SB, kWinAligned>(ring, wo, wn_n);
+#pragma unroll
+      for (int k2 = 0; k2 < SB; k2++) w[R - 1 + k2] = wn[k2];
+#pragma unroll
+      for (int di = 0; di < SB; di++)
+#pragma unroll
+        for (int r = 0; r < R; r++) acc[r] = __dadd_rn(acc[r], __dmul_rn(w[R - 1 + di - r], xi[di]));
+      if constexpr (decltype(with_sum)::value) {
+#pragma unroll
+        for (int di = 0; di < SB; di++) sum = __dadd_rn(sum, xi[di]);
+      }
+#pragma unroll
+      for (int k2 = 0; k2 < R - 1; k2++) w[k2] = w[k2 + SB];
+#pragma unroll
+      for (int k2 = 0; k2 < SB; k2++) {
+        xi[k2] = xi_n[k2];
+        wn[k2] = wn_n[k2];
+      }
+    }
+  };
+
+  // chunks [cb, c0) prime the ring with the window behind the segment, chunks [c0, c1) are computed
+  const long long c0 = i0 / chunk, c1 = (i1 + chunk - 1) / chunk;
+  const long long cb = c0 - (lag_hi + R + 8 + chunk - 1) / chunk;
+  load_chunk(cb);
+  for (long long c = cb; c < c1; c++) {
+    if (c + 1 < c1) {
+      load_chunk(c + 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    group_sync();
+    if (c < c0) continue;
+    if (c == c0) {  // w[k] = x[i0 - l0 - (R-1) + k]: the R-1 window values a running walk would carry into this block
+#pragma unroll
+      for (int k2 = 0; k2 < R - 1; k2++)
+        w[k2] = *reinterpret_cast<const double*>(ring + Ring<R>::off((uint32_t)((i0 - l0 - (R - 1) + k2) & mask)));
+    }
+    if (do_sum)
+      compute_chunk(c, std::true_type{});
+    else
+      compute_chunk(c, std::false_type{});
+  }
+
+  if (k + 1 == prm.n_seg) {
+    if (do_sum && tid == 0) prm.sums[trace] = sum;
+    if (l0 + R <= prm.lags_stride) {
+      double* out = prm.sls + trace * (long long)prm.lags_stride + l0;
+#pragma unroll
+      for (int r = 0; r < R; r++) out[r] = acc[r];
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < R; r++) __stcg(park + tid * R + r, acc[r]);
+    if (do_sum && tid == 0) __stcg(park + NT * R, sum);
+    __threadfence();
+    group_sync();
+    if (tid == 0) st_release(prm.progress + j, k + 1);
+  }
+}
+
+__global__ void __launch_bounds__(128) ess_ticket_kernel(const __grid_constant__ EssTicketParams prm) {
+  extern __shared__ __align__(128) char ring_all[];
+  __shared__ long long ticket_s[4];
+  const int NT = prm.gthreads;
+  const int group = threadIdx.x / NT, tid = threadIdx.x - group * NT;
+  char* ring = ring_all + (size_t)group * prm.ring_stride;
+  const long long total = (long long)prm.n_jobs * prm.n_seg;
+  for (;;) {
+    // every thread is done with the previous ticket's ring and has read ticket_s
+    if (NT == 32)
+      __syncwarp();
+    else
+      asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(NT) : "memory");
+    if (tid == 0) ticket_s[group] = (long long)atomicAdd(prm.ticket_counter, 1ULL);
+    if (NT == 32)
+      __syncwarp();
+    else
+      asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(NT) : "memory");
+    const long long t = ticket_s[group];
+    if (t >= total) break;
+    const int k = (int)(t / prm.n_jobs), j = (int)(t - (long long)k * prm.n_jobs);
+    const EssJobSet& js = prm.set[(prm.n_sets > 1 && j >= prm.set[1].first_job) ? 1 : 0];
+    switch (js.R) {  // the same for every thread of the worker
+      case 8: ess_ticket_body<8>(prm, js, k, j, ring, NT, group, tid); break;
+      case 4: ess_ticket_body<4>(prm, js, k, j, ring, NT, group, tid); break;
+      case 2: ess_ticket_body<2>(prm, js, k, j, ring, NT, group, tid); break;
+      default: ess_ticket_body<1>(prm, js, k, j, ring, NT, group, tid); break;
+    }
+  }
+}
+
 // per-trace state of the integral loop carried from stage to stage
 struct EssState {
   double integral, prev, sum1, sum2, ac0;
@@ -329,25 +554,31 @@ __global__ void __launch_bounds__(256) concat_kernel(const __grid_constant__ Con
 __global__ void __launch_bounds__(256) ess_pilot_kernel(const double* __restrict__ traces, long long stride, int n_traces,
                                                          int P, int lag, double threshold, int* __restrict__ ids_short,
                                                          int* __restrict__ ids_long, int* __restrict__ counts) {
-  const int lane = threadIdx.x & 31;
-  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (t >= n_traces) return;
+  __shared__ double red[3][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int t = blockIdx.x;
   const double* __restrict__ x = traces + (long long)t * stride;
+  auto block_sum = [&](double v, int slot) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[slot][warp] = v;
+    __syncthreads();
+    double r = 0.0;
+    for (int k = 0; k < 8; k++) r += red[slot][k];
+    __syncthreads();
+    return r;
+  };
   double m = 0.0;
-  for (int i = lane; i < P; i += 32) m += x[i];
-  for (int o = 16; o > 0; o >>= 1) m += __shfl_xor_sync(0xffffffffu, m, o);
-  m /= (double)P;
+  for (int i = threadIdx.x; i < P; i += 256) m += x[i];
+  m = block_sum(m, 0) / (double)P;
   double v = 0.0, c = 0.0;
-  for (int i = lane; i < P; i += 32) {
+  for (int i = threadIdx.x; i < P; i += 256) {
     const double d = x[i] - m;
     v += d * d;
     if (i + lag < P) c += d * (x[i + lag] - m);
   }
-  for (int o = 16; o > 0; o >>= 1) {
-    v += __shfl_xor_sync(0xffffffffu, v, o);
-    c += __shfl_xor_sync(0xffffffffu, c, o);
-  }
-  if (lane == 0) {
+  v = block_sum(v, 1);
+  c = block_sum(c, 2);
+  if (threadIdx.x == 0) {
     const bool is_long = v > 0.0 && c > threshold * v;
     if (is_long)
       ids_long[atomicAdd(&counts[1], 1)] = t;
@@ -664,13 +895,224 @@ static void ess_env_bounds(const char* name, EssGroup& g) {  // tuning aid: "0,1
   if (k >= 2 && g.bounds[0] == 0 && g.bounds[k - 1] == 2048) g.n_stage = k - 1;
 }
 
-// CTAs of the first stage of a group of `n_open` traces whose plan starts with `lags` lags (shape as ess_pick_shape
-// would choose it on an empty GPU)
-static int ess_first_stage_ctas(const asm_ctx* ctx, int n_open, int lags) {
-  if (n_open <= 0) return 0;
-  int e = lags;
-  const EssShape sh = ess_pick_shape(ctx, n_open, 0, &e, 0, false, false);
-  return ((n_open + sh.groups - 1) / sh.groups) * sh.blocks_y;
+// ---- ticket rounds (resident path) ------------------------------------------------------------------------------
+// One ROUND = one ess_ticket_kernel launch that covers the current stage of every group still open (at most two: the
+// "short" and "long" halves of the pilot split, or one group), then one ess_scan_kernel per group, then one host
+// synchronisation for the open counts.
+
+// dynamic shared memory a ticket CTA may ask for: the opt-in maximum less the kernel's static ticket slots
+static int ess_ticket_smem(const asm_ctx* ctx) { return ctx->smem_optin - 1024; }
+
+struct EssTicketShape {
+  int R[2] = {0, 0}, gthreads = 0, chunk = 0, ring = 0, n_ctas = 0;
+  size_t ring_bytes = 0;
+  double model_ms = 0;
+};
+
+static size_t ess_ring_bytes(int R, int max_lag_end, int* ring_out, int* chunk_out) {
+  int chunk = kChunkMax;
+  auto ring_for = [&](int ck) {
+    int ring = 1024;
+    while (ring < max_lag_end + 2 * R + 16 + 3 * ck) ring *= 2;
+    return ring;
+  };
+  int ring = ring_for(kChunkMax);
+  if (ring_for(kChunkMax / 2) < ring) chunk = kChunkMax / 2, ring = ring_for(kChunkMax / 2);
+  *ring_out = ring;
+  *chunk_out = chunk;
+  switch (R) {
+    case 8: return Ring<8>::bytes((uint32_t)ring, (uint32_t)chunk);
+    case 4: return Ring<4>::bytes((uint32_t)ring, (uint32_t)chunk);
+    case 2: return Ring<2>::bytes((uint32_t)ring, (uint32_t)chunk);
+    default: return Ring<1>::bytes((uint32_t)ring, (uint32_t)chunk);
+  }
+}
+
+// Shape of one round: workers of `gthreads` threads, R[a] lags per thread for the jobs of set a, `n_ctas` CTAs of four
+// warps (one per sub-partition).  A chain is sequential, so at most one worker per job is busy at any time: the grid is
+// never larger than the number of jobs, and it is a whole number of CTAs per SM so that every sub-partition carries the
+// same number of busy warps.  Model (milliseconds per million samples): the FP64 issue time of the round over all
+// sub-partitions at the efficiency each R reaches (ncu, profiles/; less with a single warp per sub-partition, which
+// cannot hide the latency of its own dependent adds), but never less than one job's own walk (2R FP64 instructions per
+// sample at one per 2.07 clocks, or the 8.4-clock latency of its adds).
+static EssTicketShape ess_ticket_shape(const asm_ctx* ctx, const int* n_open, const int* width, int n_sets, int max_lag_end) {
+  static const int kR[4] = {8, 4, 2, 1};
+  static const double kEff[4] = {0.90, 0.76, 0.68, 0.62};
+  EssTicketShape best;
+  int forced_R = 0, forced_g = 0;
+  if (const char* env = getenv("ASM_ESS_TICKET_R")) forced_R = atoi(env);
+  if (const char* env = getenv("ASM_ESS_TICKET_G")) forced_g = atoi(env);
+  const double clk_ghz = 1.9;
+  const bool mixed = getenv("ASM_ESS_TICKET_MIXED") != nullptr;
+  for (int g = 128; g >= 32; g /= 2) {
+    if (forced_g && g != forced_g) continue;
+    for (int k0 = 0; k0 < 4; k0++)
+      for (int k1 = 0; k1 < (n_sets > 1 ? 4 : 1); k1++) {
+        const int ks[2] = {k0, k1};
+        // Measured (cfg3, profiles/r02_ess_ticket_rounds.md): with one ring per warp a round that mixes 8 and 4 lags per
+        // thread is slower than the same round at 4 throughout, so both sets take the same R unless asked otherwise.
+        if (n_sets > 1 && k1 != k0 && !mixed) continue;
+        bool ok = true;
+        long long jobs = 0;
+        double issue = 0, chain = 0;
+        size_t ring_bytes = 0;
+        EssTicketShape sh;
+        sh.gthreads = g;
+        for (int a = 0; a < n_sets && ok; a++) {
+          const int R = kR[ks[a]];
+          if (forced_R && R != forced_R) ok = false;
+          if (width[a] % (g * R) != 0) ok = false;
+          if (!ok) break;
+          sh.R[a] = R;
+          jobs += (long long)n_open[a] * (width[a] / (g * R));
+          issue += (double)n_open[a] * width[a] * 2.0 / 32.0 * 2.07 / kEff[ks[a]];
+          chain = std::max(chain, std::max(2.0 * R * 2.07, 8.4));
+          int ring, chunk;
+          ring_bytes = std::max(ring_bytes, ess_ring_bytes(R, max_lag_end, &ring, &chunk));
+          sh.ring = ring;  // the same for every R: it depends on max_lag_end (+ 2R)
+          sh.chunk = chunk;
+        }
+        if (!ok || jobs == 0) continue;
+        sh.ring_bytes = ring_bytes;
+        const int groups = 128 / g;
+        const int fit = (int)std::min<size_t>(8, (size_t)ess_ticket_smem(ctx) / (groups * ring_bytes + 1024));
+        if (fit < 1) continue;
+        long long ctas = std::min<long long>((long long)ctx->sm_count * fit, (jobs + groups - 1) / groups);
+        if (ctas > ctx->sm_count) ctas -= ctas % ctx->sm_count;
+        sh.n_ctas = (int)ctas;
+        const double wps = (double)ctas / ctx->sm_count;  // busy warps per sub-partition: every worker always has a job
+        const double hide = wps >= 2 ? 1.0 : (wps >= 1 ? 0.85 : 0.85 * wps);
+        sh.model_ms = std::max(issue / (4.0 * ctx->sm_count) / hide, chain) / clk_ghz;
+        if (best.gthreads == 0 || sh.model_ms < best.model_ms - 1e-9) best = sh;
+      }
+  }
+  return best;
+}
+
+static void ess_ticket_launch(asm_ctx* ctx, const EssTicketParams& prm, const EssTicketShape& sh, cudaStream_t st) {
+  const int groups = 128 / sh.gthreads;
+  // spread a grid of fewer CTAs than fit over the SMs instead of stacking it: ask for just too much shared memory for
+  // one more CTA per SM than an even spread needs
+  const int per_sm = (sh.n_ctas + ctx->sm_count - 1) / ctx->sm_count;
+  const size_t smem = std::max<size_t>(groups * sh.ring_bytes,
+                                       std::min<size_t>((size_t)ess_ticket_smem(ctx), (size_t)ess_ticket_smem(ctx) / (per_sm + 1) + 1024));
+  LaunchScope ls(ctx, ASM_K_ESS_LAG, st);
+  ess_ticket_kernel<<<(unsigned)sh.n_ctas, 128, smem, st>>>(prm);
+}
+
+static int32_t ess_run_rounds(asm_ctx* ctx, EssGroup* groups, int n_groups, int32_t n_traces, int64_t n_samples,
+                              int64_t stride, const double* d_traces, int32_t max_lag, const EssScratch& sc) {
+  const long long L = std::min<long long>(n_samples, max_lag);
+  const int lags_stride = 2048;
+  cudaStream_t st = ctx->stream;
+  int32_t rc;
+  if (!(ctx->func_attr_done & kAttrEssTicket)) {
+    ASM_CUDA(ctx, cudaFuncSetAttribute(ess_ticket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ess_ticket_smem(ctx)));
+    ctx->func_attr_done |= kAttrEssTicket;
+  }
+  ctx->ess_lag_slots = 0;
+  for (int gi = 0; gi < n_groups; gi++) {
+    EssGroup& g = groups[gi];
+    g.stage = 0;
+    if (g.slot < 0) g.slot = gi;
+    g.n_open = g.subset ? g.n0 : g.nt;
+    g.ids_in = g.subset ? g.ids0 : nullptr;
+    g.done = g.n_open == 0;
+  }
+  const bool trace_on = getenv("ASM_ESS_TRACE") != nullptr;
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto now_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
+  const int seg_len = 65536;
+  const long long nR = (n_samples + 7) / 8 * 8;
+  const int n_seg = (int)std::max<long long>(1, (nR + seg_len - 1) / seg_len);
+  for (int round = 0;; round++) {
+    int act[2], n_act = 0, n_open[2], width[2], max_lag_end = 0;
+    for (int gi = 0; gi < n_groups; gi++)
+      if (!groups[gi].done) {
+        const EssGroup& g = groups[gi];
+        n_open[n_act] = g.n_open;
+        width[n_act] = g.bounds[g.stage + 1] - g.bounds[g.stage];
+        max_lag_end = std::max(max_lag_end, g.bounds[g.stage + 1]);
+        act[n_act++] = gi;
+      }
+    if (n_act == 0) break;
+    const EssTicketShape sh = ess_ticket_shape(ctx, n_open, width, n_act, max_lag_end);
+    if (sh.gthreads == 0) return asm_fail(ctx, ASM_E_UNSUPPORTED, "ess: no thread shape tiles the stages of this round");
+    EssTicketParams prm{};
+    prm.traces = d_traces;
+    prm.stride = stride;
+    prm.n = n_samples;
+    prm.seg_len = seg_len;
+    prm.n_seg = n_seg;
+    prm.lags_stride = lags_stride;
+    prm.sls = sc.sls;
+    prm.sums = sc.sums;
+    prm.gthreads = sh.gthreads;
+    prm.ring_size = sh.ring;
+    prm.chunk = sh.chunk;
+    prm.ring_stride = sh.ring_bytes;
+    int first = 0;
+    size_t park_doubles = 0;
+    for (int a = 0; a < n_act; a++) {
+      const EssGroup& g = groups[act[a]];
+      EssJobSet& js = prm.set[a];
+      js.ids = g.ids_in;
+      js.n = g.n_open;
+      js.lag_begin = g.bounds[g.stage];
+      js.R = sh.R[a];
+      js.n_blocks = width[a] / (sh.gthreads * js.R);
+      js.first_job = first;
+      js.with_sum = g.stage == 0 ? 1 : 0;
+      js.park_off = park_doubles;
+      park_doubles += (size_t)js.n * js.n_blocks * ((size_t)sh.gthreads * js.R + 1);
+      first += js.n * js.n_blocks;
+      ctx->ess_lag_slots += (long long)g.n_open * width[a];
+    }
+    prm.n_sets = n_act;
+    prm.n_jobs = first;
+    if (n_samples > 0 && prm.n_jobs > 0) {
+      if ((rc = asm_reserve(ctx, ctx->ess_park, sizeof(double) * park_doubles + sizeof(int) * (size_t)prm.n_jobs + 64)) != ASM_OK) return rc;
+      prm.park = (double*)ctx->ess_park.p;
+      prm.progress = (int*)(prm.park + park_doubles);
+      prm.ticket_counter = (unsigned long long*)(((uintptr_t)(prm.progress + prm.n_jobs) + 15) & ~(uintptr_t)15);
+      ASM_CUDA(ctx, cudaMemsetAsync(prm.progress, 0, sizeof(int) * (size_t)prm.n_jobs + 48, st));
+      ess_ticket_launch(ctx, prm, sh, st);
+      ASM_CUDA(ctx, cudaGetLastError());
+    }
+    for (int a = 0; a < n_act; a++) {
+      const int gi = act[a];
+      EssGroup& g = groups[gi];
+      ASM_CUDA(ctx, cudaMemsetAsync(sc.counter + gi, 0, sizeof(int), st));
+      {
+        LaunchScope ls(ctx, ASM_K_ESS_FINISH, st);
+        ess_scan_kernel<<<(g.n_open + 127) / 128, 128, 0, st>>>(d_traces, stride, n_samples, g.n_open, g.ids_in, max_lag,
+                                                               g.bounds[g.stage + 1], lags_stride, sc.sls, sc.sums, sc.state,
+                                                               sc.act, sc.ess, sc.used, sc.ids(g.slot, g.stage & 1),
+                                                               sc.counter + gi);
+      }
+      ASM_CUDA(ctx, cudaGetLastError());
+      ASM_CUDA(ctx, cudaMemcpyAsync(sc.h_counter + gi, sc.counter + gi, sizeof(int), cudaMemcpyDeviceToHost, st));
+    }
+    ASM_CUDA(ctx, cudaStreamSynchronize(st));
+    for (int a = 0; a < n_act; a++) {
+      const int gi = act[a];
+      EssGroup& g = groups[gi];
+      const int cnt = sc.h_counter[gi];
+      if (trace_on)
+        fprintf(stderr, "[ess %8.2f ms] round %d (R = %d x %d threads, %d CTAs, model %.1f): group %d stage %d [%d,%d) done, %d of %d traces still open\n",
+                now_ms(), round, sh.R[a], sh.gthreads, sh.n_ctas, sh.model_ms, gi, g.stage, g.bounds[g.stage], g.bounds[g.stage + 1], cnt,
+                g.n_open);
+      const int next = g.stage + 1;
+      if (next < g.n_stage && cnt > 0 && g.bounds[next] < L) {
+        g.ids_in = sc.ids(g.slot, g.stage & 1);
+        g.n_open = cnt;
+        g.stage = next;
+      } else {
+        g.done = true;
+      }
+    }
+  }
+  return ASM_OK;
 }
 
 int32_t ess_batch_device(asm_ctx* ctx, int32_t n_traces, int64_t n_samples, int64_t stride, const double* d_traces,
@@ -684,57 +1126,62 @@ int32_t ess_batch_device(asm_ctx* ctx, int32_t n_traces, int64_t n_samples, int6
   g[0].join = ctx->ev_join;
   if (ctx->ess_adaptive) g[0].plan({0, 128, 256, 768, 1792, 2048});
   ess_env_bounds("ASM_ESS_BOUNDS", g[0]);
-  // Pilot split.  With the staged plan a slowly decaying trace walks through every stage, each of which costs at
-  // least one latency-bound pass of its slowest warp over all samples while most of the GPU idles.  A cheap estimate
-  // of the lag-128 autocorrelation (first 128k samples) picks those traces out beforehand; they form a second group
-  // whose first stage covers [0, 768) at once and runs BESIDE the first stage of the others, so the early stages keep
-  // every sub-partition busy.  A wrong guess only costs time: a "short" trace that is still open after a stage simply
-  // goes on to the next one, a "long" one that stops early has computed lags it did not need.
+  // Resident path: pilot split + ticket rounds (ess_run_rounds).  ASM_ESS_TICKETS=0 / ASM_ESS_PILOT=0 fall back to one
+  // whole-trace warp group per lag block (ess_lag_kernel, the kernels the host-pointer entry overlaps with its upload).
+  // The pilot split is what the rounds are for; without it (staging switched off, short traces, few traces, tuning
+  // knobs) the whole-trace kernels run as before.
+  const char* te = getenv("ASM_ESS_TICKETS");
   const char* pe = getenv("ASM_ESS_PILOT");
-  const bool pilot = ctx->ess_adaptive && (pe && pe[0] == '1') && n_traces >= 8 && n_samples >= 65536 &&
+  const bool pilot = ctx->ess_adaptive && !(te && te[0] == '0') && !(pe && pe[0] == '0') && n_traces >= 8 && n_samples >= 65536 &&
                      std::min<int64_t>(n_samples, max_lag) >= 1024 && !getenv("ASM_ESS_BOUNDS");
   if (!pilot) return ess_run_groups(ctx, g, 1, n_traces, n_samples, stride, d_traces, max_lag, act_out_host, ess_out_host);
-
   int32_t rc;
   const int lags_stride = 2048;
   if ((rc = asm_reserve(ctx, ctx->ess_sls, sizeof(double) * (size_t)n_traces * lags_stride)) != ASM_OK) return rc;
   EssScratch sc;
   if ((rc = ess_scratch(ctx, n_traces, sc)) != ASM_OK) return rc;
-  int* ids_short = sc.ids_base + 4 * sc.nd;
-  int* ids_long = sc.ids_base + 5 * sc.nd;
-  int* counts = sc.counter + 16;
-  ASM_CUDA(ctx, cudaMemsetAsync(counts, 0, 2 * sizeof(int), ctx->stream));
+  int n_groups = 1;
+  // Pilot split.  With the staged plan a slowly decaying trace walks through every stage, and each thin stage costs at
+  // least one latency-bound walk of a chain over all samples while most of the GPU idles.  A cheap estimate of the
+  // lag-128 autocorrelation (first 128k samples) picks those traces out beforehand; they form a second group whose
+  // first stage covers [0, 768) at once, in the SAME launch as the first stage of the others.  A wrong guess only costs
+  // time: a "short" trace that is still open after a stage simply goes on to the next one, a "long" one that stops
+  // early has computed lags it did not need.  Results do not depend on the split.
   {
-    LaunchScope ls(ctx, ASM_K_ESS_FINISH);
-    const int P = (int)std::min<int64_t>(n_samples, 131072);
-    const double thr = getenv("ASM_ESS_PILOT_THRESHOLD") ? atof(getenv("ASM_ESS_PILOT_THRESHOLD")) : 0.15;
-    ess_pilot_kernel<<<(n_traces + 7) / 8, 256, 0, ctx->stream>>>(d_traces, stride, n_traces, P, 128, thr, ids_short, ids_long, counts);
+    int* ids_short = sc.ids_base + 4 * sc.nd;
+    int* ids_long = sc.ids_base + 5 * sc.nd;
+    int* counts = sc.counter + 16;
+    ASM_CUDA(ctx, cudaMemsetAsync(counts, 0, 2 * sizeof(int), ctx->stream));
+    {
+      LaunchScope ls(ctx, ASM_K_ESS_FINISH);
+      const int P = (int)std::min<int64_t>(n_samples, 131072);
+      const double thr = getenv("ASM_ESS_PILOT_THRESHOLD") ? atof(getenv("ASM_ESS_PILOT_THRESHOLD")) : 0.15;
+      ess_pilot_kernel<<<n_traces, 256, 0, ctx->stream>>>(d_traces, stride, n_traces, P, 128, thr, ids_short, ids_long, counts);
+    }
+    ASM_CUDA(ctx, cudaGetLastError());
+    ASM_CUDA(ctx, cudaMemcpyAsync(sc.h_counter + 16, counts, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    ASM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const int n_short = sc.h_counter[16], n_long = sc.h_counter[17];
+    if (getenv("ASM_ESS_TRACE")) fprintf(stderr, "[ess] pilot: %d short, %d long traces\n", n_short, n_long);
+    g[0].subset = true;
+    g[0].ids0 = ids_short;
+    g[0].n0 = n_short;
+    g[0].slot = 0;
+    g[1] = g[0];
+    g[1].ids0 = ids_long;
+    g[1].n0 = n_long;
+    g[1].slot = 1;
+    if (n_long == 0) {  // nothing to split off: the staged plan with the whole-trace kernels, over the whole range
+      g[0].subset = false;
+      g[0].ids0 = nullptr;
+      return ess_run_groups(ctx, g, 1, n_traces, n_samples, stride, d_traces, max_lag, act_out_host, ess_out_host);
+    }
+    g[1].plan({0, 768, 2048});
+    ess_env_bounds("ASM_ESS_LONG_BOUNDS", g[1]);
+    n_groups = 2;
   }
-  ASM_CUDA(ctx, cudaGetLastError());
-  ASM_CUDA(ctx, cudaMemsetAsync(sc.state, 0, sizeof(EssState) * (size_t)n_traces, ctx->stream));  // once, for both halves
-  ASM_CUDA(ctx, cudaMemcpyAsync(sc.h_counter + 16, counts, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  ASM_CUDA(ctx, cudaEventRecord(ctx->group_event[0], ctx->stream));
-  ASM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  const int n_short = sc.h_counter[16], n_long = sc.h_counter[17];
-  if (getenv("ASM_ESS_TRACE")) fprintf(stderr, "[ess] pilot: %d short, %d long traces\n", n_short, n_long);
-  g[0].subset = true;
-  g[0].ids0 = ids_short;
-  g[0].n0 = n_short;
-  g[0].slot = 0;
-  g[1] = g[0];
-  g[1].ids0 = ids_long;
-  g[1].n0 = n_long;
-  g[1].slot = 1;
-  g[1].st = ctx->group_stream[0];
-  g[1].st2 = ctx->group_stream2[0];
-  g[1].fork = ctx->group_fork[0];
-  g[1].join = ctx->group_join[0];
-  g[1].ready = ctx->group_event[0];  // the cleared state is in place
-  g[1].plan({0, 768, 1792, 2048});
-  ess_env_bounds("ASM_ESS_LONG_BOUNDS", g[1]);
-  g[0].peer_ctas = ess_first_stage_ctas(ctx, n_long, g[1].bounds[1]);
-  g[1].peer_ctas = ess_first_stage_ctas(ctx, n_short, g[0].bounds[1]);
-  if ((rc = ess_run_groups(ctx, g, 2, n_traces, n_samples, stride, d_traces, max_lag, nullptr, nullptr)) != ASM_OK) return rc;
+  ASM_CUDA(ctx, cudaMemsetAsync(sc.state, 0, sizeof(EssState) * (size_t)n_traces, ctx->stream));
+  if ((rc = ess_run_rounds(ctx, g, n_groups, n_traces, n_samples, stride, d_traces, max_lag, sc)) != ASM_OK) return rc;
   if (act_out_host)
     ASM_CUDA(ctx, cudaMemcpyAsync(act_out_host, sc.act, sizeof(double) * (size_t)n_traces, cudaMemcpyDeviceToHost, ctx->stream));
   if (ess_out_host)

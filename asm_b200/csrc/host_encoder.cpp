@@ -6,12 +6,14 @@
 // clade is keyed by a 128-bit Zobrist hash (XOR of per-leaf random words) and every dictionary
 // hit is confirmed against the stored leaf list, so the mapping is exact, not probabilistic.
 #include <algorithm>
+#include <atomic>
 #include <cctype>
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -19,7 +21,11 @@
 
 // Post-order walk (left subtree, right subtree, node) without recursion limits: emits one clade id
 // per internal node.  Returns false if the arrays do not describe a binary tree on n_taxa leaves.
-bool asm_encode_tree(asm_encoder* enc, const int32_t* left, const int32_t* right, int32_t root, int32_t* ids_out) {
+// `resolve(key, leaf set, position in the post-order) -> id` names a clade: the serial path inserts into the dictionary,
+// the parallel path looks it up read-only and records a miss.
+template <class Resolve>
+static bool encode_tree_with(const asm_encoder* enc, const int32_t* left, const int32_t* right, int32_t root, int32_t* ids_out,
+                             Resolve&& resolve) {
   const int n = enc->n_taxa, nn = 2 * n - 1, W = enc->set_words;
   if (root < 0 || root >= nn) return false;
   struct Frame {
@@ -82,13 +88,99 @@ bool asm_encode_tree(asm_encoder* enc, const int32_t* left, const int32_t* right
     sets.resize(sets.size() - (size_t)W);
     const Key128 k{kl.a ^ kr.a, kl.b ^ kr.b};
     if (n_out >= n - 1) return false;
-    ids_out[n_out++] = enc->get_or_add_set(k, sets.data() + (sets.size() - (size_t)W));
+    ids_out[n_out] = resolve(k, sets.data() + (sets.size() - (size_t)W), n_out);
+    n_out++;
     sizes.push_back(nl + nr);
     keys.push_back(k);
     st.pop_back();
   }
   return n_out == n - 1 && sizes.size() == 1 && sizes[0] == n;
 }
+
+bool asm_encode_tree(asm_encoder* enc, const int32_t* left, const int32_t* right, int32_t root, int32_t* ids_out) {
+  return encode_tree_with(enc, left, right, root, ids_out,
+                          [enc](const Key128& k, const uint64_t* set, int) { return enc->get_or_add_set(k, set); });
+}
+
+namespace {
+
+int encoder_threads(int64_t n_trees) {
+  int t = (int)std::thread::hardware_concurrency();
+  if (const char* e = getenv("ASM_ENCODER_THREADS")) t = atoi(e);
+  if (t < 1) t = 1;
+  if (t > 64) t = 64;
+  if (n_trees < 512) t = 1;  // the live runner adds one tree per chain per check
+  return t;
+}
+
+// Two-phase batch encoder.  Phase 1 (parallel over the trees of a batch, dictionary frozen): walk every tree, look each
+// clade up read-only -- the exact look-up of the serial path, key + stored leaf set -- and record the clades that are
+// not in the dictionary yet.  Phase 2 (serial, tree order, post-order inside a tree): insert the recorded clades.  A
+// clade gets the id the serial encoder would have given it: ids of known clades do not change, new ones are numbered
+// in the same first-seen order.  `walk(t, ids_out, resolve)` encodes tree t of the batch.
+template <class Walk>
+int32_t encode_batch(asm_encoder* enc, int64_t n_trees, int32_t* ids_out, int threads, Walk&& walk) {
+  const int64_t k = enc->n_taxa - 1;
+  const int W = enc->set_words;
+  if (threads <= 1) {
+    for (int64_t t = 0; t < n_trees; t++)
+      if (!walk(t, ids_out + t * k, [enc](const Key128& key, const uint64_t* set, int) { return enc->get_or_add_set(key, set); }))
+        return ASM_E_INVALID;
+    return ASM_OK;
+  }
+  constexpr int64_t kBatch = 8192;  // largest batch; the first ones are small (see below)
+  struct PerThread {
+    std::vector<asm_encoder_miss> misses;
+    std::vector<uint64_t> pool;
+  };
+  std::vector<PerThread> per((size_t)threads);
+  std::vector<int32_t> owner((size_t)kBatch), first((size_t)kBatch), count((size_t)kBatch);
+  // Batches grow geometrically: the first trees of a run meet an empty dictionary, so nearly all of their clades are
+  // misses and go through the serial phase; a short first batch warms the dictionary up for the next, longer one.
+  int64_t batch = 8 * threads;
+  for (int64_t b0 = 0, nb = 0; b0 < n_trees; b0 += nb, batch = std::min(kBatch, batch * 2)) {
+    nb = std::min(batch, n_trees - b0);
+    std::atomic<int64_t> next{0};
+    std::atomic<int> bad{0};
+    for (auto& p : per) {
+      p.misses.clear();
+      p.pool.clear();
+    }
+    auto work = [&](int tid) {
+      PerThread& me = per[(size_t)tid];
+      for (;;) {
+        const int64_t i = next.fetch_add(1, std::memory_order_relaxed);
+        if (i >= nb || bad.load(std::memory_order_relaxed)) break;
+        owner[(size_t)i] = tid;
+        first[(size_t)i] = (int32_t)me.misses.size();
+        const bool ok = walk(b0 + i, ids_out + (b0 + i) * k, [&](const Key128& key, const uint64_t* set, int pos) {
+          const int32_t id = enc->find_set(key, set);
+          if (id >= 0) return id;
+          me.misses.push_back(asm_encoder_miss{pos, key, me.pool.size()});
+          me.pool.insert(me.pool.end(), set, set + W);
+          return (int32_t)-1;
+        });
+        count[(size_t)i] = (int32_t)me.misses.size() - first[(size_t)i];
+        if (!ok) bad.store(1, std::memory_order_relaxed);
+      }
+    };
+    std::vector<std::thread> pool;
+    for (int tid = 1; tid < threads; tid++) pool.emplace_back(work, tid);
+    work(0);
+    for (auto& th : pool) th.join();
+    if (bad.load()) return ASM_E_INVALID;
+    for (int64_t i = 0; i < nb; i++) {  // phase 2: first-seen order
+      const PerThread& o = per[(size_t)owner[(size_t)i]];
+      for (int32_t m = 0; m < count[(size_t)i]; m++) {
+        const asm_encoder_miss& ms = o.misses[(size_t)(first[(size_t)i] + m)];
+        ids_out[(b0 + i) * k + ms.pos] = enc->get_or_add_set(ms.key, o.pool.data() + ms.set_off);
+      }
+    }
+  }
+  return ASM_OK;
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -116,19 +208,25 @@ int32_t asm_encoder_destroy(asm_encoder* enc) {
 int32_t asm_encoder_add_topologies(asm_encoder* enc, int64_t n_trees, const int32_t* left, const int32_t* right,
                                    const int32_t* root, int32_t* clade_ids_out) {
   if (!enc || n_trees < 0 || !left || !right || !root || !clade_ids_out) return ASM_E_INVALID;
-  const int64_t nn = 2 * (int64_t)enc->n_taxa - 1, k = enc->n_taxa - 1;
-  for (int64_t t = 0; t < n_trees; t++)
-    if (!asm_encode_tree(enc, left + t * nn, right + t * nn, root[t], clade_ids_out + t * k)) return ASM_E_INVALID;
-  return ASM_OK;
+  const int64_t nn = 2 * (int64_t)enc->n_taxa - 1;
+  return encode_batch(enc, n_trees, clade_ids_out, encoder_threads(n_trees), [&](int64_t t, int32_t* out, auto&& resolve) {
+    return encode_tree_with(enc, left + t * nn, right + t * nn, root[t], out, resolve);
+  });
 }
 
-// Minimal Newick reader for BEAST tree logs: "(...)label:length[&meta]...;" with integer leaf labels.
-int32_t asm_encoder_add_newick(asm_encoder* enc, const char* s, int32_t label_offset, int32_t* clade_ids_out) {
-  if (!enc || !s || !clade_ids_out) return ASM_E_INVALID;
-  const int n = enc->n_taxa, nn = 2 * n - 1;
-  std::vector<int32_t> left((size_t)nn, -1), right((size_t)nn, -1);
-  std::vector<int32_t> stack;          // completed subtree roots
-  std::vector<int32_t> open_marks;     // stack depth at each '('
+}  // extern "C"
+
+// Minimal Newick reader for BEAST tree logs: "(...)label:length[&meta]...;" with integer leaf labels.  Fills the child
+// arrays (left/right: 2n-1 entries, -1 for leaves) and the root; ASM_OK or the error the caller reports.
+static int32_t parse_newick(int n, const char* s, int32_t label_offset, std::vector<int32_t>& left, std::vector<int32_t>& right,
+                            int32_t* root_out) {
+  const int nn = 2 * n - 1;
+  left.assign((size_t)nn, -1);
+  right.assign((size_t)nn, -1);
+  static thread_local std::vector<int32_t> stack;          // completed subtree roots
+  static thread_local std::vector<int32_t> open_marks;     // stack depth at each '('
+  stack.clear();
+  open_marks.clear();
   int next_internal = n;
   const char* p = s;
   auto skip_meta = [&]() {
@@ -150,7 +248,8 @@ int32_t asm_encoder_add_newick(asm_encoder* enc, const char* s, int32_t label_of
       }
     }
   };
-  std::vector<uint8_t> seen((size_t)n, 0);
+  static thread_local std::vector<uint8_t> seen;
+  seen.assign((size_t)n, 0);
   while (*p && *p != ';') {
     skip_meta();
     if (*p == '(') {
@@ -188,8 +287,39 @@ int32_t asm_encoder_add_newick(asm_encoder* enc, const char* s, int32_t label_of
     }
   }
   if (stack.size() != 1 || next_internal != nn) return ASM_E_INVALID;
-  int32_t root = stack[0];
+  *root_out = stack[0];
+  return ASM_OK;
+}
+
+extern "C" {
+
+int32_t asm_encoder_add_newick(asm_encoder* enc, const char* s, int32_t label_offset, int32_t* clade_ids_out) {
+  if (!enc || !s || !clade_ids_out) return ASM_E_INVALID;
+  std::vector<int32_t> left, right;
+  int32_t root = -1;
+  const int32_t rc = parse_newick(enc->n_taxa, s, label_offset, left, right, &root);
+  if (rc != ASM_OK) return rc;
   return asm_encode_tree(enc, left.data(), right.data(), root, clade_ids_out) ? ASM_OK : ASM_E_INVALID;
+}
+
+// n_trees Newick strings at once (an offline caller that has read whole .trees files, TreeConvergenceCheck.java:94-112):
+// parsing and the clade walks run on every host core, the dictionary ids are those the one-by-one calls would give.
+int32_t asm_encoder_add_newick_batch(asm_encoder* enc, int64_t n_trees, const char* const* newicks, int32_t label_offset,
+                                     int32_t* clade_ids_out) {
+  if (!enc || n_trees < 0 || (n_trees > 0 && (!newicks || !clade_ids_out))) return ASM_E_INVALID;
+  std::atomic<int32_t> first_err{ASM_OK};
+  const int32_t rc = encode_batch(enc, n_trees, clade_ids_out, encoder_threads(n_trees), [&](int64_t t, int32_t* out, auto&& resolve) {
+    static thread_local std::vector<int32_t> left, right;
+    int32_t root = -1;
+    const int32_t prc = newicks[t] ? parse_newick(enc->n_taxa, newicks[t], label_offset, left, right, &root) : ASM_E_INVALID;
+    if (prc != ASM_OK) {
+      int32_t expect = ASM_OK;
+      first_err.compare_exchange_strong(expect, prc);
+      return false;
+    }
+    return encode_tree_with(enc, left.data(), right.data(), root, out, resolve);
+  });
+  return rc == ASM_OK ? ASM_OK : (first_err.load() != ASM_OK ? first_err.load() : rc);
 }
 
 int64_t asm_encoder_num_clades(const asm_encoder* enc) { return enc ? enc->num_clades() : 0; }
@@ -215,16 +345,31 @@ int32_t asm_encoder_words(const asm_encoder* enc) {
 int32_t asm_encode_bits(const int32_t* clade_ids, int64_t n_trees, int32_t ids_per_tree, int32_t words_per_tree,
                         uint64_t* bits_out) {
   if (!clade_ids || !bits_out || n_trees < 0 || ids_per_tree < 0 || words_per_tree <= 0) return ASM_E_INVALID;
-  std::memset(bits_out, 0, sizeof(uint64_t) * (size_t)n_trees * (size_t)words_per_tree);
-  for (int64_t t = 0; t < n_trees; t++) {
-    uint64_t* row = bits_out + t * words_per_tree;
-    for (int32_t j = 0; j < ids_per_tree; j++) {
-      int32_t id = clade_ids[t * ids_per_tree + j];
-      if (id < 0 || (id >> 6) >= words_per_tree) return ASM_E_RANGE;
-      row[id >> 6] |= 1ULL << (id & 63);
+  std::atomic<int> bad{0};
+  auto rows = [&](int64_t t0, int64_t t1) {
+    for (int64_t t = t0; t < t1; t++) {
+      uint64_t* row = bits_out + t * words_per_tree;
+      std::memset(row, 0, sizeof(uint64_t) * (size_t)words_per_tree);
+      for (int32_t j = 0; j < ids_per_tree; j++) {
+        int32_t id = clade_ids[t * ids_per_tree + j];
+        if (id < 0 || (id >> 6) >= words_per_tree) {
+          bad.store(1);
+          return;
+        }
+        row[id >> 6] |= 1ULL << (id & 63);
+      }
     }
+  };
+  const int threads = encoder_threads(n_trees);
+  if (threads <= 1) {
+    rows(0, n_trees);
+  } else {
+    std::vector<std::thread> pool;
+    const int64_t per = (n_trees + threads - 1) / threads;
+    for (int k = 0; k < threads; k++) pool.emplace_back(rows, std::min<int64_t>(k * per, n_trees), std::min<int64_t>((k + 1) * per, n_trees));
+    for (auto& th : pool) th.join();
   }
-  return ASM_OK;
+  return bad.load() ? ASM_E_RANGE : ASM_OK;
 }
 
 }  // extern "C"

@@ -90,6 +90,16 @@ struct asm_encoder {
     slots[h] = Slot{k, id};
     return id;
   }
+  // read-only lookup (no insertion, safe from several threads while nobody inserts): id or -1
+  int32_t find_set(const Key128& k, const uint64_t* bits) const {
+    if (slots.empty()) return -1;
+    size_t h = KeyHash()(k) & mask;
+    for (;; h = (h + 1) & mask) {
+      const Slot& s = slots[h];
+      if (s.id < 0) return -1;
+      if (s.key == k && std::memcmp(clade_set(s.id), bits, sizeof(uint64_t) * (size_t)set_words) == 0) return s.id;
+    }
+  }
   // the same from a list of leaf numbers (any order)
   int32_t get_or_add(const Key128& k, const int32_t* leaves, int32_t n) {
     scratch.assign((size_t)set_words, 0);
@@ -102,3 +112,10 @@ struct asm_encoder {
 // Post-order walk of one tree (host_encoder.cpp): one clade id per internal node; false if the arrays do not
 // describe a binary tree on n_taxa leaves.
 bool asm_encode_tree(asm_encoder* enc, const int32_t* left, const int32_t* right, int32_t root, int32_t* ids_out);
+
+// A clade met during the parallel phase that the dictionary (frozen for that phase) does not hold yet.
+struct asm_encoder_miss {
+  int32_t pos;      // position of the clade in the tree's post-order
+  Key128 key;
+  size_t set_off;   // leaf set: set_words words at this offset of the recording thread's pool
+};

@@ -247,6 +247,11 @@ int32_t asm_encoder_add_topologies(asm_encoder* enc, int64_t n_trees, const int3
  * subtracted from each label (parser.offsetInput = 1, AutoStopMCMC.java:527).  Branch lengths and
  * [&...] annotations are skipped. */
 int32_t asm_encoder_add_newick(asm_encoder* enc, const char* newick, int32_t label_offset, int32_t* clade_ids_out);
+/* n_trees Newick strings at once: parsing and the clade walks use every host core (ASM_ENCODER_THREADS), the ids are
+ * the ones one-by-one calls in the same order would hand out.  asm_encoder_add_topologies is parallel in the same
+ * way (two phases per batch: look-ups against the frozen dictionary in parallel, insertions in first-seen order). */
+int32_t asm_encoder_add_newick_batch(asm_encoder* enc, int64_t n_trees, const char* const* newicks, int32_t label_offset,
+                                     int32_t* clade_ids_out);
 int64_t asm_encoder_num_clades(const asm_encoder* enc);
 /* Sorted leaf numbers of clade `id`; returns the clade size or ASM_E_*. */
 int32_t asm_encoder_clade_leaves(const asm_encoder* enc, int64_t id, int32_t* leaves_out, int32_t cap);
