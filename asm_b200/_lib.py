@@ -78,6 +78,7 @@ SIGNATURES = {
     "asm_ess_set_adaptive": (_i32, [_p, _i32]),
     "asm_psrf_last_layout": (_i32, [_p, _i64p, _i64p, _i64p, _i64p]),
     "asm_encoder_create": (_i32, [C.POINTER(_p), _i32]),
+    "asm_seq_sum": (_i32, [_p, _p, _i64, _p]),
     "asm_encoder_destroy": (_i32, [_p]),
     "asm_encoder_add_topologies": (_i32, [_p, _i64, _p, _p, _p, _p]),
     "asm_encoder_add_newick": (_i32, [_p, C.c_char_p, _i32, _p]),
@@ -341,6 +342,13 @@ class GpuContext:
         rows = np.empty((Cn, n_rows, Cn), dtype=np.float64) if want_rows else None
         self._check(lib().asm_psrf_finish_device(self._h, C.c_void_p(d_S_ptr), n_rows, _ptr(rows), _ptr(mean)))
         return (rows, mean) if want_rows else mean
+
+    def seq_sum(self, values) -> float:
+        """asm_seq_sum: the left-to-right sum of `values`, rounded add by add, evaluated in parallel on the device."""
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        out = C.c_double()
+        self._check(lib().asm_seq_sum(self._h, _ptr(v), v.shape[0], C.byref(out)))
+        return out.value
 
     def psrf_eval(self, burnin, row_start: int, end: int, delta: int = 1, method: int = ASM_RF_POPC,
                   want_rows: bool = False):

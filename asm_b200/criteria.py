@@ -20,6 +20,8 @@ HOST_SIGNATURES = {
     "asmh_trace_info_destroy": (_i32, [_p]),
     "asmh_read_log_line": (_i32, [_p, _i32, C.c_char_p, _i32p]),
     "asmh_read_tree_log_line": (_i32, [_p, _i32, C.c_char_p, _i32p]),
+    "asmh_parse_log_cell": (_f64, [C.c_char_p, _i32p]),
+    "asmh_flush": (_i32, [_p]),
     "asmh_set_taxon_count": (_i32, [_p, _i32]),
     "asmh_add_tree": (_i32, [_p, _i32, _p, _p, _i32]),
     "asmh_add_log_line": (_i32, [_p, _i32, _p, _i32]),
@@ -72,6 +74,14 @@ def _check(rc: int):
     if rc == L.ASM_E_INVALID:
         raise IllegalArgumentException(msg)
     raise L.AsmGpuError(rc, msg)
+
+
+def parse_log_cell(token: str):
+    """One trace-log cell as AutoStopMCMC.readLogLines converts it (:460-466): (value, parsed) -- value is 0.0 where
+    Double.parseDouble would throw.  Host only."""
+    ok = C.c_int32()
+    v = _h().asmh_parse_log_cell(token.encode(), C.byref(ok))
+    return float(v), bool(ok.value)
 
 
 class TraceInfo:
@@ -129,6 +139,10 @@ class TraceInfo:
 
     def cladeCount(self) -> int:
         return int(_h().asmh_clade_count(self._p))
+
+    def flush(self):
+        """Upload what has been appended since the last check (done implicitly by every criterion)."""
+        _check(_h().asmh_flush(self._p))
 
 
 class _Criterion:

@@ -161,6 +161,7 @@ int32_t psrf_gather_f4(asm_ctx* ctx);    // layout (col_block = 240) -> opnd_f4 
 int32_t psrf_check_max_bits(asm_ctx* ctx, int32_t limit);  // ASM_E_UNSUPPORTED if a gathered row has more set bits
 int32_t psrf_compact(asm_ctx* ctx, asm_shard shard, int64_t* d_S_out);  // S_pad -> [C][n_rows][C], pad-corrected
 int32_t psrf_finish(asm_ctx* ctx, const int64_t* d_S, int32_t n_rows, double* psrf_rows_host, double* psrf_mean_host);
+int32_t seq_sum(asm_ctx* ctx, const double* values_host, int64_t n, double* sum_host);  // left-to-right sum, seq_sum.cuh
 // rf_popc.cu
 int32_t rf_popc_sums(asm_ctx* ctx, asm_shard shard);
 int32_t rf_popc_block(asm_ctx* ctx, int32_t chainA, int64_t r0, int64_t r1, int32_t chainB, int64_t c0, int64_t c1,

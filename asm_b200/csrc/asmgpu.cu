@@ -538,6 +538,13 @@ int32_t asm_psrf_finish_device(asm_ctx* ctx, const int64_t* d_S, int32_t n_rows,
   return psrf_finish(ctx, d_S, n_rows, psrf_rows, psrf_mean);
 }
 
+int32_t asm_seq_sum(asm_ctx* ctx, const double* values, int64_t n, double* sum_out) {
+  ASM_NULLCHECK(ctx);
+  if (is_group(ctx)) return group_run_one(ctx, 0, [=](asm_ctx* m) { return asm_seq_sum(m, values, n, sum_out); });
+  ASM_ENTER(ctx);
+  return seq_sum(ctx, values, n, sum_out);
+}
+
 // psrf_mean == NULL (members of a group other than the first): take part in the sums and the all-reduce only
 static int32_t psrf_eval_rank(asm_ctx* ctx, const int32_t* burnin, int32_t row_start, int32_t end, int32_t delta,
                               int32_t method, double* psrf_rows, double* psrf_mean) {

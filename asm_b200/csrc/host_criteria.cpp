@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <locale.h>
 #include <fstream>
 #include <sstream>
 
@@ -54,19 +55,67 @@ std::string trim(const std::string& s) {
   return s.substr(a, b - a);
 }
 
+// Double.parseDouble's grammar (FloatingDecimal.readJavaFormatString): surrounding whitespace trimmed, optional sign,
+// then exactly "NaN", exactly "Infinity", a decimal literal (digits with an optional point, optional exponent) or a
+// hexadecimal one (0x, hex digits with an optional point, mandatory binary exponent), optional type suffix f/F/d/D.
+// Anything else -- "inf", "nan", "0x10", "1,5", "1e" -- is a NumberFormatException there and false here.  The value
+// comes from strtod_l under the "C" locale: correctly rounded like Java's, overflow to Infinity, underflow towards 0,
+// and independent of the embedding process's LC_NUMERIC.
+bool java_parse_double(const std::string& raw, double* out) {
+  size_t a = 0, b = raw.size();
+  while (a < b && (unsigned char)raw[a] <= ' ') a++;  // String.trim()
+  while (b > a && (unsigned char)raw[b - 1] <= ' ') b--;
+  if (a == b) return false;
+  const std::string t = raw.substr(a, b - a);
+  size_t i = 0;
+  bool neg = false;
+  if (t[i] == '+' || t[i] == '-') neg = t[i++] == '-';
+  if (t.compare(i, std::string::npos, "NaN") == 0) {
+    *out = std::numeric_limits<double>::quiet_NaN();
+    return true;
+  }
+  if (t.compare(i, std::string::npos, "Infinity") == 0) {
+    *out = neg ? -std::numeric_limits<double>::infinity() : std::numeric_limits<double>::infinity();
+    return true;
+  }
+  const size_t body = i;
+  auto digits = [&](bool hex) {
+    size_t n = 0;
+    while (i < t.size() && (hex ? std::isxdigit((unsigned char)t[i]) : std::isdigit((unsigned char)t[i]))) i++, n++;
+    return n;
+  };
+  const bool hex = i + 1 < t.size() && t[i] == '0' && (t[i + 1] == 'x' || t[i + 1] == 'X');
+  if (hex) i += 2;
+  size_t nd = digits(hex);
+  if (i < t.size() && t[i] == '.') {
+    i++;
+    nd += digits(hex);
+  }
+  if (nd == 0) return false;
+  const bool has_exp = i < t.size() && (hex ? (t[i] == 'p' || t[i] == 'P') : (t[i] == 'e' || t[i] == 'E'));
+  if (has_exp) {
+    i++;
+    if (i < t.size() && (t[i] == '+' || t[i] == '-')) i++;
+    if (digits(false) == 0) return false;
+  } else if (hex) {
+    return false;  // the binary exponent is mandatory
+  }
+  const size_t num_end = i;
+  if (i < t.size() && (t[i] == 'f' || t[i] == 'F' || t[i] == 'd' || t[i] == 'D')) i++;
+  if (i != t.size()) return false;
+  static const locale_t c_locale = newlocale(LC_ALL_MASK, "C", (locale_t)0);
+  const std::string num = t.substr(body, num_end - body);
+  char* end = nullptr;
+  const double v = c_locale ? strtod_l(num.c_str(), &end, c_locale) : std::strtod(num.c_str(), &end);
+  if (end != num.c_str() + num.size()) return false;
+  *out = neg ? -v : v;
+  return true;
+}
+
 // Double.parseDouble, NumberFormatException -> 0.0 (AutoStopMCMC.java:461-465)
 double parse_double_or_zero(const std::string& t) {
-  if (t.empty()) return 0.0;
-  if (t == "NaN") return std::numeric_limits<double>::quiet_NaN();
-  if (t == "Infinity" || t == "+Infinity") return std::numeric_limits<double>::infinity();
-  if (t == "-Infinity") return -std::numeric_limits<double>::infinity();
-  const char* c = t.c_str();
-  if (!(std::isdigit((unsigned char)c[0]) || c[0] == '-' || c[0] == '+' || c[0] == '.')) return 0.0;
-  char* end = nullptr;
-  double v = std::strtod(c, &end);
-  if (end == c) return 0.0;
-  if (*end == 'd' || *end == 'D' || *end == 'f' || *end == 'F') end++;  // Java accepts a type suffix
-  return *end == 0 ? v : 0.0;
+  double v = 0.0;
+  return java_parse_double(t, &v) ? v : 0.0;
 }
 
 // Java Math.min(double, double): NaN if either is NaN
@@ -91,6 +140,8 @@ TraceInfo::TraceInfo(int chainCount, int device) {
   if (rc != ASM_OK) throw std::runtime_error(std::string("asm_create: ") + asm_last_error(nullptr));
   nTrees_.assign((size_t)chainCount, 0);
   nLines_.assign((size_t)chainCount, 0);
+  pendingIds_.resize((size_t)chainCount);
+  linesUploaded_.assign((size_t)chainCount, 0);
 }
 
 TraceInfo::~TraceInfo() {
@@ -107,9 +158,12 @@ void TraceInfo::setLabels(const std::vector<std::string>& labels) {
 
 void TraceInfo::addLogLine(int chain, const double* values, int n) {
   if (chain < 0 || chain >= chainCount()) throw IllegalArgumentException("chain out of range");
-  GPU_CHECK(ctx_, asm_traces_append(ctx_, chain, n, 1, values));
+  if (n < 1 || !values) throw IllegalArgumentException("empty log line");
   if (hostLogs_.empty()) hostLogs_.resize(nLines_.size()), hostCols_.assign(nLines_.size(), 0);
   if (hostCols_[(size_t)chain] == 0) hostCols_[(size_t)chain] = n;
+  if (hostCols_[(size_t)chain] != n)  // what asm_traces_append would answer when the line is uploaded
+    throw IllegalArgumentException("log line with " + std::to_string(n) + " columns, chain " + std::to_string(chain) + " has " +
+                                   std::to_string(hostCols_[(size_t)chain]));
   hostLogs_[(size_t)chain].insert(hostLogs_[(size_t)chain].end(), values, values + n);  // asm_traces_append checked n
   nLines_[(size_t)chain]++;
 }
@@ -138,13 +192,33 @@ void TraceInfo::setTaxonCount(int nTaxa) {
   idsScratch_.resize((size_t)std::max(1, nTaxa - 1));
 }
 
+// The encoded tree waits on the host (its clade ids: a bit row is only as wide as the dictionary at upload time, so
+// rows are built then, all at the final width, and the chains already on the GPU are re-strided at most once).
 void TraceInfo::appendIds_(int chain) {
-  const int words = asm_encoder_words(enc_);
-  bitsScratch_.resize((size_t)words);
-  if (asm_encode_bits(idsScratch_.data(), 1, nTaxa_ - 1, words, bitsScratch_.data()) != ASM_OK)
-    throw std::runtime_error("asm_encode_bits failed");
-  GPU_CHECK(ctx_, asm_trees_append(ctx_, chain, 1, words, bitsScratch_.data()));
+  std::vector<int32_t>& p = pendingIds_[(size_t)chain];
+  p.insert(p.end(), idsScratch_.begin(), idsScratch_.begin() + (nTaxa_ - 1));
   nTrees_[(size_t)chain]++;
+}
+
+void TraceInfo::flush() {
+  for (int c = 0; c < chainCount(); c++) {
+    std::vector<int32_t>& p = pendingIds_[(size_t)c];
+    if (!p.empty()) {
+      const int per = nTaxa_ - 1;
+      const int64_t n = (int64_t)(p.size() / (size_t)per);
+      const int words = asm_encoder_words(enc_);
+      bitsScratch_.resize((size_t)words * (size_t)n);
+      if (asm_encode_bits(p.data(), n, per, words, bitsScratch_.data()) != ASM_OK) throw std::runtime_error("asm_encode_bits failed");
+      GPU_CHECK(ctx_, asm_trees_append(ctx_, c, n, words, bitsScratch_.data()));
+      p.clear();
+    }
+    const int64_t up = linesUploaded_[(size_t)c], have = nLines_[(size_t)c];
+    if (have > up) {
+      const int cols = hostCols_[(size_t)c];
+      GPU_CHECK(ctx_, asm_traces_append(ctx_, c, cols, have - up, hostLogs_[(size_t)c].data() + (size_t)up * (size_t)cols));
+      linesUploaded_[(size_t)c] = have;
+    }
+  }
 }
 
 void TraceInfo::addTreeNewick(int chain, const std::string& newick, int labelOffset) {
@@ -512,6 +586,8 @@ std::map<std::string, double> TraceESS::getLogMap() {  // :191-198
 
 // ------------------------------------------------------------------------------------------------ GelmanRubin
 bool GelmanRubin::converged(const int*, int available) {  // GelmanRubin.java:32-51
+  lastMaxGR = 0;
+  if (nChains < 2) return true;  // no pair to look at (:40-41): true whatever `available` is, nothing is read
   asm_ctx* ctx = traceInfo->ctx();
   int32_t nItems = 0;
   asm_traces_count(ctx, 0, nullptr, &nItems);
@@ -780,6 +856,15 @@ int32_t asmh_read_log_line(asmh_trace_info* ti, int32_t chain, const char* line,
     bool r = TI(ti)->readLogLine(chain, line);
     if (appended) *appended = r;
   })
+}
+double asmh_parse_log_cell(const char* token, int32_t* is_number) {
+  double v = 0.0;
+  const bool ok = token && java_parse_double(token, &v);
+  if (is_number) *is_number = ok;
+  return ok ? v : 0.0;
+}
+int32_t asmh_flush(asmh_trace_info* ti) {
+  HOST_TRY({ TI(ti)->flush(); })
 }
 int32_t asmh_read_tree_log_line(asmh_trace_info* ti, int32_t chain, const char* line, int32_t* appended) {
   HOST_TRY({

@@ -13,6 +13,7 @@
 #include <cmath>
 
 #include "asm_internal.h"
+#include "seq_sum.cuh"
 
 namespace {
 
@@ -190,64 +191,36 @@ __global__ void __launch_bounds__(256) compact_kernel(const __grid_constant__ Co
   }
 }
 
-// One block per ordered chain pair (a, b).  The per-row values are produced in parallel into shared
-// memory, then thread 0 adds them in ascending row order: the sequential sum of TreePSRF.mean
-// (TreePSRF.java:264-271).  Row value: TreePSRF.java:287-292.  The sum is one dependent DADD per row
-// (8.3 clocks each) and cannot be split, so it is the long pole: warps 1..7 fill the next chunk of row
-// values into the other half of the buffer while thread 0 adds the current one.
-constexpr int kFinishChunk = 2048;
-__global__ void __launch_bounds__(256) psrf_finish_kernel(const long long* __restrict__ S, int C, int n_rows,
-                                                           double* __restrict__ psrf_rows,
-                                                           double* __restrict__ psrf_mean) {
-  __shared__ double vals[2][kFinishChunk];
+// One block per ordered chain pair (a, b).  Row value: TreePSRF.java:287-292.  The mean is the sum of the row values
+// in ascending row order, one rounding per add (TreePSRF.mean, TreePSRF.java:264-271), divided by the row count.
+// The order is kept and the chain of dependent adds is not: seq_sum.cuh evaluates the same roundings as an integer
+// scan over the block (plain DADDs only where the running sum changes binade).
+__global__ void __launch_bounds__(seqsum::kThreads) psrf_finish_kernel(const long long* __restrict__ S, int C, int n_rows,
+                                                                        double* __restrict__ psrf_rows,
+                                                                        double* __restrict__ psrf_mean) {
+  __shared__ seqsum::Shared sh;
   const int a = blockIdx.x / C, b = blockIdx.x % C;
-  const int n_chunks = (n_rows + kFinishChunk - 1) / kFinishChunk;
-  // rows [ck*kFinishChunk, ...) -> vals[ck & 1], by the threads first .. first+count-1
-  auto fill = [&](int ck, int first, int count) {
-    const int r0 = ck * kFinishChunk;
-    const int n = min(kFinishChunk, n_rows - r0);
-    double* dst = vals[ck & 1];
-    for (int k = (int)threadIdx.x - first; k < n; k += count) {
-      const long long* row = S + ((size_t)a * n_rows + (r0 + k)) * C;
-      const double varIn = (double)row[a];
-      const double varBetween = (double)row[b];
-      double psrf;
-      if (varIn != 0) {
-        psrf = sqrt(varBetween / varIn);
-      } else {
-        psrf = sqrt(varBetween);
-      }
-      dst[k] = psrf;
-      if (psrf_rows) psrf_rows[((size_t)a * n_rows + (r0 + k)) * C + b] = psrf;
+  const double sum = seqsum::block_sum(sh, n_rows, [&](int r) {
+    const long long* row = S + ((size_t)a * n_rows + r) * C;
+    const double varIn = (double)row[a];
+    const double varBetween = (double)row[b];
+    double psrf;
+    if (varIn != 0) {
+      psrf = sqrt(varBetween / varIn);
+    } else {
+      psrf = sqrt(varBetween);
     }
-  };
-  double sum = 0;
-  if (n_chunks > 0) fill(0, 0, blockDim.x);
-  __syncthreads();
-  for (int ck = 0; ck < n_chunks; ck++) {
-    if (threadIdx.x >= 32) {
-      if (ck + 1 < n_chunks) fill(ck + 1, 32, blockDim.x - 32);
-    } else if (threadIdx.x == 0) {
-      const double* v = vals[ck & 1];
-      const int n = min(kFinishChunk, n_rows - ck * kFinishChunk);
-      int k = 0;
-      for (; k + 8 <= n; k += 8) {  // loads first, then the dependent chain of 8 adds
-        const double v0 = v[k], v1 = v[k + 1], v2 = v[k + 2], v3 = v[k + 3];
-        const double v4 = v[k + 4], v5 = v[k + 5], v6 = v[k + 6], v7 = v[k + 7];
-        sum = __dadd_rn(sum, v0);
-        sum = __dadd_rn(sum, v1);
-        sum = __dadd_rn(sum, v2);
-        sum = __dadd_rn(sum, v3);
-        sum = __dadd_rn(sum, v4);
-        sum = __dadd_rn(sum, v5);
-        sum = __dadd_rn(sum, v6);
-        sum = __dadd_rn(sum, v7);
-      }
-      for (; k < n; k++) sum = __dadd_rn(sum, v[k]);
-    }
-    __syncthreads();  // chunk ck is consumed and chunk ck+1 is complete
-  }
+    if (psrf_rows) psrf_rows[((size_t)a * n_rows + r) * C + b] = psrf;
+    return psrf;
+  });
   if (threadIdx.x == 0) psrf_mean[a * C + b] = sum / (double)n_rows;  // 0/0 = NaN for no rows, as in Java
+}
+
+// The same walk over doubles in memory (asm_seq_sum).
+__global__ void __launch_bounds__(seqsum::kThreads) seq_sum_kernel(const double* __restrict__ v, int n, double* __restrict__ out) {
+  __shared__ seqsum::Shared sh;
+  const double sum = seqsum::block_sum(sh, n, [&](int k) { return v[k]; });
+  if (threadIdx.x == 0) *out = sum;
 }
 
 inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
@@ -513,12 +486,28 @@ int32_t psrf_finish(asm_ctx* ctx, const int64_t* d_S, int32_t n_rows, double* ps
   }
   {
     LaunchScope ls(ctx, ASM_K_PSRF_FINISH);
-    psrf_finish_kernel<<<C * C, 256, 0, ctx->stream>>>((const long long*)d_S, C, n_rows, d_rows, (double*)ctx->psrf_mean.p);
+    psrf_finish_kernel<<<C * C, seqsum::kThreads, 0, ctx->stream>>>((const long long*)d_S, C, n_rows, d_rows, (double*)ctx->psrf_mean.p);
   }
   ASM_CUDA(ctx, cudaGetLastError());
   ASM_CUDA(ctx, cudaMemcpyAsync(psrf_mean_host, ctx->psrf_mean.p, sizeof(double) * (size_t)C * C, cudaMemcpyDeviceToHost,
                                 ctx->stream));
   if (d_rows) ASM_CUDA(ctx, cudaMemcpyAsync(psrf_rows_host, d_rows, rows_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  ASM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return ASM_OK;
+}
+
+int32_t seq_sum(asm_ctx* ctx, const double* values_host, int64_t n, double* sum_host) {
+  if (n < 0 || n > INT32_MAX || (n > 0 && !values_host) || !sum_host) return asm_fail(ctx, ASM_E_INVALID, "seq_sum: bad argument");
+  int32_t rc = asm_reserve(ctx, ctx->misc, sizeof(double) * ((size_t)n + 1));
+  if (rc != ASM_OK) return rc;
+  double* d = (double*)ctx->misc.p;
+  if (n) ASM_CUDA(ctx, cudaMemcpyAsync(d + 1, values_host, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  {
+    LaunchScope ls(ctx, ASM_K_MISC);
+    seq_sum_kernel<<<1, seqsum::kThreads, 0, ctx->stream>>>(d + 1, (int)n, d);
+  }
+  ASM_CUDA(ctx, cudaGetLastError());
+  ASM_CUDA(ctx, cudaMemcpyAsync(sum_host, d, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   ASM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return ASM_OK;
 }

@@ -1,0 +1,252 @@
+// seq_sum.cuh -- the left-to-right double sum  s = (((0 + v0) + v1) + ...)  evaluated in parallel, bit for bit.
+//
+// TreePSRF.mean (TreePSRF.java:264-271) adds the n row values in order, one rounding per add, and the result must
+// be the Java's to the last bit, so the order cannot change.  A dependent DADD costs 8.3 clocks on B200
+// (profiles/r01_microbench_pipes.json): 10,000 rows are 42 us of one idle thread, and the chain grows with the
+// number of trees while everything around it scales.
+//
+// What makes the chain splittable: while the running sum s stays inside one binade [2^e, 2^(e+1)) it is an integer
+// multiple M of u = 2^(e-52), and adding a value 0 <= v < 2^(e+1) is integer arithmetic,
+//     v = q*u + r (0 <= r < u)   ->   M' = M + q + (r > u/2  or  (r == u/2 and M+q odd)),      round-to-nearest-even
+// i.e. a step depends on the running sum only through ITS PARITY, and only for exact ties.  A run of elements is
+// therefore a pair (d0, d1) = ulps added when the run starts on an even / odd M; two runs compose as
+//     (a then b).d_p = a.d_p + b.d_{p xor (a.d_p & 1)}
+// which is associative: threads fold their own elements, an ordered reduction combines the threads.  A run ends
+// where a conservative bound M + sum(q_k + 1) could reach 2^53 (the sum would leave the binade), or at an element
+// that is negative, non-finite or >= 2^(e+1); that element is added with a plain DADD and the walk restarts in the
+// new binade.  Binade changes are rare (log2 of the sum), so nearly all adds take the parallel path.
+#pragma once
+#include <cstdint>
+#include <cstring>
+
+#if defined(__CUDACC__)
+#define SEQ_HD __host__ __device__ __forceinline__
+#else
+#define SEQ_HD inline
+#endif
+
+namespace seqsum {
+
+struct Seg {  // ulps a run of elements adds to a running sum that starts even (d0) / odd (d1)
+  unsigned long long d0, d1;
+};
+
+SEQ_HD Seg then(Seg a, Seg b) {
+  Seg r;
+  r.d0 = a.d0 + ((a.d0 & 1ull) ? b.d1 : b.d0);
+  r.d1 = a.d1 + ((a.d1 & 1ull) ? b.d0 : b.d1);  // started odd: still odd after `a` iff a.d1 is even
+  return r;
+}
+
+SEQ_HD unsigned long long bits_of(double v) {
+#if defined(__CUDA_ARCH__)
+  return (unsigned long long)__double_as_longlong(v);
+#else
+  unsigned long long b;
+  std::memcpy(&b, &v, sizeof b);
+  return b;
+#endif
+}
+SEQ_HD double double_of(unsigned long long b) {
+#if defined(__CUDA_ARCH__)
+  return __longlong_as_double((long long)b);
+#else
+  double v;
+  std::memcpy(&v, &b, sizeof v);
+  return v;
+#endif
+}
+
+constexpr unsigned long long kTwo52 = 1ull << 52, kTwo53 = 1ull << 53, kBoundCap = 1ull << 54;
+constexpr int kMinExp = -900;  // binades below stay on the plain path (u = 2^(e-52) must be far from subnormal)
+
+// Can the running sum s take the integer path?  (positive, normal, not tiny.)  On success e = its exponent and
+// M = s / 2^(e-52) in [2^52, 2^53).
+SEQ_HD bool binade_of(double s, int* e, unsigned long long* M) {
+  const unsigned long long b = bits_of(s);
+  const int ef = (int)((b >> 52) & 0x7ff);
+  if ((b >> 63) || ef == 0 || ef == 0x7ff) return false;
+  *e = ef - 1023;
+  if (*e < kMinExp) return false;
+  *M = (b & (kTwo52 - 1)) | kTwo52;
+  return true;
+}
+SEQ_HD double from_binade(int e, unsigned long long M) {  // M in [2^52, 2^53)
+  return double_of(((unsigned long long)(e + 1023) << 52) | (M & (kTwo52 - 1)));
+}
+
+// One element against a running sum in binade e.  false: it needs the plain add.  Otherwise seg = what it does to
+// M, bound = an upper bound of that (q + 1, or 0 for an element that cannot change M).
+SEQ_HD bool element(double v, int e, Seg* seg, unsigned long long* bound) {
+  const unsigned long long b = bits_of(v);
+  const int ef = (int)((b >> 52) & 0x7ff);
+  unsigned long long m = b & (kTwo52 - 1);
+  seg->d0 = seg->d1 = 0;
+  *bound = 0;
+  if (ef == 0 && m == 0) return true;  // +0.0 and -0.0 leave a positive sum as it is
+  if ((b >> 63) || ef == 0x7ff) return false;
+  int ek = -1022;
+  if (ef != 0) {
+    m |= kTwo52;
+    ek = ef - 1023;
+  }
+  if (ek > e) return false;
+  const int d = e - ek;  // v = m * 2^-d ulps
+  if (d >= 64) return true;  // far below half an ulp
+  const unsigned long long q = m >> d;
+  *bound = q + 1;
+  if (d == 0) {
+    seg->d0 = seg->d1 = q;
+    return true;
+  }
+  const unsigned long long rem = m & ((1ull << d) - 1), half = 1ull << (d - 1);
+  if (rem > half) {
+    seg->d0 = seg->d1 = q + 1;
+  } else if (rem < half) {
+    seg->d0 = seg->d1 = q;
+  } else {  // exact tie: to the even neighbour
+    seg->d0 = q + (q & 1ull);
+    seg->d1 = q + ((q & 1ull) ^ 1ull);
+  }
+  return true;
+}
+
+SEQ_HD unsigned long long sat_add(unsigned long long a, unsigned long long b) {
+  const unsigned long long s = a + b;  // both <= kBoundCap: no wrap
+  return s > kBoundCap ? kBoundCap : s;
+}
+
+}  // namespace seqsum
+
+#if defined(__CUDACC__)
+namespace seqsum {
+
+constexpr int kThreads = 256, kPerThread = 8, kTile = kThreads * kPerThread;
+constexpr int kPrelude = 64;   // the first adds cross a binade almost every time: plain
+constexpr int kPlainRun = 32;  // after a run that made little progress, this many plain adds before trying again
+__device__ __forceinline__ int pad(int k) { return k + (k >> 3); }  // thread t's 8 values: stride 9 doubles in shared memory
+
+struct Shared {
+  double vals[kTile + kTile / 8];
+  unsigned long long warp_u64[kThreads / 32];
+  Seg warp_seg[kThreads / 32];
+  int warp_cut[kThreads / 32];
+  double s;
+  int lo;
+};
+
+// Sum of value(0) .. value(n-1) in that order, every add rounded as a scalar loop would; all kThreads threads of
+// the block call it, the result is returned to every thread.  value(k) is evaluated once per element (by some
+// thread, in no particular order) and may have side effects for that k (storing the row value).
+template <class Value>
+__device__ double block_sum(Shared& sh, int n, Value&& value) {
+  const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    sh.s = 0.0;
+    sh.lo = 0;
+  }
+  for (int t0 = 0; t0 < n; t0 += kTile) {
+    const int tn = min(kTile, n - t0);
+    __syncthreads();  // the previous tile's values are consumed
+    for (int k = tid; k < tn; k += kThreads) sh.vals[pad(k)] = value(t0 + k);
+    __syncthreads();
+    if (tid == 0) {
+      double s = sh.s;
+      int lo = 0;
+      if (t0 == 0)
+        for (; lo < min(kPrelude, tn); lo++) s = __dadd_rn(s, sh.vals[pad(lo)]);
+      sh.s = s;
+      sh.lo = lo;
+    }
+    __syncthreads();
+    for (;;) {
+      const int lo = sh.lo;  // uniform
+      if (lo >= tn) break;
+      const double s = sh.s;
+      int e = 0;
+      unsigned long long M = 0;
+      const bool integer_path = binade_of(s, &e, &M);  // uniform
+      int cut = lo;  // first element of [lo, tn) that does not go the integer way
+      Seg mine{0, 0};
+      if (integer_path) {
+        // this thread's elements: lo + tid*8 .. +7, i.e. the run starts at `lo`, not at a multiple of 8
+        const int first = lo + tid * kPerThread;
+        Seg segs[kPerThread];
+        unsigned long long bnd[kPerThread];
+        bool ok[kPerThread];
+        unsigned long long local = 0;
+#pragma unroll
+        for (int i = 0; i < kPerThread; i++) {
+          const int k = first + i;
+          ok[i] = false;
+          bnd[i] = 0;
+          segs[i] = Seg{0, 0};
+          if (k < tn) ok[i] = element(sh.vals[pad(k)], e, &segs[i], &bnd[i]);
+          local = sat_add(local, bnd[i]);  // bnd <= 2^53
+        }
+        // exclusive prefix of the bounds over the threads; saturating adds of non-negative terms = min(sum, cap)
+        unsigned long long incl = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl = sat_add(incl, up);
+        }
+        const unsigned long long prev = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 31) sh.warp_u64[warp] = incl;
+        __syncthreads();
+        unsigned long long run = lane ? prev : 0ull;
+        for (int w = 0; w < warp; w++) run = sat_add(run, sh.warp_u64[w]);
+        int my_cut = tn;
+#pragma unroll
+        for (int i = 0; i < kPerThread; i++) {
+          const int k = first + i;
+          if (k < tn && my_cut == tn) {
+            run = sat_add(run, bnd[i]);
+            if (!ok[i] || M + run >= kTwo53) my_cut = k;
+          }
+        }
+        if (first >= tn) my_cut = tn;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) my_cut = min(my_cut, __shfl_xor_sync(0xffffffffu, my_cut, o));
+        if (lane == 0) sh.warp_cut[warp] = my_cut;
+        __syncthreads();
+        cut = tn;
+        for (int w = 0; w < kThreads / 32; w++) cut = min(cut, sh.warp_cut[w]);
+        // fold this thread's elements below the cut, then the threads in order
+#pragma unroll
+        for (int i = 0; i < kPerThread; i++)
+          if (first + i < cut) mine = then(mine, segs[i]);
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          Seg other;
+          other.d0 = __shfl_down_sync(0xffffffffu, mine.d0, o);
+          other.d1 = __shfl_down_sync(0xffffffffu, mine.d1, o);
+          if (lane + o < 32) mine = then(mine, other);  // lanes that are not a multiple of 2*o go unused from here on
+        }
+        if (lane == 0) sh.warp_seg[warp] = mine;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        double s1 = s;
+        int next = cut;
+        if (integer_path && cut > lo) {
+          Seg all = sh.warp_seg[0];
+          for (int w = 1; w < kThreads / 32; w++) all = then(all, sh.warp_seg[w]);
+          s1 = from_binade(e, M + ((M & 1ull) ? all.d1 : all.d0));
+        }
+        // the element that ended the run, and more of them if the run was short (negative values, a sum that is
+        // still tiny): plain adds
+        const int plain = (cut - lo < 16) ? kPlainRun : 1;
+        for (int i = 0; i < plain && next < tn; i++, next++) s1 = __dadd_rn(s1, sh.vals[pad(next)]);
+        sh.s = s1;
+        sh.lo = next;
+      }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  return sh.s;
+}
+
+}  // namespace seqsum
+#endif

@@ -66,7 +66,13 @@ class TraceInfo {  // TraceInfo.java
   double logValue(int chain, int col, int64_t x) const { return hostLogs_[(size_t)chain][(size_t)x * (size_t)hostCols_[(size_t)chain] + (size_t)col]; }
   int taxonCount() const { return nTaxa_; }
   int64_t cladeCount() const;
-  asm_ctx* ctx() const { return ctx_; }
+  // The GPU context with everything appended so far uploaded: trees and log lines are staged on the host as they
+  // arrive and go up in one copy per chain here, i.e. once per convergence check instead of once per sample.
+  asm_ctx* ctx() {
+    flush();
+    return ctx_;
+  }
+  void flush();
 
  private:
   asm_ctx* ctx_ = nullptr;
@@ -84,6 +90,8 @@ class TraceInfo {  // TraceInfo.java
   int translateCount_ = 0;
   std::vector<int32_t> idsScratch_;
   std::vector<uint64_t> bitsScratch_;
+  std::vector<std::vector<int32_t>> pendingIds_;  // [chain]: clade ids of the trees not uploaded yet
+  std::vector<int64_t> linesUploaded_;            // [chain]: lines of hostLogs_ already on the GPU
   void appendIds_(int chain);
 };
 

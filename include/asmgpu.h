@@ -157,6 +157,12 @@ void* asm_stream_handle(asm_ctx* ctx);
  * Both outputs are host buffers. */
 int32_t asm_psrf_finish_device(asm_ctx* ctx, const int64_t* d_S, int32_t n_rows, double* psrf_rows,
                                double* psrf_mean);
+/* sum_out = values[0] + values[1] + ... + values[n-1] added left to right, every add rounded as the scalar loop
+ * `for (i) s += values[i]` rounds it -- the summation TreePSRF.mean does (TreePSRF.java:264-271) and that
+ * asm_psrf_finish_device applies to the row values -- evaluated in parallel on the device (the
+ * roundings are replayed as an integer scan while the running sum stays inside one binade).  Any doubles are
+ * accepted; negative and non-finite values take plain adds.  Host buffers. */
+int32_t asm_seq_sum(asm_ctx* ctx, const double* values, int64_t n, double* sum_out);
 /* asm_psrf_sums + asm_psrf_finish in one call on one GPU: everything converged2sided
  * (TreePSRF.java:141-158) needs from the device.  psrf_mean[0*C+1] is psrf1mean and
  * psrf_mean[1*C+0] is psrf2mean of the two-chain reference. */

@@ -28,6 +28,12 @@ int32_t asmh_trace_info_destroy(asmh_trace_info* ti);
 /* AutoStopMCMC.readLogLines (AutoStopMCMC.java:430-479) / readTreeLogLine (:486-538), one line at a time */
 int32_t asmh_read_log_line(asmh_trace_info* ti, int32_t chain, const char* line, int32_t* appended);
 int32_t asmh_read_tree_log_line(asmh_trace_info* ti, int32_t chain, const char* line, int32_t* appended);
+/* One cell of a trace log as readLogLines converts it (AutoStopMCMC.java:460-466): Double.parseDouble's grammar, 0.0
+ * where Java would throw NumberFormatException.  *is_number (may be NULL) says which of the two happened.  No GPU. */
+double asmh_parse_log_cell(const char* token, int32_t* is_number);
+/* Trees and log lines are staged on the host and uploaded, one copy per chain, when a criterion next asks for the
+ * context (asmh_ctx, asmh_criterion_converged); asmh_flush does it now. */
+int32_t asmh_flush(asmh_trace_info* ti);
 /* direct feeding, for callers that hold parsed data */
 int32_t asmh_set_taxon_count(asmh_trace_info* ti, int32_t n_taxa);
 int32_t asmh_add_tree(asmh_trace_info* ti, int32_t chain, const int32_t* left, const int32_t* right, int32_t root);

@@ -74,3 +74,67 @@ def test_synthetic_generators_are_reproducible():
     assert np.array_equal(df, dr)
     x = G.synth_ar1(1000, -1e4, 0.9, 5)
     assert np.array_equal(x, G.synth_ar1(1000, -1e4, 0.9, 5)) and abs(x.mean() + 1e4) < 5
+
+
+def _newick_of(left, right, root, offset=1):
+    """Child arrays -> Newick with integer labels (leaf number + offset), iteratively."""
+    out, stack = [], [(int(root), 0)]
+    while stack:
+        v, stage = stack.pop()
+        if left[v] < 0:
+            out.append(str(v + offset))
+        elif stage == 0:
+            out.append("(")
+            stack.append((v, 1))
+            stack.append((int(left[v]), 0))
+        elif stage == 1:
+            out.append(",")
+            stack.append((v, 2))
+            stack.append((int(right[v]), 0))
+        else:
+            out.append(")")
+    return "".join(out) + ";"
+
+
+@pytest.mark.parametrize("threads", [2, 5, 8])
+def test_parallel_encoder_hands_out_the_serial_ids(monkeypatch, threads):
+    # two-phase batch encoder (look-ups against the frozen dictionary on every core, insertions in first-seen order):
+    # the ids are those of the one-tree-at-a-time encoder, i.e. CladeDifference.traverse's numbering
+    n_taxa, n_trees = 60, 3000
+    l, r, root, _ = G.synth_tree_chain(n_taxa, n_trees, 1, 777, 2, 3.0)
+    l2, r2, root2, _ = G.synth_tree_chain(n_taxa, 700, 1, 778, 2, 3.0)
+    monkeypatch.setenv("ASM_ENCODER_THREADS", "1")
+    serial = A.Encoder(n_taxa)
+    ids_s = serial.add_topologies(l, r, root)
+    ids_s2 = serial.add_topologies(l2, r2, root2)
+    monkeypatch.setenv("ASM_ENCODER_THREADS", str(threads))
+    par = A.Encoder(n_taxa)
+    ids_p = par.add_topologies(l, r, root)
+    ids_p2 = par.add_topologies(l2, r2, root2)  # second call: the dictionary is warm, most clades are hits
+    assert np.array_equal(ids_s, ids_p) and np.array_equal(ids_s2, ids_p2)
+    assert serial.num_clades == par.num_clades
+    for cid in range(0, serial.num_clades, 101):
+        assert np.array_equal(serial.clade_leaves(cid), par.clade_leaves(cid))
+    assert np.array_equal(serial.bits(ids_s), par.bits(ids_p))  # asm_encode_bits is threaded the same way
+
+
+def test_newick_batch_matches_one_by_one(monkeypatch):
+    n_taxa, n_trees = 33, 1500
+    l, r, root, _ = G.synth_tree_chain(n_taxa, n_trees, 1, 4242, 2, 2.5)
+    newicks = [_newick_of(l[t], r[t], root[t]) for t in range(n_trees)]
+    one = A.Encoder(n_taxa)
+    ids_one = np.stack([one.add_newick(s, 1) for s in newicks])
+    monkeypatch.setenv("ASM_ENCODER_THREADS", "6")
+    batch = A.Encoder(n_taxa)
+    ids_batch = batch.add_newick_batch(newicks, 1)
+    assert np.array_equal(ids_one, ids_batch)
+    # and both equal the child-array path
+    topo = A.Encoder(n_taxa)
+    assert np.array_equal(topo.add_topologies(l, r, root), ids_batch)
+    # a malformed tree anywhere in a batch is reported with the reader's own error code
+    bad = list(newicks)
+    bad[1234] = "((1,2,3),(4,5));"
+    with pytest.raises(L.AsmGpuError) as ei:
+        A.Encoder(n_taxa).add_newick_batch(bad, 1)
+    assert ei.value.code in (L.ASM_E_UNSUPPORTED, L.ASM_E_INVALID)
+    assert A.Encoder(n_taxa).add_newick_batch([], 1).shape == (0, n_taxa - 1)

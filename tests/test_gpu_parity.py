@@ -379,3 +379,52 @@ def test_gelman_rubin_and_clade_difference_criteria(gpu, multi_chains):
                     ws += d
                     wq += d * d
                 assert s[c, k] == ws and q[c, k] == wq
+
+
+@pytest.mark.gpu
+def test_deliberate_deviations_of_the_host_mirror(gpu, small_chains):
+    """The places where the C++ mirror does NOT do what the Java does ("Deviations"), pinned so that they
+    stay deliberate."""
+    from asm_b200 import criteria as K
+    ch = small_chains
+    rng = np.random.default_rng(5)
+    # (1) TraceInfo.getMap with labels set and setUpMap never called: the reference dereferences tracesString == null
+    # (TraceInfo.java:57 -> :76, NullPointerException); the mirror reads the default "posterior,likelihood,prior".
+    ti = K.TraceInfo(2)
+    assert ti.getMap() == [1, 2, 3]                      # no labels yet: DEFAULT_MAP (:46), as in the reference
+    ti.readLogLine(0, "Sample\tprior\tposterior\tkappa\tlikelihood")
+    assert ti.getMap() == [2, 4, 1]
+    # (2) GelmanRubin with a single chain: no pair, true whatever `available` is -- same as the reference (:40-41)
+    one = K.TraceInfo(1)
+    one.addLogLine(0, [0.0, 1.0, 2.0])
+    g1 = K.GelmanRubin()
+    g1.setup(1, one)
+    assert g1.converged([0], 1) is True and g1.converged([0], 10**6) is True
+    # (3) GelmanRubin validates `available` against every chain before the first pair; the reference only throws when
+    # calcGRStat reaches a short chain (:56-58), so with chains 0/1 already above the threshold it returns false
+    # instead.  The runner never asks for more samples than the shortest chain holds (AutoStopMCMC.java:389-395).
+    t3 = K.TraceInfo(3)
+    for i in range(50):
+        t3.addLogLine(0, [float(i), rng.normal()])
+        t3.addLogLine(1, [float(i), 100.0 + rng.normal()])
+        if i < 10:
+            t3.addLogLine(2, [float(i), rng.normal()])
+    g3 = K.GelmanRubin(threshold=1.05)
+    g3.setup(3, t3)
+    assert g3.converged([0, 0, 0], 10) is False          # enough samples everywhere: chains 0 and 1 disagree
+    with pytest.raises(K.IllegalArgumentException):
+        g3.converged([0, 0, 0], 50)                      # the reference: false (pair (0,1) decides first)
+    # (4) CladeDifference counts [0, available) afresh on every call; the reference keeps counting from `current`
+    # (CladeDifference.java:47-53), so the two differ only if `available` ever decreases, which the runner never does.
+    tc = K.TraceInfo(2)
+    tc.setTaxonCount(ch.n_taxa)
+    for c in range(2):
+        l, r, root = ch.topo[c]
+        for i in range(300):
+            tc.addTree(c, l[i], r[i], int(root[i]))
+    cd = K.CladeDifference(threshold=0.25)
+    cd.setup(2, tc)
+    cd.converged([0, 0], 300)
+    cd.converged([0, 0], 120)                            # the reference would still report the 300-tree counts
+    _, mx120 = O.clade_difference_converged(ch.ts, 120, 0.25)
+    assert bits_equal(np.array([cd.lastValue]), np.array([mx120]))
