@@ -56,7 +56,6 @@ struct PsrfLayout {
 struct ChainTrees {
   uint64_t* d_bits = nullptr;  // [cap][ctx->words]
   int64_t n = 0, cap = 0;
-  int32_t top_word = 0;        // highest non-zero word of any stored row (scanned on the device at upload): the K extent
 };
 
 struct ChainTraces {
@@ -82,14 +81,13 @@ struct asm_ctx {
   cudaStream_t group_stream[kMaxGroups] = {}, group_stream2[kMaxGroups] = {};   // ESS chunk groups
   cudaEvent_t group_event[kMaxGroups] = {}, group_fork[kMaxGroups] = {}, group_join[kMaxGroups] = {};
   void* h_pinned = nullptr;            // small page-locked scratch for asynchronous counters
-  DevBuf top_word_dev;                 // scratch of the upload scan (ChainTrees::top_word)
-  int* h_top_word = nullptr;           // pinned
+  DevBuf top_word_dev;                 // highest non-zero word of the gathered rows (gather_f4_kernel -> rf_f4x2_kernel)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int32_t words = 0;  // stored row width of every chain (uint64 words)
   std::vector<ChainTrees> trees;
   std::vector<ChainTraces> traces;
   // scratch
-  DevBuf opnd_bits, opnd_i8, opnd_f4, nbits, S_pad, blk_meta, S_compact, psrf_rows, psrf_mean, misc, flush, ess_tr,
+  DevBuf opnd_bits, opnd_i8, opnd_f4, nbits, S_pad, blk_meta, S_compact, psrf_rows, psrf_vals, psrf_mean, misc, flush, ess_tr,
       ess_sls, ess_out, tile_counter, rf_out;
   PsrfLayout layout;
   std::vector<int2> meta_host;  // staging for tile metadata

@@ -70,17 +70,6 @@ __global__ void restride_kernel(const uint64_t* __restrict__ src, int src_words,
   }
 }
 
-// Highest non-zero word over rows [0, n_rows) of a [n_rows][words] bit matrix (0 if there is none).
-__global__ void __launch_bounds__(256) top_word_kernel(const uint64_t* __restrict__ bits, int words, int64_t n_rows,
-                                                        int* __restrict__ out) {
-  const int lane = threadIdx.x & 31;
-  int top = 0;
-  for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n_rows; r += (int64_t)gridDim.x * (blockDim.x >> 5))
-    for (int w = lane; w < words; w += 32)
-      if (bits[(size_t)r * words + w]) top = max(top, w);
-  top = __reduce_max_sync(0xffffffffu, top);
-  if (lane == 0 && top > 0) atomicMax(out, top);
-}
 
 __global__ void flush_kernel(uint4* p, size_t n, uint32_t v) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -155,31 +144,6 @@ static int32_t trees_upload_rows(asm_ctx* ctx, int32_t chain, int64_t at, int64_
   return ASM_OK;
 }
 
-// Enqueue the scan of rows [at, at + n) of `chain` for their highest non-zero word; trees_scan_finish (after the
-// caller's stream synchronisation) folds the result into the chain's K extent.
-static int32_t trees_scan_rows(asm_ctx* ctx, int32_t chain, int64_t at, int64_t n) {
-  if (n <= 0) return ASM_OK;
-  int32_t rc = asm_reserve(ctx, ctx->top_word_dev, sizeof(int));
-  if (rc != ASM_OK) return rc;
-  if (!ctx->h_top_word) ASM_CUDA(ctx, cudaMallocHost(&ctx->h_top_word, sizeof(int)));
-  ASM_CUDA(ctx, cudaMemsetAsync(ctx->top_word_dev.p, 0, sizeof(int), ctx->stream));
-  {
-    LaunchScope ls(ctx, ASM_K_MISC);
-    const int blocks = (int)std::min<int64_t>((n + 7) / 8, (int64_t)ctx->sm_count * 8);
-    top_word_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->trees[chain].d_bits + (size_t)at * ctx->words, ctx->words, n,
-                                                    (int*)ctx->top_word_dev.p);
-  }
-  ASM_CUDA(ctx, cudaGetLastError());
-  *ctx->h_top_word = 0;
-  ASM_CUDA(ctx, cudaMemcpyAsync(ctx->h_top_word, ctx->top_word_dev.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  return ASM_OK;
-}
-static void trees_scan_finish(asm_ctx* ctx, int32_t chain, bool replace) {
-  ChainTrees& t = ctx->trees[chain];
-  const int32_t v = ctx->h_top_word ? *ctx->h_top_word : 0;
-  t.top_word = replace ? v : std::max(t.top_word, v);
-}
-
 static int32_t trees_check(asm_ctx* ctx, int32_t chain, int64_t n_new, int32_t words, const void* bits) {
   if (chain < 0 || chain >= ctx->n_chains || n_new < 0 || words <= 0 || (n_new > 0 && !bits))
     return asm_fail(ctx, ASM_E_INVALID, "trees: bad argument (chain=%d n=%lld words=%d)", chain, (long long)n_new, words);
@@ -192,10 +156,7 @@ static int32_t trees_put(asm_ctx* ctx, int32_t chain, int64_t at, int64_t n_new,
   if (rc != ASM_OK) return rc;
   if ((rc = ensure_tree_capacity(ctx, chain, at + n_new, words)) != ASM_OK) return rc;
   if ((rc = trees_upload_rows(ctx, chain, at, n_new, words, bits, kind)) != ASM_OK) return rc;
-  if (ctx->h_top_word) *ctx->h_top_word = 0;
-  if ((rc = trees_scan_rows(ctx, chain, at, n_new)) != ASM_OK) return rc;
-  if (n_new > 0) ASM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the caller may free `bits` on return
-  trees_scan_finish(ctx, chain, at == 0);
+  if (n_new > 0) ASM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the caller may free or overwrite `bits` on return
   ctx->trees[chain].n = at + n_new;
   return ASM_OK;
 }
@@ -212,10 +173,7 @@ static int32_t trees_set_sharded(asm_ctx* ctx, int32_t chain, int64_t n, int32_t
                               cudaMemcpyHostToDevice)) != ASM_OK)
     return rc;
   if ((rc = comm_all_gather_u64_inplace(ctx, ctx->trees[chain].d_bits, (size_t)per * ctx->words)) != ASM_OK) return rc;
-  if (ctx->h_top_word) *ctx->h_top_word = 0;
-  if ((rc = trees_scan_rows(ctx, chain, 0, n)) != ASM_OK) return rc;
   ASM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  trees_scan_finish(ctx, chain, true);
   ctx->trees[chain].n = n;
   return ASM_OK;
 }
@@ -302,7 +260,7 @@ int32_t asm_destroy(asm_ctx* ctx) {
   for (auto& t : ctx->traces)
     if (t.d_vals) cudaFree(t.d_vals);
   DevBuf* bufs[] = {&ctx->opnd_bits, &ctx->opnd_i8, &ctx->opnd_f4, &ctx->nbits, &ctx->S_pad, &ctx->blk_meta,
-                    &ctx->S_compact, &ctx->psrf_rows, &ctx->psrf_mean, &ctx->misc, &ctx->flush, &ctx->ess_tr,
+                    &ctx->S_compact, &ctx->psrf_rows, &ctx->psrf_vals, &ctx->psrf_mean, &ctx->misc, &ctx->flush, &ctx->ess_tr,
                     &ctx->ess_sls, &ctx->ess_out, &ctx->tile_counter, &ctx->rf_out, &ctx->walk_dev, &ctx->ess_res, &ctx->f4_blk_dev, &ctx->f4_walk_dev, &ctx->top_word_dev, &ctx->ess_park};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
@@ -322,7 +280,6 @@ int32_t asm_destroy(asm_ctx* ctx) {
     if (ctx->group_join[k]) cudaEventDestroy(ctx->group_join[k]);
   }
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
-  if (ctx->h_top_word) cudaFreeHost(ctx->h_top_word);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return ASM_OK;
@@ -356,10 +313,7 @@ static int32_t trees_set_device_rank(asm_ctx* ctx, int32_t chain, int64_t n_tree
   if (ctx->rank == 0 && (rc = trees_upload_rows(ctx, chain, 0, n_trees, words, d_bits, cudaMemcpyDeviceToDevice)) != ASM_OK)
     return rc;
   if ((rc = comm_broadcast_u64(ctx, ctx->trees[chain].d_bits, (size_t)n_trees * ctx->words, 0)) != ASM_OK) return rc;
-  if (ctx->h_top_word) *ctx->h_top_word = 0;
-  if ((rc = trees_scan_rows(ctx, chain, 0, n_trees)) != ASM_OK) return rc;
   ASM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  trees_scan_finish(ctx, chain, true);
   ctx->trees[chain].n = n_trees;
   return ASM_OK;
 }
@@ -885,7 +839,16 @@ int32_t asm_psrf_last_layout(const asm_ctx* ctx, int64_t* padded_rows, int64_t* 
   if (!ctx) return ASM_E_INVALID;
   const asm_ctx* c0 = is_group(ctx) ? ctx->members[0] : ctx;
   if (padded_rows) *padded_rows = c0->layout.Tp;
-  if (padded_bits) *padded_bits = c0->layout.bits_used;
+  if (padded_bits) {
+    *padded_bits = c0->layout.bits_used;
+    if (c0->layout.bits_used < 0) {  // fp4: the K extent was found on the device by the gather (rf_f4.cu); fetch it now
+      int top = 0;
+      if (select_device(c0) != ASM_OK || !c0->top_word_dev.p || cudaStreamSynchronize(c0->stream) != cudaSuccess ||
+          cudaMemcpy(&top, c0->top_word_dev.p, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess)
+        return ASM_E_CUDA;
+      *padded_bits = (int64_t)(top + 1) * 64;
+    }
+  }
   if (tiles_total) *tiles_total = c0->layout.tiles_total;
   if (tiles_done) {
     *tiles_done = c0->layout.tiles_done;

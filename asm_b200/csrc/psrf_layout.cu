@@ -114,8 +114,10 @@ __global__ void __launch_bounds__(256) gather_i8_kernel(const __grid_constant__ 
 // even clade in the low nibble).  One source byte becomes one 32-bit word through a 256-entry table in shared
 // memory; one 64-bit word -> 32 bytes, two 16-byte stores per lane.
 __global__ void __launch_bounds__(256) gather_f4_kernel(const __grid_constant__ SegTableDev tab_, uint4* __restrict__ out,
-                                                         int W4, int32_t* __restrict__ nbits) {
+                                                         int W4, int32_t* __restrict__ nbits, int* __restrict__ top_word) {
   __shared__ uint32_t lut[256];
+  __shared__ int top_s;
+  if (threadIdx.x == 0) top_s = 0;
   {
     uint32_t v = 0;
 #pragma unroll
@@ -128,6 +130,7 @@ __global__ void __launch_bounds__(256) gather_f4_kernel(const __grid_constant__ 
   const int warps_per_block = blockDim.x >> 5;
   const int64_t Tp = tab->Tp;
   const int words = tab->words, delta = tab->delta;
+  int top = 0;  // highest non-zero word this lane has seen: the K extent of the contraction (rf_f4.cu)
   for (int64_t p = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); p < Tp;
        p += (int64_t)gridDim.x * warps_per_block) {
     const RowRef rr = locate_row(tab, p);
@@ -138,6 +141,7 @@ __global__ void __launch_bounds__(256) gather_f4_kernel(const __grid_constant__ 
     for (int w = lane; w < W4; w += 32) {
       const uint64_t v = (live && w < words) ? __ldg(src + w) : 0ULL;
       cnt += __popcll(v);
+      if (v) top = max(top, w);
       uint4 q[2];
       uint32_t* o = reinterpret_cast<uint32_t*>(q);
 #pragma unroll
@@ -148,6 +152,10 @@ __global__ void __launch_bounds__(256) gather_f4_kernel(const __grid_constant__ 
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     if (lane == 0) nbits[p] = cnt;
   }
+  top = __reduce_max_sync(0xffffffffu, top);
+  if (lane == 0 && top > 0) atomicMax(&top_s, top);
+  __syncthreads();
+  if (threadIdx.x == 0 && top_s > 0) atomicMax(top_word, top_s);  // one global atomic per block
 }
 
 __global__ void __launch_bounds__(256) max_bits_kernel(const int32_t* __restrict__ nbits, long long n, int* __restrict__ out) {
@@ -191,29 +199,40 @@ __global__ void __launch_bounds__(256) compact_kernel(const __grid_constant__ Co
   }
 }
 
-// One block per ordered chain pair (a, b).  Row value: TreePSRF.java:287-292.  The mean is the sum of the row values
-// in ascending row order, one rounding per add (TreePSRF.mean, TreePSRF.java:264-271), divided by the row count.
-// The order is kept and the chain of dependent adds is not: seq_sum.cuh evaluates the same roundings as an integer
-// scan over the block (plain DADDs only where the running sum changes binade).
-__global__ void __launch_bounds__(seqsum::kThreads) psrf_finish_kernel(const long long* __restrict__ S, int C, int n_rows,
-                                                                        double* __restrict__ psrf_rows,
-                                                                        double* __restrict__ psrf_mean) {
-  __shared__ seqsum::Shared sh;
-  const int a = blockIdx.x / C, b = blockIdx.x % C;
-  const double sum = seqsum::block_sum(sh, n_rows, [&](int r) {
-    const long long* row = S + ((size_t)a * n_rows + r) * C;
+// Row values (TreePSRF.java:287-292) of every ordered chain pair, one thread per row (a, r) of the table:
+// vals[a*C+b][r] for the sums below and, when the caller asked for the rows, psrf_rows[a][r][b].
+__global__ void __launch_bounds__(256) psrf_rows_kernel(const long long* __restrict__ S, int C, int n_rows,
+                                                         double* __restrict__ vals, double* __restrict__ psrf_rows) {
+  const long long total = (long long)C * n_rows;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int a = (int)(i / n_rows), r = (int)(i % n_rows);
+    const long long* row = S + (size_t)i * C;
     const double varIn = (double)row[a];
-    const double varBetween = (double)row[b];
-    double psrf;
-    if (varIn != 0) {
-      psrf = sqrt(varBetween / varIn);
-    } else {
-      psrf = sqrt(varBetween);
+#pragma unroll 4
+    for (int b = 0; b < C; b++) {
+      const double varBetween = (double)row[b];
+      double psrf;
+      if (varIn != 0) {
+        psrf = sqrt(varBetween / varIn);
+      } else {
+        psrf = sqrt(varBetween);
+      }
+      vals[((size_t)a * C + b) * n_rows + r] = psrf;
+      if (psrf_rows) psrf_rows[(size_t)i * C + b] = psrf;
     }
-    if (psrf_rows) psrf_rows[((size_t)a * n_rows + r) * C + b] = psrf;
-    return psrf;
-  });
-  if (threadIdx.x == 0) psrf_mean[a * C + b] = sum / (double)n_rows;  // 0/0 = NaN for no rows, as in Java
+  }
+}
+
+// One block per ordered chain pair (a, b).  The mean is the sum of the row values in ascending row order, one
+// rounding per add (TreePSRF.mean, TreePSRF.java:264-271), divided by the row count.  The order is kept and the
+// chain of dependent adds is not: seq_sum.cuh evaluates the same roundings as an integer scan over the block (plain
+// DADDs only where the running sum changes binade).
+__global__ void __launch_bounds__(seqsum::kThreads) psrf_mean_kernel(const double* __restrict__ vals, int n_rows,
+                                                                      double* __restrict__ psrf_mean) {
+  __shared__ seqsum::Shared sh;
+  const double* v = vals + (size_t)blockIdx.x * n_rows;
+  const double sum = seqsum::block_sum(sh, n_rows, [&](int k) { return v[k]; });
+  if (threadIdx.x == 0) psrf_mean[blockIdx.x] = sum / (double)n_rows;  // 0/0 = NaN for no rows, as in Java
 }
 
 // The same walk over doubles in memory (asm_seq_sum).
@@ -421,10 +440,13 @@ int32_t psrf_gather_f4(asm_ctx* ctx) {
   SegTableDev tab;
   if ((rc = psrf_prepare(ctx, tab)) != ASM_OK) return rc;
   if ((rc = psrf_build_f4_blocks(ctx)) != ASM_OK) return rc;
+  if ((rc = asm_reserve(ctx, ctx->top_word_dev, sizeof(int))) != ASM_OK) return rc;
+  ASM_CUDA(ctx, cudaMemsetAsync(ctx->top_word_dev.p, 0, sizeof(int), ctx->stream));
   {
     LaunchScope ls(ctx, ASM_K_GATHER);
     int blocks = (int)std::min<int64_t>((L.Tp + 7) / 8, (int64_t)ctx->sm_count * 16);
-    gather_f4_kernel<<<blocks, 256, 0, ctx->stream>>>(tab, (uint4*)ctx->opnd_f4.p, L.pitch4 / 32, (int32_t*)ctx->nbits.p);
+    gather_f4_kernel<<<blocks, 256, 0, ctx->stream>>>(tab, (uint4*)ctx->opnd_f4.p, L.pitch4 / 32, (int32_t*)ctx->nbits.p,
+                                                     (int*)ctx->top_word_dev.p);
   }
   ASM_CUDA(ctx, cudaGetLastError());
   return ASM_OK;
@@ -484,9 +506,17 @@ int32_t psrf_finish(asm_ctx* ctx, const int64_t* d_S, int32_t n_rows, double* ps
     if ((rc = asm_reserve(ctx, ctx->psrf_rows, rows_bytes)) != ASM_OK) return rc;
     d_rows = (double*)ctx->psrf_rows.p;
   }
+  const size_t vals_bytes = sizeof(double) * (size_t)C * (size_t)C * (size_t)n_rows;
+  if ((rc = asm_reserve(ctx, ctx->psrf_vals, vals_bytes ? vals_bytes : 8)) != ASM_OK) return rc;
+  if (n_rows > 0) {
+    LaunchScope ls(ctx, ASM_K_PSRF_FINISH);
+    const int64_t total = (int64_t)C * n_rows;
+    const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)ctx->sm_count * 8);
+    psrf_rows_kernel<<<blocks, 256, 0, ctx->stream>>>((const long long*)d_S, C, n_rows, (double*)ctx->psrf_vals.p, d_rows);
+  }
   {
     LaunchScope ls(ctx, ASM_K_PSRF_FINISH);
-    psrf_finish_kernel<<<C * C, seqsum::kThreads, 0, ctx->stream>>>((const long long*)d_S, C, n_rows, d_rows, (double*)ctx->psrf_mean.p);
+    psrf_mean_kernel<<<C * C, seqsum::kThreads, 0, ctx->stream>>>((const double*)ctx->psrf_vals.p, n_rows, (double*)ctx->psrf_mean.p);
   }
   ASM_CUDA(ctx, cudaGetLastError());
   ASM_CUDA(ctx, cudaMemcpyAsync(psrf_mean_host, ctx->psrf_mean.p, sizeof(double) * (size_t)C * C, cudaMemcpyDeviceToHost,

@@ -116,7 +116,7 @@ struct WorkQueueF4 {
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsF, 1)
-rf_f4x2_kernel(const __grid_constant__ CUtensorMap tm, int nkb, int last_kk, const int* __restrict__ nbits,
+rf_f4x2_kernel(const __grid_constant__ CUtensorMap tm, const int* __restrict__ top_word, const int* __restrict__ nbits,
                const int2* __restrict__ blk_rows, const int2* __restrict__ blk_cols, int nR, int nC, long long n_slots,
                const uint32_t* __restrict__ walk_tiles, int shard_index, int shard_count,
                unsigned long long* __restrict__ slot_counter, unsigned long long* __restrict__ S, int C, int dbg) {
@@ -136,8 +136,12 @@ rf_f4x2_kernel(const __grid_constant__ CUtensorMap tm, int nkb, int last_kk, con
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = (int)cluster_ctarank();
-  // K extent (kernel parameters, so that they live in uniform registers): nkb whole 128-byte K blocks up to the highest
-  // non-zero word of any stored row; the last block issues `last_kk` of its four K = 64 instructions
+  // K extent: nkb whole 128-byte K blocks up to the highest non-zero word of any gathered row (found by the gather
+  // kernel that ran before this one, so the host never waits for it); the last block issues `last_kk` of its four
+  // K = 64 instructions
+  const int used_bits = (__ldg(top_word) + 1) * 64;
+  const int nkb = (used_bits + 2 * kBlockK - 1) / (2 * kBlockK);
+  const int last_kk = (used_bits - (nkb - 1) * 2 * kBlockK + 63) / 64;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages2; s++) {
@@ -508,17 +512,11 @@ int32_t rf_f4_sums(asm_ctx* ctx, asm_shard shard) {
   const int clusters = (int)std::min<long long>(std::max<long long>(L.tiles_done / 2, 1), ctx->sm_count / 2);
   if (clusters <= 0 || n_slots == 0) return ASM_OK;
   const int2* blk = (const int2*)ctx->f4_blk_dev.p;
-  // K extent: the highest non-zero word over every stored row (scanned at upload, ChainTrees::top_word)
-  int top = 0;
-  for (const ChainTrees& t : ctx->trees) top = std::max(top, t.top_word);
-  const int used_bits = (top + 1) * 64;
-  const int nkb = (used_bits + 2 * kBlockK - 1) / (2 * kBlockK);
-  const int last_kk = (used_bits - (nkb - 1) * 2 * kBlockK + 63) / 64;
-  L.bits_used = (int64_t)(nkb - 1) * 2 * kBlockK + last_kk * 64;
+  L.bits_used = -1;  // known on the device only (gather_f4_kernel's top word): asm_psrf_last_layout reads it back
   {
     LaunchScope ls(ctx, ASM_K_RF_I8);
     rf_f4x2_kernel<<<2 * clusters, kThreadsF, kSmemBytesF, ctx->stream>>>(
-        tm, nkb, last_kk, (const int*)ctx->nbits.p, blk, blk + ctx->f4_nR, ctx->f4_nR, ctx->f4_nC, n_slots,
+        tm, (const int*)ctx->top_word_dev.p, (const int*)ctx->nbits.p, blk, blk + ctx->f4_nR, ctx->f4_nR, ctx->f4_nC, n_slots,
         (const uint32_t*)ctx->f4_walk_dev.p, shard.shard_index, shard.shard_count, (unsigned long long*)ctx->tile_counter.p,
         (unsigned long long*)ctx->S_pad.p, L.C, getenv("ASM_F4_DEBUG") ? atoi(getenv("ASM_F4_DEBUG")) : 0);
   }

@@ -76,39 +76,27 @@ SEQ_HD double from_binade(int e, unsigned long long M) {  // M in [2^52, 2^53)
 }
 
 // One element against a running sum in binade e.  false: it needs the plain add.  Otherwise seg = what it does to
-// M, bound = an upper bound of that (q + 1, or 0 for an element that cannot change M).
+// M, bound = an upper bound of that (q + 1, or 0 for an element that cannot change M).  Branch-free: eight of these
+// per thread run interleaved.
 SEQ_HD bool element(double v, int e, Seg* seg, unsigned long long* bound) {
   const unsigned long long b = bits_of(v);
   const int ef = (int)((b >> 52) & 0x7ff);
-  unsigned long long m = b & (kTwo52 - 1);
-  seg->d0 = seg->d1 = 0;
-  *bound = 0;
-  if (ef == 0 && m == 0) return true;  // +0.0 and -0.0 leave a positive sum as it is
-  if ((b >> 63) || ef == 0x7ff) return false;
-  int ek = -1022;
-  if (ef != 0) {
-    m |= kTwo52;
-    ek = ef - 1023;
-  }
-  if (ek > e) return false;
-  const int d = e - ek;  // v = m * 2^-d ulps
-  if (d >= 64) return true;  // far below half an ulp
-  const unsigned long long q = m >> d;
-  *bound = q + 1;
-  if (d == 0) {
-    seg->d0 = seg->d1 = q;
-    return true;
-  }
-  const unsigned long long rem = m & ((1ull << d) - 1), half = 1ull << (d - 1);
-  if (rem > half) {
-    seg->d0 = seg->d1 = q + 1;
-  } else if (rem < half) {
-    seg->d0 = seg->d1 = q;
-  } else {  // exact tie: to the even neighbour
-    seg->d0 = q + (q & 1ull);
-    seg->d1 = q + ((q & 1ull) ^ 1ull);
-  }
-  return true;
+  const unsigned long long frac = b & (kTwo52 - 1);
+  const bool zero = (b << 1) == 0;                       // +0.0 and -0.0 leave a positive sum as it is
+  const bool bad = (b >> 63) != 0 || ef == 0x7ff;        // negative, infinite, NaN
+  const unsigned long long m = ef ? (frac | kTwo52) : frac;
+  const int ek = ef ? ef - 1023 : -1022;
+  const int d = e - ek;                                  // v = m * 2^-d ulps of the running sum
+  const bool small = zero || d >= 64;                    // far below half an ulp (m < 2^53)
+  const int dc = d < 0 ? 0 : (d > 63 ? 63 : d);
+  const unsigned long long q = m >> dc;
+  const unsigned long long low = dc ? (m << (64 - dc)) : 0ull;  // the bits shifted out, left-aligned
+  const unsigned long long half = 1ull << 63;
+  const unsigned long long up = low > half ? 1ull : 0ull, tie = low == half ? 1ull : 0ull;
+  seg->d0 = small ? 0ull : q + (up | (tie & q & 1ull));          // exact tie: to the even neighbour
+  seg->d1 = small ? 0ull : q + (up | (tie & ~q & 1ull));
+  *bound = small ? 0ull : q + 1;
+  return zero || (!bad && d >= 0);                       // d < 0: the element is above the binade
 }
 
 SEQ_HD unsigned long long sat_add(unsigned long long a, unsigned long long b) {
@@ -116,28 +104,36 @@ SEQ_HD unsigned long long sat_add(unsigned long long a, unsigned long long b) {
   return s > kBoundCap ? kBoundCap : s;
 }
 
+// ---- shape of the block-wide walk (shared with the host check, tests/c/seq_sum_check.cpp)
+constexpr int kThreads = 512, kPerThread = 4, kTile = kThreads * kPerThread, kWarps = kThreads / 32;
+constexpr int kPrelude = 64;   // the first adds cross a binade almost every time: plain
+constexpr int kPlainRun = 32;  // after a run that made little progress, this many plain adds before trying again
+constexpr int kMinWindow = 256;
+// thread t's 4 values sit 5 doubles apart in shared memory (odd stride: no bank conflicts wherever the run starts)
+SEQ_HD int pad(int k) { return k + (k >> 2); }
+// A run is cut where the sum may leave its binade, and with values of similar size that happens when the number of
+// elements added so far has doubled: looking further ahead than that decomposes elements against the wrong binade.
+SEQ_HD int window_of(int consumed) {
+  return consumed < kMinWindow ? kMinWindow : (consumed > kTile ? kTile : consumed);
+}
+
 }  // namespace seqsum
 
 #if defined(__CUDACC__)
 namespace seqsum {
 
-constexpr int kThreads = 256, kPerThread = 8, kTile = kThreads * kPerThread;
-constexpr int kPrelude = 64;   // the first adds cross a binade almost every time: plain
-constexpr int kPlainRun = 32;  // after a run that made little progress, this many plain adds before trying again
-__device__ __forceinline__ int pad(int k) { return k + (k >> 3); }  // thread t's 8 values: stride 9 doubles in shared memory
-
 struct Shared {
-  double vals[kTile + kTile / 8];
-  unsigned long long warp_u64[kThreads / 32];
-  Seg warp_seg[kThreads / 32];
-  int warp_cut[kThreads / 32];
+  double vals[kTile + kTile / 4 + 4];
+  unsigned long long warp_u64[kWarps];
+  Seg warp_seg[kWarps];
+  int warp_cut[kWarps];
   double s;
   int lo;
 };
 
 // Sum of value(0) .. value(n-1) in that order, every add rounded as a scalar loop would; all kThreads threads of
 // the block call it, the result is returned to every thread.  value(k) is evaluated once per element (by some
-// thread, in no particular order) and may have side effects for that k (storing the row value).
+// thread, a tile ahead of its use) and may have side effects for that k.
 template <class Value>
 __device__ double block_sum(Shared& sh, int n, Value&& value) {
   const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -145,10 +141,25 @@ __device__ double block_sum(Shared& sh, int n, Value&& value) {
     sh.s = 0.0;
     sh.lo = 0;
   }
+  double ahead[kPerThread];  // this thread's share of the next tile, in flight while the current one is summed
+#pragma unroll
+  for (int j = 0; j < kPerThread; j++) {
+    const int k = j * kThreads + tid;
+    ahead[j] = k < n ? value(k) : 0.0;
+  }
   for (int t0 = 0; t0 < n; t0 += kTile) {
     const int tn = min(kTile, n - t0);
     __syncthreads();  // the previous tile's values are consumed
-    for (int k = tid; k < tn; k += kThreads) sh.vals[pad(k)] = value(t0 + k);
+#pragma unroll
+    for (int j = 0; j < kPerThread; j++) {
+      const int k = j * kThreads + tid;
+      if (k < tn) sh.vals[pad(k)] = ahead[j];
+    }
+#pragma unroll
+    for (int j = 0; j < kPerThread; j++) {
+      const int k = t0 + kTile + j * kThreads + tid;
+      ahead[j] = k < n ? value(k) : 0.0;
+    }
     __syncthreads();
     if (tid == 0) {
       double s = sh.s;
@@ -166,10 +177,11 @@ __device__ double block_sum(Shared& sh, int n, Value&& value) {
       int e = 0;
       unsigned long long M = 0;
       const bool integer_path = binade_of(s, &e, &M);  // uniform
-      int cut = lo;  // first element of [lo, tn) that does not go the integer way
+      int cut = lo;  // first element of [lo, wn) that does not go the integer way
       Seg mine{0, 0};
       if (integer_path) {
-        // this thread's elements: lo + tid*8 .. +7, i.e. the run starts at `lo`, not at a multiple of 8
+        const int wn = min(tn, lo + window_of(t0 + lo));
+        // this thread's elements: lo + tid*4 .. +3, i.e. the run starts at `lo`, not at a multiple of 4
         const int first = lo + tid * kPerThread;
         Seg segs[kPerThread];
         unsigned long long bnd[kPerThread];
@@ -178,10 +190,8 @@ __device__ double block_sum(Shared& sh, int n, Value&& value) {
 #pragma unroll
         for (int i = 0; i < kPerThread; i++) {
           const int k = first + i;
-          ok[i] = false;
-          bnd[i] = 0;
-          segs[i] = Seg{0, 0};
-          if (k < tn) ok[i] = element(sh.vals[pad(k)], e, &segs[i], &bnd[i]);
+          const double v = k < wn ? sh.vals[pad(k)] : 0.0;  // +0.0: no change, no bound, never a cut
+          ok[i] = element(v, e, &segs[i], &bnd[i]);
           local = sat_add(local, bnd[i]);  // bnd <= 2^53
         }
         // exclusive prefix of the bounds over the threads; saturating adds of non-negative terms = min(sum, cap)
@@ -196,22 +206,20 @@ __device__ double block_sum(Shared& sh, int n, Value&& value) {
         __syncthreads();
         unsigned long long run = lane ? prev : 0ull;
         for (int w = 0; w < warp; w++) run = sat_add(run, sh.warp_u64[w]);
-        int my_cut = tn;
+        int my_cut = wn;
 #pragma unroll
         for (int i = 0; i < kPerThread; i++) {
           const int k = first + i;
-          if (k < tn && my_cut == tn) {
-            run = sat_add(run, bnd[i]);
-            if (!ok[i] || M + run >= kTwo53) my_cut = k;
-          }
+          run = sat_add(run, bnd[i]);
+          if (k < my_cut && (!ok[i] || M + run >= kTwo53)) my_cut = k;  // k ascends: the first hit stays
         }
-        if (first >= tn) my_cut = tn;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) my_cut = min(my_cut, __shfl_xor_sync(0xffffffffu, my_cut, o));
         if (lane == 0) sh.warp_cut[warp] = my_cut;
         __syncthreads();
-        cut = tn;
-        for (int w = 0; w < kThreads / 32; w++) cut = min(cut, sh.warp_cut[w]);
+        cut = wn;
+#pragma unroll
+        for (int w = 0; w < kWarps; w++) cut = min(cut, sh.warp_cut[w]);
         // fold this thread's elements below the cut, then the threads in order
 #pragma unroll
         for (int i = 0; i < kPerThread; i++)
@@ -231,7 +239,8 @@ __device__ double block_sum(Shared& sh, int n, Value&& value) {
         int next = cut;
         if (integer_path && cut > lo) {
           Seg all = sh.warp_seg[0];
-          for (int w = 1; w < kThreads / 32; w++) all = then(all, sh.warp_seg[w]);
+          const int used = (cut - lo + 32 * kPerThread - 1) / (32 * kPerThread);  // warps with elements below the cut
+          for (int w = 1; w < used; w++) all = then(all, sh.warp_seg[w]);
           s1 = from_binade(e, M + ((M & 1ull) ? all.d1 : all.d0));
         }
         // the element that ended the run, and more of them if the run was short (negative values, a sum that is

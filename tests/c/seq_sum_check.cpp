@@ -3,8 +3,8 @@
 // branch (exact ties in both parities, zeros, subnormals, binade crossings on every add, huge and tiny values,
 // negative / non-finite values that must fall back to the plain add).  Test infrastructure; no GPU.
 //
-// The walk below is the one the kernel does (prelude, tiles, conservative cut, ordered fold, plain adds after a
-// short run) with its 256 threads folded one after the other; the arithmetic is the header's own.
+// The walk below is the one the kernel does (prelude, tiles, look-ahead window, conservative cut, ordered fold, plain adds
+// after a short run) with its threads folded one after the other; the arithmetic is the header's own.
 #include <cinttypes>
 #include <cmath>
 #include <cstdio>
@@ -24,7 +24,7 @@ static double plain_sum(const std::vector<double>& v) {
 
 static long g_integer_adds = 0, g_plain_adds = 0;
 
-static double walked_sum(const std::vector<double>& v, int threads, int per_thread, int prelude, int plain_run) {
+static double walked_sum(const std::vector<double>& v, int threads, int per_thread, int prelude, int plain_run, bool windowed) {
   const int n = (int)v.size(), tile = threads * per_thread;
   double s = 0.0;
   for (int t0 = 0; t0 < n; t0 += tile) {
@@ -45,8 +45,9 @@ static double walked_sum(const std::vector<double>& v, int threads, int per_thre
       if (integer_path) {
         // per thread: bounds and cut, with the exclusive prefix of the earlier threads
         unsigned long long run = 0;
-        cut = tn;
-        for (int k = lo; k < tn; k++) {
+        const int wn = windowed ? std::min(tn, lo + window_of(t0 + lo)) : tn;  // the kernel looks ahead this far
+        cut = wn;
+        for (int k = lo; k < wn; k++) {
           Seg sg;
           unsigned long long b;
           const bool ok = element(vals[k], e, &sg, &b);
@@ -92,9 +93,11 @@ static double walked_sum(const std::vector<double>& v, int threads, int per_thre
 static int g_fail = 0, g_cases = 0;
 static void check(const char* name, const std::vector<double>& v) {
   const double want = plain_sum(v);
-  const int shapes[][4] = {{256, 8, 64, 32}, {4, 2, 0, 1}, {32, 8, 3, 5}, {1, 1, 0, 1}};
+  // the kernel's own shape first (with its look-ahead window), then shapes that stress the fold and the tiling
+  const int shapes[][5] = {{kThreads, kPerThread, kPrelude, kPlainRun, 1}, {256, 8, 64, 32, 0}, {4, 2, 0, 1, 0}, {32, 8, 3, 5, 0},
+                           {1, 1, 0, 1, 0}};
   for (const auto& sh : shapes) {
-    const double got = walked_sum(v, sh[0], sh[1], sh[2], sh[3]);
+    const double got = walked_sum(v, sh[0], sh[1], sh[2], sh[3], sh[4] != 0);
     g_cases++;
     if (bits_of(got) != bits_of(want) && !(got != got && want != want)) {
       g_fail++;
@@ -205,7 +208,7 @@ int main() {
     std::vector<double> v(28285);
     for (auto& x : v) x = std::sqrt((double)(1000000 + rng() % 400000) / (double)(1000000 + rng() % 400000));
     g_integer_adds = g_plain_adds = 0;
-    walked_sum(v, 256, 8, 64, 32);
+    walked_sum(v, kThreads, kPerThread, kPrelude, kPlainRun, true);
     std::printf("psrf-like n=28285: %ld integer-path adds, %ld plain adds\n", g_integer_adds, g_plain_adds);
   }
   return g_fail ? 1 : 0;

@@ -428,3 +428,38 @@ def test_deliberate_deviations_of_the_host_mirror(gpu, small_chains):
     cd.converged([0, 0], 120)                            # the reference would still report the 300-tree counts
     _, mx120 = O.clade_difference_converged(ch.ts, 120, 0.25)
     assert bits_equal(np.array([cd.lastValue]), np.array([mx120]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("words,top", [(1, 0), (4, 0), (4, 3), (8, 4), (8, 7), (12, 8), (20, 9), (44, 42), (44, 43), (48, 44)])
+def test_fp4_k_extent_follows_the_highest_used_word(gpu, words, top):
+    """The fp4 kernel contracts over K blocks of 256 clades and issues only the K = 64 instructions up to the highest
+    non-zero word of the gathered rows (found on the device by the gather, read on the device by the kernel): stored
+    width `words`, bits only in words <= top, in particular at both ends of a K block (rf_f4.cu)."""
+    rng = np.random.default_rng(100 * words + top)
+    C, n = 2, 300
+    bits = []
+    for c in range(C):
+        b = np.zeros((n, words), dtype=np.uint64)
+        b[:, :top + 1] = rng.integers(0, 2 ** 63, size=(n, top + 1), dtype=np.uint64) & rng.integers(0, 2 ** 63, size=(n, top + 1), dtype=np.uint64)
+        b[:, top] |= np.uint64(1) << np.uint64(63 if c else 0)   # the top word is in use, at its first / last bit
+        bits.append(b)
+    want = np.zeros((C, n, C), dtype=np.int64)
+    for a in range(C):
+        for c in range(C):
+            d = np.bitwise_count(bits[a][:, None, :] ^ bits[c][None, :, :]).sum(-1, dtype=np.int64)
+            want[a, :, c] = ((d + 1) ** 2).sum(axis=1)
+    with gpu.GpuContext(C) as ctx:
+        for c in range(C):
+            ctx.trees_set(c, bits[c])
+        assert np.array_equal(ctx.psrf_sums([0, 0], 0, n, 1, gpu.ASM_RF_FP4), want)
+        assert ctx.last_layout()["padded_bits"] == (top + 1) * 64
+        # a shorter evaluation whose rows stop using the top word: the extent shrinks with the gathered rows
+        if top > 0:
+            for c in range(C):
+                bits[c][:100, top] = 0
+                ctx.trees_set(c, bits[c])
+            got = ctx.psrf_sums([0, 0], 0, 100, 1, gpu.ASM_RF_FP4)
+            assert np.array_equal(got, ctx.psrf_sums([0, 0], 0, 100, 1, gpu.ASM_RF_POPC))
+            ctx.psrf_sums([0, 0], 0, 100, 1, gpu.ASM_RF_FP4)
+            assert ctx.last_layout()["padded_bits"] <= top * 64
