@@ -79,6 +79,7 @@ SIGNATURES = {
     "asm_psrf_last_layout": (_i32, [_p, _i64p, _i64p, _i64p, _i64p]),
     "asm_encoder_create": (_i32, [C.POINTER(_p), _i32]),
     "asm_seq_sum": (_i32, [_p, _p, _i64, _p]),
+    "asm_bind_thread_near_device": (_i32, [_i32]),
     "asm_encoder_destroy": (_i32, [_p]),
     "asm_encoder_add_topologies": (_i32, [_p, _i64, _p, _p, _p, _p]),
     "asm_encoder_add_newick": (_i32, [_p, C.c_char_p, _i32, _p]),

@@ -8,6 +8,8 @@
 #include <new>
 #include <vector>
 
+#include <sched.h>
+
 #include "asm_internal.h"
 
 static thread_local std::string g_create_err;
@@ -189,6 +191,57 @@ int32_t asm_device_count(void) {
     return 0;
   }
   return n;
+}
+
+int32_t asm_bind_thread_near_device(int32_t device) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) {
+    cudaGetLastError();
+    return ASM_E_INVALID;
+  }
+  char bdf[32] = {0};
+  if (cudaDeviceGetPCIBusId(bdf, (int)sizeof bdf, device) != cudaSuccess) {
+    cudaGetLastError();
+    return ASM_E_CUDA;
+  }
+  for (char* c = bdf; *c; c++) *c = (char)tolower((unsigned char)*c);
+  auto slurp = [](const std::string& path) {
+    std::string out;
+    if (FILE* f = fopen(path.c_str(), "r")) {
+      char buf[4096];
+      const size_t k = fread(buf, 1, sizeof buf - 1, f);
+      buf[k] = 0;
+      out = buf;
+      fclose(f);
+    }
+    return out;
+  };
+  const std::string dir = std::string("/sys/bus/pci/devices/") + bdf + "/";
+  const std::string node = slurp(dir + "numa_node");
+  if (node.empty() || atoi(node.c_str()) < 0) return 0;            // the platform does not say (e.g. a VM): nothing to do
+  const std::string online = slurp("/sys/devices/system/node/online");
+  if (online.find_first_of(",-") == std::string::npos) return 0;   // a single NUMA node
+  const std::string list = slurp(dir + "local_cpulist");
+  cpu_set_t set;
+  CPU_ZERO(&set);
+  int count = 0;
+  for (const char* p = list.c_str(); *p;) {  // "0-15,32-47"
+    if (!isdigit((unsigned char)*p)) {
+      p++;
+      continue;
+    }
+    char* end = nullptr;
+    long a = strtol(p, &end, 10), b = a;
+    if (*end == '-') b = strtol(end + 1, &end, 10);
+    for (long c = a; c <= b && c < CPU_SETSIZE; c++) {
+      CPU_SET((int)c, &set);
+      count++;
+    }
+    p = end;
+  }
+  if (count == 0) return 0;
+  if (sched_setaffinity(0, sizeof set, &set) != 0) return 0;       // not permitted (cgroup cpuset): leave the thread where it is
+  return count;
 }
 
 int32_t asm_create(asm_ctx** out, int32_t device, int32_t n_chains) {

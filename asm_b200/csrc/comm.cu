@@ -110,6 +110,7 @@ struct WorkerPool {
       const int dev = members[(size_t)i]->device;
       me->th = std::thread([me, dev] {
         cudaSetDevice(dev);
+        asm_bind_thread_near_device(dev);  // the staging this thread allocates and the copies it drives stay on the GPU's node
         std::unique_lock<std::mutex> lk(me->mu);
         for (;;) {
           me->cv.wait(lk, [me] { return me->pending || me->quit; });

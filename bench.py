@@ -91,7 +91,8 @@ def tensor_peak(live, peaks, kind, sustained):
     cands = [(g[k][which], k) for k in keys if isinstance(g.get(k), dict)]
     if cands:
         v, k = max(cands)
-        return v, f"cuBLASLt {k} GEMM 8192^3 through torch, {which}, measured in this run (tools/peaks.py)"
+        n = g[k].get("n", g.get("n", 8192))
+        return v, f"cuBLASLt {k} GEMM through torch (best of the sizes tried; burst at {n}^3), {which}, measured in this run (tools/peaks.py)"
     mult = 4.0 if kind == "fp4" else 2.0
     base = peaks["bf16_tflops_sustained"] if sustained else peaks["bf16_tflops"]
     return mult * base, (f"{mult:g} x bf16 {which} of {peaks['source']} (DERIVED: the {kind} GEMM could not be measured here: "
@@ -258,6 +259,7 @@ class Job:
         self.local = int(os.environ.get("LOCAL_RANK", "0"))
         self.dist = None
         self.group_devices = None
+        self.numa_cpus = 0
         if self.world > 1:
             import torch
             import torch.distributed as dist
@@ -266,6 +268,10 @@ class Job:
             self.dist = dist
             self.n_gpus = self.world
             self.launch = "torchrun: one process per GPU, in-library NCCL communicator (asm_comm_init_rank)"
+            # host buffers this rank allocates and pins from here on sit on its GPU's NUMA node (a no-op where the
+            # platform shows a single node)
+            from asm_b200 import _lib as L
+            self.numa_cpus = int(L.lib().asm_bind_thread_near_device(self.local))
         elif n_gpus > 1:
             self.group_devices = list(range(n_gpus))
             self.n_gpus = n_gpus
@@ -626,6 +632,8 @@ def bench_ess(job, args, steps, warmup, live):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"cfg3: {n_tr} traces x {n} samples per GPU, AR(1) phi in {PHIS}, mu in {MUS}, max_lag 2000",
                        "l2": "inputs (8 GB per GPU and step) larger than L2", "launch": job.launch,
+                       "host_binding": (f"rank bound to the {job.numa_cpus} CPUs local to its GPU before allocating" if job.numa_cpus
+                                        else "none (one NUMA node, or the platform hides the topology)"),
                        "timing": "CUDA events on the library stream(s) per step, max over GPUs"},
             "clocks": clocks, "gpu_launches": int(round(launches)), "roofline": roof,
             "e2e": {"value": world * n_tr * n / (e_ms * 1e-3), "unit": "trace-samples/s",

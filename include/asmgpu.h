@@ -61,6 +61,14 @@ int32_t asm_device_count(void);
  * TraceInfo.java:31-41; criteria setup(nChains, traceInfo), MCMCConvergenceCriterion.java:20). */
 int32_t asm_create(asm_ctx** out, int32_t device, int32_t n_chains);
 int32_t asm_destroy(asm_ctx* ctx);
+/* Host placement for the upload paths: bind the CALLING thread to the CPUs that are local to CUDA device `device`
+ * (the local_cpulist of its PCI function in sysfs), so that buffers the thread allocates, fills and pins afterwards
+ * sit on the GPU's own NUMA node -- with 8 GPUs on two sockets the 8 GB trace uploads of asm_ess_batch otherwise
+ * cross the socket interconnect.  Returns the number of CPUs bound to, 0 where there is nothing to do (one NUMA node,
+ * no sysfs entry, a virtual machine that hides the topology), < 0 on error.  The worker threads of asm_create_multi
+ * call it for their own device; a one-process-per-GPU launcher calls it once per rank before it allocates
+ * (AutoStopMCMC's chain threads, AutoStopMCMC.java:188-214, would call it where they create their log buffers). */
+int32_t asm_bind_thread_near_device(int32_t device);
 
 /* ---- more than one GPU ---------------------------------------------------------------------------------------
  * The reference calls its criteria from ONE thread of ONE process (LogWatcherThread, AutoStopMCMC.java:214,

@@ -21,6 +21,9 @@ final class AsmGpuNative {
     }
 
     static final MethodHandle asm_create = h("asm_create", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT));
+    /** asm_create_multi(&ctx, devices[], n_devices, n_chains): one context over several GPUs of the box, driven from the
+     *  one thread that calls the criteria (AutoStopMCMC.java:397-409); every other handle takes it unchanged. */
+    static final MethodHandle asm_create_multi = h("asm_create_multi", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT));
     static final MethodHandle asm_destroy = h("asm_destroy", FunctionDescriptor.of(JAVA_INT, ADDRESS));
     static final MethodHandle asm_last_error = h("asm_last_error", FunctionDescriptor.of(ADDRESS, ADDRESS));
     static final MethodHandle asm_trees_append = h("asm_trees_append",

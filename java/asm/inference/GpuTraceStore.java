@@ -23,10 +23,20 @@ final class GpuTraceStore implements AutoCloseable {
     private final Map<BitSet, Integer> dictionary = new HashMap<>();
     private final int[] treesSent, linesSent;
 
-    GpuTraceStore(int nChains, int device) {
+    /** gpus == 1: one context on `device`; gpus > 1: devices device .. device+gpus-1 behind ONE context
+     *  (asm_create_multi: tile pairs, traces and clade counts are dealt to the GPUs inside the library and combined
+     *  with NCCL; results are bit-identical to one GPU). */
+    GpuTraceStore(int nChains, int device, int gpus) {
         MemorySegment out = arena.allocate(ADDRESS);
         try {
-            int rc = (int) AsmGpuNative.asm_create.invokeExact(out, device, nChains);
+            int rc;
+            if (gpus <= 1) {
+                rc = (int) AsmGpuNative.asm_create.invokeExact(out, device, nChains);
+            } else {
+                int[] devices = new int[gpus];
+                for (int i = 0; i < gpus; i++) devices[i] = device + i;
+                rc = (int) AsmGpuNative.asm_create_multi.invokeExact(out, arena.allocateFrom(JAVA_INT, devices), gpus, nChains);
+            }
             if (rc != 0) throw new IllegalStateException("asm_create failed (" + rc + "): no usable B200; there is no CPU fallback");
         } catch (RuntimeException e) {
             throw e;

@@ -16,14 +16,15 @@ import static java.lang.foreign.ValueLayout.*;
  */
 @Description("Stopping criterion based on ESS of selected items from trace, evaluated on a B200 GPU")
 public class TraceESSGPU extends TraceESS {
-    public Input<Integer> deviceInput = new Input<>("device", "CUDA device index", 0);
+    public Input<Integer> deviceInput = new Input<>("device", "CUDA device index (the first one when gpus > 1)", 0);
+    public Input<Integer> gpusInput = new Input<>("gpus", "number of GPUs of this box to spread the evaluation over (devices device .. device+gpus-1)", 1);
     private GpuTraceStore store;
     private double[] ess;
 
     @Override
     public void setup(int nChains, TraceInfo traceInfo) {
         super.setup(nChains, traceInfo);
-        store = new GpuTraceStore(nChains, deviceInput.get());
+        store = new GpuTraceStore(nChains, deviceInput.get(), gpusInput.get());
     }
 
     @Override

@@ -18,7 +18,8 @@ import static java.lang.foreign.ValueLayout.*;
  */
 @Description("Gelman-Rubin like criterion for convergence based on trees alone, evaluated on a B200 GPU")
 public class TreePSRFGPU extends TreePSRF {
-    public Input<Integer> deviceInput = new Input<>("device", "CUDA device index", 0);
+    public Input<Integer> deviceInput = new Input<>("device", "CUDA device index (the first one when gpus > 1)", 0);
+    public Input<Integer> gpusInput = new Input<>("gpus", "number of GPUs of this box to spread the evaluation over (devices device .. device+gpus-1)", 1);
     public Input<String> methodInput = new Input<>("method", "distance kernel: i8 (int8 tcgen05), fp4 (block-scaled FP4 tcgen05, same integers, fastest) or popc", "i8");
 
     private GpuTraceStore store;
@@ -37,7 +38,7 @@ public class TreePSRFGPU extends TreePSRF {
     @Override
     public void setup(int nChains, TraceInfo traceInfo) {
         super.setup(nChains, traceInfo);           // keeps the 2-chain rule and grValues initialisation
-        store = new GpuTraceStore(nChains, deviceInput.get());
+        store = new GpuTraceStore(nChains, deviceInput.get(), gpusInput.get());
     }
 
     @Override

@@ -105,3 +105,26 @@ def test_headers_are_plain_c(tmp_path):
     assert r.returncode == 0, r.stderr
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.startswith("asm-b200")  # the missing chain file is an error, not a crash
+
+
+def test_java_stub_handles_match_the_header():
+    """java/ cannot be compiled here (no JDK): at least every Panama downcall handle names an exported function and
+    passes as many arguments, of the right width, as include/asmgpu.h declares."""
+    src = open(os.path.join(ROOT, "java", "asm", "inference", "AsmGpuNative.java")).read()
+    handles = re.findall(r'h\("(asm_[a-z0-9_]+)",\s*FunctionDescriptor\.of\(([^;]*?)\)\);', src, flags=re.S)
+    assert len(handles) >= 10
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "asmgpu.h")).read(), flags=re.S)
+    width = {"JAVA_INT": ("int32_t",), "JAVA_LONG": ("int64_t",), "ADDRESS": ("*",), "JAVA_DOUBLE": ("double",)}
+    for name, desc in handles:
+        m = re.search(r"\b(\w[\w\s\*]*?)\b%s\s*\(([^)]*)\)\s*;" % name, hdr)
+        assert m, f"{name} is not declared in asmgpu.h"
+        c_args = [a.strip() for a in m.group(2).split(",")] if m.group(2).strip() not in ("", "void") else []
+        j = [a.strip() for a in desc.split(",")]
+        j_ret, j_args = j[0], j[1:]
+        assert len(j_args) == len(c_args), f"{name}: {len(j_args)} Java arguments, {len(c_args)} in the header"
+        for ja, ca in zip(j_args, c_args):
+            if ja == "ADDRESS":
+                assert "*" in ca, f"{name}: ADDRESS for `{ca}`"
+            else:
+                assert "*" not in ca and any(w in ca for w in width[ja]), f"{name}: {ja} for `{ca}`"
+        assert ("*" in m.group(1)) == (j_ret == "ADDRESS")

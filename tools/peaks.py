@@ -63,22 +63,34 @@ def gemm_peaks(device="cuda:0", n=8192, sustain_s=2.0):
             del a, b
         except Exception as e:  # noqa: BLE001
             res["int8_error"] = repr(e)[:900]
-        # block-scaled fp4: packed e2m1 pairs, A [M][K/2] row-major, B [K/2][N] column-major, unit scales
+        # block-scaled fp4: packed e2m1 pairs, A [M][K/2] row-major, B [K/2][N] column-major, unit scales.  Two sizes
+        # (the library's fp4 GEMM is still climbing at 8192^3); the best of them is the denominator.
         for name, sdt, blk, sval in (("fp4_mx_e8m0_block32", "float8_e8m0fnu", 32, 127), ("fp4_nv_e4m3_block16", "float8_e4m3fn", 16, 0x38)):
-            try:
-                f4 = torch.float4_e2m1fn_x2
-                a = torch.randint(0, 256, (n, n // 2), device=device, dtype=torch.uint8).view(f4)
-                b = torch.randint(0, 256, (n, n // 2), device=device, dtype=torch.uint8).view(f4).t()
-                rup = lambda x, m: (x + m - 1) // m * m  # noqa: E731
-                numel = rup(n, 128) * rup(n // blk, 4)
-                sa = torch.full((numel,), sval, device=device, dtype=torch.uint8).view(getattr(torch, sdt))
-                sb = torch.full((numel,), sval, device=device, dtype=torch.uint8).view(getattr(torch, sdt))
-                fn = lambda: torch._scaled_mm(a, b, sa, sb, out_dtype=torch.bfloat16)  # noqa: E731
-                fn()
-                res[name] = _time_gemm(torch, fn, flops, sustain_s)
-                del a, b, sa, sb
-            except Exception as e:  # noqa: BLE001
-                res[name + "_error"] = repr(e)[:900]
+            for m in (n, 2 * n):
+                try:
+                    f4 = torch.float4_e2m1fn_x2
+                    a = torch.randint(0, 256, (m, m // 2), device=device, dtype=torch.uint8).view(f4)
+                    b = torch.randint(0, 256, (m, m // 2), device=device, dtype=torch.uint8).view(f4).t()
+                    rup = lambda x, k: (x + k - 1) // k * k  # noqa: E731
+                    numel = rup(m, 128) * rup(m // blk, 4)
+                    sa = torch.full((numel,), sval, device=device, dtype=torch.uint8).view(getattr(torch, sdt))
+                    sb = torch.full((numel,), sval, device=device, dtype=torch.uint8).view(getattr(torch, sdt))
+                    fn = lambda: torch._scaled_mm(a, b, sa, sb, out_dtype=torch.bfloat16)  # noqa: E731
+                    fn()
+                    r = _time_gemm(torch, fn, 2.0 * m ** 3, sustain_s)
+                    r["n"] = m
+                    res.setdefault(name + "_by_n", {})[str(m)] = {k: r[k] for k in ("burst", "sustained")}
+                    if name not in res or r["burst"] > res[name]["burst"]:
+                        keep = dict(r)
+                        if name in res:
+                            keep["sustained"] = max(r["sustained"], res[name]["sustained"])
+                        res[name] = keep
+                    elif r["sustained"] > res[name]["sustained"]:
+                        res[name]["sustained"] = r["sustained"]
+                    del a, b, sa, sb
+                except Exception as e:  # noqa: BLE001
+                    res[name + "_error"] = repr(e)[:900]
+                    break
         torch.cuda.empty_cache()
     return res
 
