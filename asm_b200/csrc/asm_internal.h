@@ -64,6 +64,8 @@ struct ChainTraces {
   int32_t n_cols = 0;
 };
 
+constexpr int kF4CounterOff = 8;
+
 struct DevBuf {  // grow-only device scratch
   void* p = nullptr;
   size_t bytes = 0;
@@ -81,7 +83,11 @@ struct asm_ctx {
   cudaStream_t group_stream[kMaxGroups] = {}, group_stream2[kMaxGroups] = {};   // ESS chunk groups
   cudaEvent_t group_event[kMaxGroups] = {}, group_fork[kMaxGroups] = {}, group_join[kMaxGroups] = {};
   void* h_pinned = nullptr;            // small page-locked scratch for asynchronous counters
-  DevBuf top_word_dev;                 // highest non-zero word of the gathered rows (gather_f4_kernel -> rf_f4x2_kernel)
+  DevBuf top_word_dev;                 // fp4 path scalars: [0] highest non-zero word of the gathered rows (gather_f4_kernel ->
+                                       // rf_f4x2_kernel), [kF4CounterOff] the contraction's work-slot counter
+  void* h_stage = nullptr;             // page-locked staging of the per-step block tables
+  size_t h_stage_bytes = 0;
+  cudaEvent_t ev_stage = nullptr;      // the copy out of h_stage has run
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int32_t words = 0;  // stored row width of every chain (uint64 words)
   std::vector<ChainTrees> trees;

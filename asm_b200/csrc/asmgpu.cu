@@ -288,6 +288,7 @@ int32_t asm_create(asm_ctx** out, int32_t device, int32_t n_chains) {
     cudaEventCreateWithFlags(&ctx->group_fork[k], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->group_join[k], cudaEventDisableTiming);
   }
+  cudaEventCreateWithFlags(&ctx->ev_stage, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
   for (auto& ev : ctx->timer) cudaEventCreate(&ev);
@@ -321,6 +322,8 @@ int32_t asm_destroy(asm_ctx* ctx) {
     if (ev) cudaEventDestroy(ev);
   if (ctx->pe0) cudaEventDestroy(ctx->pe0);
   if (ctx->pe1) cudaEventDestroy(ctx->pe1);
+  if (ctx->ev_stage) cudaEventDestroy(ctx->ev_stage);
+  if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);

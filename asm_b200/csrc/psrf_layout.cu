@@ -11,6 +11,7 @@
 //   S        [C][n_rows][C] int64   the rows the caller asked for, zero-padding removed in closed form
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 
 #include "asm_internal.h"
 #include "seq_sum.cuh"
@@ -114,7 +115,8 @@ __global__ void __launch_bounds__(256) gather_i8_kernel(const __grid_constant__ 
 // even clade in the low nibble).  One source byte becomes one 32-bit word through a 256-entry table in shared
 // memory; one 64-bit word -> 32 bytes, two 16-byte stores per lane.
 __global__ void __launch_bounds__(256) gather_f4_kernel(const __grid_constant__ SegTableDev tab_, uint4* __restrict__ out,
-                                                         int W4, int32_t* __restrict__ nbits, int* __restrict__ top_word) {
+                                                         int W4, int32_t* __restrict__ nbits, int* __restrict__ top_word,
+                                                         long long* __restrict__ S_pad, int C) {
   __shared__ uint32_t lut[256];
   __shared__ int top_s;
   if (threadIdx.x == 0) top_s = 0;
@@ -151,6 +153,7 @@ __global__ void __launch_bounds__(256) gather_f4_kernel(const __grid_constant__ 
     }
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     if (lane == 0) nbits[p] = cnt;
+    for (int c = lane; c < C; c += 32) S_pad[(size_t)p * C + c] = 0;  // the contraction accumulates into a zeroed table
   }
   top = __reduce_max_sync(0xffffffffu, top);
   if (lane == 0 && top > 0) atomicMax(&top_s, top);
@@ -311,12 +314,12 @@ int32_t psrf_build_layout(asm_ctx* ctx, const int32_t* burnin, int32_t row_start
 }
 
 // Seg table, per-tile metadata and the zeroed S table: common to both distance kernels.
-static int32_t psrf_prepare(asm_ctx* ctx, SegTableDev& tab) {
+// (`tile_meta`: the int8 / popcount kernels' per-tile table; `zero_S`: the fp4 gather zeroes its S rows itself.)
+static int32_t psrf_prepare(asm_ctx* ctx, SegTableDev& tab, bool tile_meta = true, bool zero_S = true) {
   PsrfLayout& L = ctx->layout;
   int32_t rc;
   if ((rc = asm_reserve(ctx, ctx->nbits, sizeof(int32_t) * (size_t)L.Tp)) != ASM_OK) return rc;
   const int64_t n_tiles = L.Tp / kTileRows;
-  if ((rc = asm_reserve(ctx, ctx->blk_meta, sizeof(int2) * (size_t)n_tiles)) != ASM_OK) return rc;
   tab.n_seg = L.n_seg;
   tab.delta = L.delta;
   tab.words = ctx->words;
@@ -325,8 +328,13 @@ static int32_t psrf_prepare(asm_ctx* ctx, SegTableDev& tab) {
   tab.Tp = L.Tp;
   for (int c = 0; c < ctx->n_chains; c++) tab.chain_bits[c] = ctx->trees[c].d_bits;
   for (int s = 0; s < L.n_seg; s++) tab.seg[s] = L.seg[s];
+  if ((rc = asm_reserve(ctx, ctx->S_pad, sizeof(int64_t) * (size_t)L.Tp * L.C)) != ASM_OK) return rc;
+  // S_pad starts at zero; the distance kernels accumulate into it with integer atomics
+  if (zero_S) ASM_CUDA(ctx, cudaMemsetAsync(ctx->S_pad.p, 0, sizeof(int64_t) * (size_t)L.Tp * L.C, ctx->stream));
+  if (!tile_meta) return ASM_OK;
 
   // per-tile metadata {chain, flags}
+  if ((rc = asm_reserve(ctx, ctx->blk_meta, sizeof(int2) * (size_t)n_tiles)) != ASM_OK) return rc;
   std::vector<int2>& meta = ctx->meta_host;
   meta.assign((size_t)n_tiles, make_int2(0, 0));
   for (int s = 0; s < L.n_seg; s++) {
@@ -353,9 +361,6 @@ static int32_t psrf_prepare(asm_ctx* ctx, SegTableDev& tab) {
   // pageable source: the runtime stages the bytes before returning, so no host sync is needed here
   ASM_CUDA(ctx, cudaMemcpyAsync(ctx->blk_meta.p, meta.data(), sizeof(int2) * (size_t)n_tiles, cudaMemcpyHostToDevice,
                                 ctx->stream));
-  // S_pad starts at zero; the distance kernels accumulate into it with integer atomics
-  if ((rc = asm_reserve(ctx, ctx->S_pad, sizeof(int64_t) * (size_t)L.Tp * L.C)) != ASM_OK) return rc;
-  ASM_CUDA(ctx, cudaMemsetAsync(ctx->S_pad.p, 0, sizeof(int64_t) * (size_t)L.Tp * L.C, ctx->stream));
   return ASM_OK;
 }
 
@@ -427,8 +432,28 @@ static int32_t psrf_build_f4_blocks(asm_ctx* ctx) {
   blk.insert(blk.end(), cols.begin(), cols.end());
   int32_t rc;
   if ((rc = asm_reserve(ctx, ctx->f4_blk_dev, sizeof(int2) * std::max<size_t>(blk.size(), 1))) != ASM_OK) return rc;
-  if (!blk.empty())  // pageable source: staged by the runtime before the call returns
-    ASM_CUDA(ctx, cudaMemcpyAsync(ctx->f4_blk_dev.p, blk.data(), sizeof(int2) * blk.size(), cudaMemcpyHostToDevice, ctx->stream));
+  if (!blk.empty()) {
+    // through the context's page-locked staging: a pageable source is copied by the driver before the call returns
+    // (microseconds of host time at the head of every step); the event keeps a later call from overwriting the
+    // staging while this copy is still queued (the *_async entry points do not synchronise)
+    const size_t bytes = sizeof(int2) * blk.size();
+    if (ctx->h_stage_bytes < bytes) {
+      if (ctx->h_stage) {
+        ASM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ASM_CUDA(ctx, cudaFreeHost(ctx->h_stage));
+        ctx->h_stage = nullptr;
+        ctx->h_stage_bytes = 0;
+      }
+      const size_t want = std::max<size_t>(bytes * 2, 1 << 16);
+      ASM_CUDA(ctx, cudaMallocHost(&ctx->h_stage, want));
+      ctx->h_stage_bytes = want;
+    } else {
+      ASM_CUDA(ctx, cudaEventSynchronize(ctx->ev_stage));
+    }
+    memcpy(ctx->h_stage, blk.data(), bytes);
+    ASM_CUDA(ctx, cudaMemcpyAsync(ctx->f4_blk_dev.p, ctx->h_stage, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ASM_CUDA(ctx, cudaEventRecord(ctx->ev_stage, ctx->stream));
+  }
   return ASM_OK;
 }
 
@@ -438,15 +463,17 @@ int32_t psrf_gather_f4(asm_ctx* ctx) {
   if (L.Tp >= (int64_t)1 << 31) return asm_fail(ctx, ASM_E_UNSUPPORTED, "psrf: %lld padded rows exceed the fp4 kernel's 32-bit row index", (long long)L.Tp);
   if ((rc = asm_reserve(ctx, ctx->opnd_f4, (size_t)L.Tp * L.pitch4)) != ASM_OK) return rc;
   SegTableDev tab;
-  if ((rc = psrf_prepare(ctx, tab)) != ASM_OK) return rc;
+  if ((rc = psrf_prepare(ctx, tab, /*tile_meta=*/false, /*zero_S=*/false)) != ASM_OK) return rc;
   if ((rc = psrf_build_f4_blocks(ctx)) != ASM_OK) return rc;
-  if ((rc = asm_reserve(ctx, ctx->top_word_dev, sizeof(int))) != ASM_OK) return rc;
-  ASM_CUDA(ctx, cudaMemsetAsync(ctx->top_word_dev.p, 0, sizeof(int), ctx->stream));
+  // the two scalars of the fp4 path share 16 bytes and one memset: [0] the gather's top word, [8] the contraction's
+  // work-slot counter (kF4CounterOff)
+  if ((rc = asm_reserve(ctx, ctx->top_word_dev, 16)) != ASM_OK) return rc;
+  ASM_CUDA(ctx, cudaMemsetAsync(ctx->top_word_dev.p, 0, 16, ctx->stream));
   {
     LaunchScope ls(ctx, ASM_K_GATHER);
     int blocks = (int)std::min<int64_t>((L.Tp + 7) / 8, (int64_t)ctx->sm_count * 16);
     gather_f4_kernel<<<blocks, 256, 0, ctx->stream>>>(tab, (uint4*)ctx->opnd_f4.p, L.pitch4 / 32, (int32_t*)ctx->nbits.p,
-                                                     (int*)ctx->top_word_dev.p);
+                                                     (int*)ctx->top_word_dev.p, (long long*)ctx->S_pad.p, L.C);
   }
   ASM_CUDA(ctx, cudaGetLastError());
   return ASM_OK;

@@ -506,8 +506,8 @@ int32_t rf_f4_sums(asm_ctx* ctx, asm_shard shard) {
   const long long n_slots = (long long)ctx->f4_walk_host.size() * 64;
   L.tiles_total = n_slots;
   L.tiles_done = (n_slots - shard.shard_index + shard.shard_count - 1) / shard.shard_count;
-  if ((rc = asm_reserve(ctx, ctx->tile_counter, sizeof(unsigned long long))) != ASM_OK) return rc;
-  ASM_CUDA(ctx, cudaMemsetAsync(ctx->tile_counter.p, 0, sizeof(unsigned long long), ctx->stream));
+  // the slot counter sits beside the gather's top word and was zeroed with it (psrf_gather_f4)
+  unsigned long long* slot_counter = (unsigned long long*)((char*)ctx->top_word_dev.p + kF4CounterOff);
   // a slot is one of the 64 pairs of a walk tile; roughly half of them carry work
   const int clusters = (int)std::min<long long>(std::max<long long>(L.tiles_done / 2, 1), ctx->sm_count / 2);
   if (clusters <= 0 || n_slots == 0) return ASM_OK;
@@ -517,7 +517,7 @@ int32_t rf_f4_sums(asm_ctx* ctx, asm_shard shard) {
     LaunchScope ls(ctx, ASM_K_RF_I8);
     rf_f4x2_kernel<<<2 * clusters, kThreadsF, kSmemBytesF, ctx->stream>>>(
         tm, (const int*)ctx->top_word_dev.p, (const int*)ctx->nbits.p, blk, blk + ctx->f4_nR, ctx->f4_nR, ctx->f4_nC, n_slots,
-        (const uint32_t*)ctx->f4_walk_dev.p, shard.shard_index, shard.shard_count, (unsigned long long*)ctx->tile_counter.p,
+        (const uint32_t*)ctx->f4_walk_dev.p, shard.shard_index, shard.shard_count, slot_counter,
         (unsigned long long*)ctx->S_pad.p, L.C, getenv("ASM_F4_DEBUG") ? atoi(getenv("ASM_F4_DEBUG")) : 0);
   }
   ASM_CUDA(ctx, cudaGetLastError());

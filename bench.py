@@ -549,7 +549,7 @@ def bench_ess(job, args, steps, warmup, live):
     n = CFG3["n_samples"]
     # traces this PROCESS holds: its own GPU's (torchrun) or every GPU's (one process drives them all)
     n_here = n_tr * (len(job.group_devices) if job.group_devices else 1)
-    first = job.rank * n_tr
+    first = job.rank * n_tr + args.ess_first
     ctx = job.make_ctx(1)
     host_t = torch.empty((n_here, n), dtype=torch.float64)
     try:
@@ -658,6 +658,7 @@ def main():
     ap.add_argument("--ref-rows", type=int, default=512,
                     help="row trees per chain per step of --impl reference (about 2 s of CPU work per step at cfg2)")
     ap.add_argument("--ess-traces", type=int, default=0, help="traces per GPU of the ESS block (default 1000 = cfg3)")
+    ap.add_argument("--ess-first", type=int, default=0, help="index of the first synthetic trace (probe: the traces another rank would hold)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ess", action="store_true", help="skip the ESS (cfg3) block")
     ap.add_argument("--no-cfg5", action="store_true", help="skip the cfg5 strong-scaling block")
