@@ -115,8 +115,7 @@ __global__ void __launch_bounds__(256) gather_i8_kernel(const __grid_constant__ 
 // even clade in the low nibble).  One source byte becomes one 32-bit word through a 256-entry table in shared
 // memory; one 64-bit word -> 32 bytes, two 16-byte stores per lane.
 __global__ void __launch_bounds__(256) gather_f4_kernel(const __grid_constant__ SegTableDev tab_, uint4* __restrict__ out,
-                                                         int W4, int32_t* __restrict__ nbits, int* __restrict__ top_word,
-                                                         long long* __restrict__ S_pad, int C) {
+                                                         int W4, int32_t* __restrict__ nbits, int* __restrict__ top_word) {
   __shared__ uint32_t lut[256];
   __shared__ int top_s;
   if (threadIdx.x == 0) top_s = 0;
@@ -153,7 +152,6 @@ __global__ void __launch_bounds__(256) gather_f4_kernel(const __grid_constant__ 
     }
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     if (lane == 0) nbits[p] = cnt;
-    for (int c = lane; c < C; c += 32) S_pad[(size_t)p * C + c] = 0;  // the contraction accumulates into a zeroed table
   }
   top = __reduce_max_sync(0xffffffffu, top);
   if (lane == 0 && top > 0) atomicMax(&top_s, top);
@@ -231,21 +229,28 @@ __global__ void __launch_bounds__(256) psrf_rows_kernel(const long long* __restr
 // chain of dependent adds is not: seq_sum.cuh evaluates the same roundings as an integer scan over the block (plain
 // DADDs only where the running sum changes binade).
 __global__ void __launch_bounds__(seqsum::kThreads) psrf_mean_kernel(const double* __restrict__ vals, int n_rows,
-                                                                      double* __restrict__ psrf_mean) {
+                                                                      double* __restrict__ psrf_mean, int planned) {
   __shared__ seqsum::Shared sh;
   const double* v = vals + (size_t)blockIdx.x * n_rows;
-  const double sum = seqsum::block_sum(sh, n_rows, [&](int k) { return v[k]; });
+  const double sum = seqsum::block_sum(sh, n_rows, [&](int k) { return v[k]; }, planned != 0);
   if (threadIdx.x == 0) psrf_mean[blockIdx.x] = sum / (double)n_rows;  // 0/0 = NaN for no rows, as in Java
 }
 
 // The same walk over doubles in memory (asm_seq_sum).
-__global__ void __launch_bounds__(seqsum::kThreads) seq_sum_kernel(const double* __restrict__ v, int n, double* __restrict__ out) {
+__global__ void __launch_bounds__(seqsum::kThreads) seq_sum_kernel(const double* __restrict__ v, int n, double* __restrict__ out,
+                                                                    int planned) {
   __shared__ seqsum::Shared sh;
-  const double sum = seqsum::block_sum(sh, n, [&](int k) { return v[k]; });
+  const double sum = seqsum::block_sum(sh, n, [&](int k) { return v[k]; }, planned != 0);
   if (threadIdx.x == 0) *out = sum;
 }
 
 inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+// ASM_SEQSUM_PLANNED=0: the binade-by-binade walk alone (tuning / test knob; same bits)
+inline int seq_sum_planned() {
+  const char* e = getenv("ASM_SEQSUM_PLANNED");
+  return !(e && e[0] == '0');
+}
 
 }  // namespace
 
@@ -314,8 +319,8 @@ int32_t psrf_build_layout(asm_ctx* ctx, const int32_t* burnin, int32_t row_start
 }
 
 // Seg table, per-tile metadata and the zeroed S table: common to both distance kernels.
-// (`tile_meta`: the int8 / popcount kernels' per-tile table; `zero_S`: the fp4 gather zeroes its S rows itself.)
-static int32_t psrf_prepare(asm_ctx* ctx, SegTableDev& tab, bool tile_meta = true, bool zero_S = true) {
+// (`tile_meta`: the int8 / popcount kernels' per-tile table; the fp4 kernel has block tables of its own.)
+static int32_t psrf_prepare(asm_ctx* ctx, SegTableDev& tab, bool tile_meta = true) {
   PsrfLayout& L = ctx->layout;
   int32_t rc;
   if ((rc = asm_reserve(ctx, ctx->nbits, sizeof(int32_t) * (size_t)L.Tp)) != ASM_OK) return rc;
@@ -330,7 +335,7 @@ static int32_t psrf_prepare(asm_ctx* ctx, SegTableDev& tab, bool tile_meta = tru
   for (int s = 0; s < L.n_seg; s++) tab.seg[s] = L.seg[s];
   if ((rc = asm_reserve(ctx, ctx->S_pad, sizeof(int64_t) * (size_t)L.Tp * L.C)) != ASM_OK) return rc;
   // S_pad starts at zero; the distance kernels accumulate into it with integer atomics
-  if (zero_S) ASM_CUDA(ctx, cudaMemsetAsync(ctx->S_pad.p, 0, sizeof(int64_t) * (size_t)L.Tp * L.C, ctx->stream));
+  ASM_CUDA(ctx, cudaMemsetAsync(ctx->S_pad.p, 0, sizeof(int64_t) * (size_t)L.Tp * L.C, ctx->stream));
   if (!tile_meta) return ASM_OK;
 
   // per-tile metadata {chain, flags}
@@ -463,7 +468,7 @@ int32_t psrf_gather_f4(asm_ctx* ctx) {
   if (L.Tp >= (int64_t)1 << 31) return asm_fail(ctx, ASM_E_UNSUPPORTED, "psrf: %lld padded rows exceed the fp4 kernel's 32-bit row index", (long long)L.Tp);
   if ((rc = asm_reserve(ctx, ctx->opnd_f4, (size_t)L.Tp * L.pitch4)) != ASM_OK) return rc;
   SegTableDev tab;
-  if ((rc = psrf_prepare(ctx, tab, /*tile_meta=*/false, /*zero_S=*/false)) != ASM_OK) return rc;
+  if ((rc = psrf_prepare(ctx, tab, /*tile_meta=*/false)) != ASM_OK) return rc;
   if ((rc = psrf_build_f4_blocks(ctx)) != ASM_OK) return rc;
   // the two scalars of the fp4 path share 16 bytes and one memset: [0] the gather's top word, [8] the contraction's
   // work-slot counter (kF4CounterOff)
@@ -473,7 +478,7 @@ int32_t psrf_gather_f4(asm_ctx* ctx) {
     LaunchScope ls(ctx, ASM_K_GATHER);
     int blocks = (int)std::min<int64_t>((L.Tp + 7) / 8, (int64_t)ctx->sm_count * 16);
     gather_f4_kernel<<<blocks, 256, 0, ctx->stream>>>(tab, (uint4*)ctx->opnd_f4.p, L.pitch4 / 32, (int32_t*)ctx->nbits.p,
-                                                     (int*)ctx->top_word_dev.p, (long long*)ctx->S_pad.p, L.C);
+                                                     (int*)ctx->top_word_dev.p);
   }
   ASM_CUDA(ctx, cudaGetLastError());
   return ASM_OK;
@@ -543,7 +548,8 @@ int32_t psrf_finish(asm_ctx* ctx, const int64_t* d_S, int32_t n_rows, double* ps
   }
   {
     LaunchScope ls(ctx, ASM_K_PSRF_FINISH);
-    psrf_mean_kernel<<<C * C, seqsum::kThreads, 0, ctx->stream>>>((const double*)ctx->psrf_vals.p, n_rows, (double*)ctx->psrf_mean.p);
+    psrf_mean_kernel<<<C * C, seqsum::kThreads, 0, ctx->stream>>>((const double*)ctx->psrf_vals.p, n_rows, (double*)ctx->psrf_mean.p,
+                                                                seq_sum_planned());
   }
   ASM_CUDA(ctx, cudaGetLastError());
   ASM_CUDA(ctx, cudaMemcpyAsync(psrf_mean_host, ctx->psrf_mean.p, sizeof(double) * (size_t)C * C, cudaMemcpyDeviceToHost,
@@ -561,7 +567,7 @@ int32_t seq_sum(asm_ctx* ctx, const double* values_host, int64_t n, double* sum_
   if (n) ASM_CUDA(ctx, cudaMemcpyAsync(d + 1, values_host, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
   {
     LaunchScope ls(ctx, ASM_K_MISC);
-    seq_sum_kernel<<<1, seqsum::kThreads, 0, ctx->stream>>>(d + 1, (int)n, d);
+    seq_sum_kernel<<<1, seqsum::kThreads, 0, ctx->stream>>>(d + 1, (int)n, d, seq_sum_planned());
   }
   ASM_CUDA(ctx, cudaGetLastError());
   ASM_CUDA(ctx, cudaMemcpyAsync(sum_host, d, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

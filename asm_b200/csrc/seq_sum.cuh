@@ -116,6 +116,13 @@ SEQ_HD int pad(int k) { return k + (k >> 2); }
 SEQ_HD int window_of(int consumed) {
   return consumed < kMinWindow ? kMinWindow : (consumed > kTile ? kTile : consumed);
 }
+// ---- the planned pass (plan_tile): one thread's 4 consecutive elements form a group; a group is either a RUN group
+// (its elements are decomposed against the binade the running sum is predicted to be in) or a PLAIN group (added with
+// DADDs).  Consecutive run groups of one binade form an event, every plain group is an event of its own.
+constexpr int kMaxEvents = 16;       // more events than this in a tile: the tile is left to the walk
+constexpr int kPlainCls = 1 << 20;   // class of a plain group (a run group's class is its binade exponent)
+constexpr int kParts = kMaxEvents + kWarps;  // (event, warp) pieces of the run events: one per lane of the warp that adds them up
+static_assert(kParts <= 32, "one piece per lane");
 
 }  // namespace seqsum
 
@@ -129,13 +136,171 @@ struct Shared {
   int warp_cut[kWarps];
   double s;
   int lo;
+  // plan_tile
+  double warp_sum[kWarps];
+  int warp_cls[kWarps], warp_heads[kWarps];
+  int ev_first[kMaxEvents], ev_cls[kMaxEvents];
+  Seg part_seg[kParts];
+  int part_ev[kParts];
+  Seg ev_tot[kMaxEvents];
 };
+
+// The planned pass over the elements [lo, tn) of the tile in shared memory, all threads.
+//
+// The walk below (block_sum's loop) learns where the running sum changes binade by running into it, one block-wide
+// pass per binade.  But a sum of doubles in ANY order is within ~n ulps of the left-to-right one, so a parallel prefix
+// sum predicts the binade of the running sum before every element, wrong only when the sum passes within ~1e-12 of a
+// power of two.  So: (1) approximate prefix sums B (before a thread's 4 elements) and A (after them); (2) a group
+// whose B and A share a binade e is a run group and is decomposed against e, any other group is plain; (3) run
+// groups are folded per event with ONE segmented warp scan, the pieces (event, warp) land in shared memory in
+// order; (4) thread 0 stitches the events in order with the EXACT running sum: a run event is applied only if the
+// exact sum is in the predicted binade and stays in it (M + d < 2^53; the partial sums are monotone, so then every
+// element was decomposed against the right binade), a plain group is 4 DADDs.  The prediction is never trusted:
+// the first event that fails the check ends the pass, sh.lo points at it, and the walk takes over from there.
+// Tiles with negative or non-finite values, or with more than kMaxEvents events, are left to the walk entirely.
+__device__ __forceinline__ void plan_tile(Shared& sh, int tn) {
+  const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lo = sh.lo;
+  const double s = sh.s;
+  if (lo >= tn) return;  // uniform
+  const int first = lo + tid * kPerThread;
+  const bool active = first < tn;
+  double v[kPerThread];
+  bool bad = false;
+#pragma unroll
+  for (int i = 0; i < kPerThread; i++) {
+    const int k = first + i;
+    v[i] = k < tn ? sh.vals[pad(k)] : 0.0;
+    const unsigned long long b = bits_of(v[i]);
+    bad = bad || (((b >> 63) != 0 && (b << 1) != 0) || ((b >> 52) & 0x7ff) == 0x7ff);  // negative (not -0.0), infinite, NaN
+  }
+  if (tid < kParts) sh.part_ev[tid] = -1;
+  if (__syncthreads_or(bad)) return;
+  // (1) approximate running sum before / after this thread's elements
+  double a = v[0];
+#pragma unroll
+  for (int i = 1; i < kPerThread; i++) a += v[i];
+  double incl = a;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double up = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += up;
+  }
+  if (lane == 31) sh.warp_sum[warp] = incl;
+  __syncthreads();
+  double B = s;
+  for (int w = 0; w < warp; w++) B += sh.warp_sum[w];
+  B += incl - a;
+  const double A = B + a;
+  // (2) class of the group and, for a run group, the fold of its elements
+  int cls = kPlainCls;
+  Seg mine{0, 0};
+  {
+    int e = 0, eA = 0;
+    unsigned long long M = 0, MA = 0;
+    if (binade_of(B, &e, &M) && binade_of(A, &eA, &MA) && e == eA) {
+      bool ok = true;
+#pragma unroll
+      for (int i = 0; i < kPerThread; i++) {
+        Seg sg;
+        unsigned long long bnd;
+        ok = element(v[i], e, &sg, &bnd) && ok;
+        mine = then(mine, sg);
+      }
+      if (ok) cls = e;
+    }
+  }
+  // (3) events: a group starts one if it is plain or its class differs from the group before it
+  if (lane == 31) sh.warp_cls[warp] = cls;
+  __syncthreads();
+  int prev_cls = __shfl_up_sync(0xffffffffu, cls, 1);
+  if (lane == 0) prev_cls = warp ? sh.warp_cls[warp - 1] : kPlainCls;
+  const bool head = active && (cls == kPlainCls || cls != prev_cls);
+  const unsigned heads = __ballot_sync(0xffffffffu, head);
+  if (lane == 0) sh.warp_heads[warp] = __popc(heads);
+  __syncthreads();
+  int ev = -1, n_events = 0;
+  for (int w = 0; w < kWarps; w++) {
+    if (w == warp) ev = n_events;
+    n_events += sh.warp_heads[w];
+  }
+  if (n_events > kMaxEvents) return;  // uniform
+  ev += __popc(heads & (0xffffffffu >> (31 - lane))) - 1;  // index of the event this group belongs to
+  if (head) {
+    sh.ev_first[ev] = tid;
+    sh.ev_cls[ev] = cls;
+  }
+  // segmented fold within the warp: event indices ascend with the lane, so "same event" = no head in between
+  const int key = active ? ev : -2 - lane;  // inactive groups: keys of their own, never written
+  if (cls == kPlainCls) mine = Seg{0, 0};
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    Seg other;
+    other.d0 = __shfl_up_sync(0xffffffffu, mine.d0, o);
+    other.d1 = __shfl_up_sync(0xffffffffu, mine.d1, o);
+    const int okey = __shfl_up_sync(0xffffffffu, key, o);
+    if (lane >= o && okey == key) mine = then(other, mine);
+  }
+  const int next_key = __shfl_down_sync(0xffffffffu, key, 1);
+  if (active && cls != kPlainCls && (lane == 31 || next_key != key)) {  // the last group of this event in this warp
+    sh.part_seg[ev + warp] = mine;  // (event, warp) pieces in order: ev + warp ascends strictly from piece to piece
+    sh.part_ev[ev + warp] = ev;
+  }
+  __syncthreads();
+  // the pieces of one event sit in consecutive slots: warp 0 adds them up in order, one slot per lane, with the same
+  // segmented scan, so that the stitch reads one total per event
+  if (warp == 0) {
+    const int pkey = lane < kParts ? sh.part_ev[lane] : -1;
+    Seg tot = pkey >= 0 ? sh.part_seg[lane] : Seg{0, 0};
+    const int skey = pkey >= 0 ? pkey : -2 - lane;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      Seg other;
+      other.d0 = __shfl_up_sync(0xffffffffu, tot.d0, o);
+      other.d1 = __shfl_up_sync(0xffffffffu, tot.d1, o);
+      const int okey = __shfl_up_sync(0xffffffffu, skey, o);
+      if (lane >= o && okey == skey) tot = then(other, tot);
+    }
+    const int nkey = __shfl_down_sync(0xffffffffu, skey, 1);
+    if (pkey >= 0 && (lane == 31 || nkey != skey)) sh.ev_tot[pkey] = tot;
+    __syncwarp();
+  }
+  // (4) stitch with the exact running sum
+  if (tid == 0) {
+    double s1 = s;
+    int done = tn;
+    for (int j = 0; j < n_events; j++) {
+      const int c = sh.ev_cls[j], g = sh.ev_first[j];
+      if (c == kPlainCls) {
+#pragma unroll
+        for (int i = 0; i < kPerThread; i++) {
+          const int k = lo + g * kPerThread + i;
+          if (k < tn) s1 = __dadd_rn(s1, sh.vals[pad(k)]);
+        }
+        continue;
+      }
+      const Seg tot = sh.ev_tot[j];
+      int e = 0;
+      unsigned long long M = 0;
+      const bool in_binade = binade_of(s1, &e, &M) && e == c;
+      const unsigned long long d = (M & 1ull) ? tot.d1 : tot.d0;
+      if (!in_binade || d >= kTwo53 || M + d >= kTwo53) {  // the prediction was off: the walk takes over here
+        done = lo + g * kPerThread;
+        break;
+      }
+      s1 = from_binade(e, M + d);
+    }
+    sh.s = s1;
+    sh.lo = done;
+  }
+  __syncthreads();
+}
 
 // Sum of value(0) .. value(n-1) in that order, every add rounded as a scalar loop would; all kThreads threads of
 // the block call it, the result is returned to every thread.  value(k) is evaluated once per element (by some
 // thread, a tile ahead of its use) and may have side effects for that k.
 template <class Value>
-__device__ double block_sum(Shared& sh, int n, Value&& value) {
+__device__ double block_sum(Shared& sh, int n, Value&& value, bool planned = true) {
   const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
     sh.s = 0.0;
@@ -170,6 +335,7 @@ __device__ double block_sum(Shared& sh, int n, Value&& value) {
       sh.lo = lo;
     }
     __syncthreads();
+    if (planned) plan_tile(sh, tn);  // normally consumes the whole tile; the walk below takes what it leaves
     for (;;) {
       const int lo = sh.lo;  // uniform
       if (lo >= tn) break;

@@ -24,7 +24,12 @@ static double plain_sum(const std::vector<double>& v) {
 
 static long g_integer_adds = 0, g_plain_adds = 0;
 
-static double walked_sum(const std::vector<double>& v, int threads, int per_thread, int prelude, int plain_run, bool windowed) {
+static double walked_sum(const std::vector<double>& v, int threads, int per_thread, int prelude, int plain_run, bool windowed,
+                         int planned = 0, std::mt19937_64* jitter = nullptr);
+static int planned_tile(const double* vals, int lo, int tn, double& s_io, std::mt19937_64* jitter);
+
+static double walked_sum(const std::vector<double>& v, int threads, int per_thread, int prelude, int plain_run, bool windowed,
+                         int planned, std::mt19937_64* jitter) {
   const int n = (int)v.size(), tile = threads * per_thread;
   double s = 0.0;
   for (int t0 = 0; t0 < n; t0 += tile) {
@@ -37,6 +42,7 @@ static double walked_sum(const std::vector<double>& v, int threads, int per_thre
         s = t;
         g_plain_adds++;
       }
+    if (planned) lo = planned_tile(vals, lo, tn, s, jitter);
     while (lo < tn) {
       int e = 0;
       unsigned long long M = 0;
@@ -90,12 +96,166 @@ static double walked_sum(const std::vector<double>& v, int threads, int per_thre
   return s;
 }
 
+// The planned pass of the kernel (plan_tile) over [lo, tn) of one tile, its 512 threads and 16 warps walked one after
+// the other with the kernel's own order of operations.  `jitter` perturbs the approximate prefix sums (0: none), to
+// drive the prediction wrong on purpose: the result must not depend on it, only the share of work left to the walk.
+// Returns the new lo; s is updated.
+static long g_planned_adds = 0, g_plan_fallbacks = 0;
+static int planned_tile(const double* vals, int lo, int tn, double& s_io, std::mt19937_64* jitter) {
+  const int T = kThreads, W = kWarps;
+  const double s = s_io;
+  if (lo >= tn) return lo;
+  std::vector<double> a(T), incl(T), B(T), A(T);
+  std::vector<int> cls(T), ev(T, -1);
+  std::vector<Seg> mine(T, Seg{0, 0});
+  std::vector<char> active(T), head(T);
+  bool bad = false;
+  for (int t = 0; t < T; t++) {
+    const int first = lo + t * kPerThread;
+    active[t] = first < tn;
+    double acc = 0;
+    for (int i = 0; i < kPerThread; i++) {
+      const int k = first + i;
+      const double v = k < tn ? vals[k] : 0.0;
+      const unsigned long long b = bits_of(v);
+      bad = bad || (((b >> 63) != 0 && (b << 1) != 0) || ((b >> 52) & 0x7ff) == 0x7ff);
+      acc = i ? acc + v : v;
+    }
+    a[t] = acc;
+  }
+  if (bad) return lo;
+  std::vector<double> warp_sum(W);
+  for (int w = 0; w < W; w++) {  // Hillis-Steele inclusive scan of a warp's 32 lanes
+    double x[32];
+    for (int l = 0; l < 32; l++) x[l] = a[w * 32 + l];
+    for (int o = 1; o < 32; o <<= 1) {
+      double y[32];
+      for (int l = 0; l < 32; l++) y[l] = l >= o ? x[l] + x[l - o] : x[l];
+      for (int l = 0; l < 32; l++) x[l] = y[l];
+    }
+    for (int l = 0; l < 32; l++) incl[w * 32 + l] = x[l];
+    warp_sum[w] = x[31];
+  }
+  for (int t = 0; t < T; t++) {
+    double b = s;
+    for (int w = 0; w < t / 32; w++) b += warp_sum[w];
+    b += incl[t] - a[t];
+    B[t] = b;
+    A[t] = b + a[t];
+    if (jitter) {  // a wrong prediction now and then
+      const unsigned r = (unsigned)((*jitter)() & 1023);
+      if (r < 8) B[t] *= (r & 1) ? 0.49 : 2.1;
+      else if (r < 16) A[t] *= (r & 1) ? 0.49 : 2.1;
+      else if (r < 20) B[t] *= 2.0, A[t] *= 2.0;   // the whole group predicted one binade up / down: the stitch must notice
+      else if (r < 24) B[t] *= 0.5, A[t] *= 0.5;
+      else if (r < 48) B[t] *= 1.0 + ((r & 1) ? 1e-9 : -1e-9), A[t] = B[t] + a[t];
+    }
+  }
+  for (int t = 0; t < T; t++) {
+    cls[t] = kPlainCls;
+    int e = 0, eA = 0;
+    unsigned long long M = 0, MA = 0;
+    if (binade_of(B[t], &e, &M) && binade_of(A[t], &eA, &MA) && e == eA) {
+      bool ok = true;
+      Seg m{0, 0};
+      for (int i = 0; i < kPerThread; i++) {
+        const int k = lo + t * kPerThread + i;
+        Seg sg;
+        unsigned long long bnd;
+        ok = element(k < tn ? vals[k] : 0.0, e, &sg, &bnd) && ok;
+        m = then(m, sg);
+      }
+      if (ok) cls[t] = e, mine[t] = m;
+    }
+  }
+  int n_events = 0;
+  for (int t = 0; t < T; t++) {
+    const int prev = t ? cls[t - 1] : kPlainCls;
+    head[t] = active[t] && (cls[t] == kPlainCls || cls[t] != prev);
+    if (head[t]) n_events++;
+    ev[t] = n_events - 1;
+  }
+  if (n_events > kMaxEvents) return lo;
+  std::vector<int> ev_first(n_events), ev_cls(n_events);
+  for (int t = 0; t < T; t++)
+    if (head[t]) ev_first[ev[t]] = t, ev_cls[ev[t]] = cls[t];
+  // pieces (event, warp): segmented Hillis-Steele scan per warp, the last lane of an event in a warp writes slot ev + warp
+  std::vector<Seg> part_seg(kParts, Seg{0, 0});
+  std::vector<int> part_ev(kParts, -1);
+  for (int w = 0; w < W; w++) {
+    Seg x[32];
+    int key[32];
+    for (int l = 0; l < 32; l++) {
+      const int t = w * 32 + l;
+      key[l] = active[t] ? ev[t] : -2 - l;
+      x[l] = cls[t] == kPlainCls ? Seg{0, 0} : mine[t];
+    }
+    for (int o = 1; o < 32; o <<= 1) {
+      Seg y[32];
+      for (int l = 0; l < 32; l++) y[l] = (l >= o && key[l - o] == key[l]) ? then(x[l - o], x[l]) : x[l];
+      for (int l = 0; l < 32; l++) x[l] = y[l];
+    }
+    for (int l = 0; l < 32; l++) {
+      const int t = w * 32 + l;
+      if (active[t] && cls[t] != kPlainCls && (l == 31 || key[l + 1] != key[l])) {
+        if (part_ev[ev[t] + w] != -1) std::printf("FAIL piece slot reused\n"), std::exit(1);
+        part_seg[ev[t] + w] = x[l];
+        part_ev[ev[t] + w] = ev[t];
+      }
+    }
+  }
+  // stitch
+  double s1 = s;
+  int slot = 0, done = tn;
+  for (int j = 0; j < n_events; j++) {
+    const int c = ev_cls[j], g = ev_first[j];
+    if (c == kPlainCls) {
+      for (int i = 0; i < kPerThread; i++) {
+        const int k = lo + g * kPerThread + i;
+        if (k < tn) {
+          volatile double t = s1 + vals[k];
+          s1 = t;
+          g_plain_adds++;
+        }
+      }
+      continue;
+    }
+    Seg tot{0, 0};
+    while (slot < kParts && part_ev[slot] < j) slot++;
+    while (slot < kParts && part_ev[slot] == j) tot = then(tot, part_seg[slot++]);
+    int e = 0;
+    unsigned long long M = 0;
+    const bool in_binade = binade_of(s1, &e, &M) && e == c;
+    const unsigned long long d = (M & 1ull) ? tot.d1 : tot.d0;
+    if (!in_binade || d >= kTwo53 || M + d >= kTwo53) {
+      done = lo + g * kPerThread;
+      g_plan_fallbacks++;
+      break;
+    }
+    s1 = from_binade(e, M + d);
+    const int g_end = j + 1 < n_events ? ev_first[j + 1] : T;
+    g_planned_adds += std::min(tn, lo + g_end * kPerThread) - (lo + g * kPerThread);
+  }
+  s_io = s1;
+  return done;
+}
+
 static int g_fail = 0, g_cases = 0;
 static void check(const char* name, const std::vector<double>& v) {
   const double want = plain_sum(v);
   // the kernel's own shape first (with its look-ahead window), then shapes that stress the fold and the tiling
   const int shapes[][5] = {{kThreads, kPerThread, kPrelude, kPlainRun, 1}, {256, 8, 64, 32, 0}, {4, 2, 0, 1, 0}, {32, 8, 3, 5, 0},
                            {1, 1, 0, 1, 0}};
+  // the kernel as shipped (planned pass, then the walk for what it leaves), and the same with the prediction jittered
+  static std::mt19937_64 jit(777);
+  for (int mode = 0; mode < 3; mode++) {
+    const double got = walked_sum(v, kThreads, kPerThread, kPrelude, kPlainRun, true, 1, mode ? &jit : nullptr);
+    g_cases++;
+    if (bits_of(got) != bits_of(want) && !(got != got && want != want)) {
+      g_fail++;
+      std::printf("FAIL %s (planned, jitter %d): got %.17g want %.17g\n", name, mode, got, want);
+    }
+  }
   for (const auto& sh : shapes) {
     const double got = walked_sum(v, sh[0], sh[1], sh[2], sh[3], sh[4] != 0);
     g_cases++;
@@ -201,15 +361,16 @@ int main() {
     std::vector<double> v(40000, c);
     check("constant", v);
   }
-  std::printf("%s: %d cases, %d failures; last run took %ld integer-path adds, %ld plain adds\n", g_fail ? "FAILED" : "ok", g_cases,
-              g_fail, g_integer_adds, g_plain_adds);
+  std::printf("%s: %d cases, %d failures; last run took %ld integer-path adds, %ld plain adds; planned pass: %ld adds, %ld hand-overs to the walk\n",
+              g_fail ? "FAILED" : "ok", g_cases, g_fail, g_integer_adds, g_plain_adds, g_planned_adds, g_plan_fallbacks);
   // share of plain adds on a PSRF-like row of 28,285 values
   {
     std::vector<double> v(28285);
     for (auto& x : v) x = std::sqrt((double)(1000000 + rng() % 400000) / (double)(1000000 + rng() % 400000));
-    g_integer_adds = g_plain_adds = 0;
-    walked_sum(v, kThreads, kPerThread, kPrelude, kPlainRun, true);
-    std::printf("psrf-like n=28285: %ld integer-path adds, %ld plain adds\n", g_integer_adds, g_plain_adds);
+    g_integer_adds = g_plain_adds = g_planned_adds = g_plan_fallbacks = 0;
+    walked_sum(v, kThreads, kPerThread, kPrelude, kPlainRun, true, 1);
+    std::printf("psrf-like n=28285: %ld integer-path adds, %ld plain adds (planned pass: %ld adds, %ld fallbacks to the walk)\n",
+                g_integer_adds + g_planned_adds, g_plain_adds, g_planned_adds, g_plan_fallbacks);
   }
   return g_fail ? 1 : 0;
 }

@@ -77,8 +77,12 @@ CASES = _cases()
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("planned", ["1", "0"])
 @pytest.mark.parametrize("name", sorted(CASES))
-def test_device_sum_is_the_scalar_loop_bit_for_bit(gpu, name):
+def test_device_sum_is_the_scalar_loop_bit_for_bit(gpu, monkeypatch, name, planned):
+    # planned = "1": the shipped kernel (predicted binades, one pass per tile, the walk for what the stitch rejects);
+    # "0": the binade-by-binade walk alone
+    monkeypatch.setenv("ASM_SEQSUM_PLANNED", planned)
     v = CASES[name]
     with np.errstate(all="ignore"):
         want = _left_to_right(v)
