@@ -626,6 +626,25 @@ def bench_ess(job, args, steps, warmup, live):
             ess2 = ctx.all_gather_f64(ess2)
         e2e_ms.append((time.perf_counter() - t0) * 1e3)
     e_ms = job.reduce(float(min(e2e_ms)), "max")
+    # ---- the same 1,000 traces as the one-GPU cfg3 run, dealt over the N GPUs (BASELINE.json configs[2]: "1 and 8 GPUs") ----
+    strong = None
+    if world > 1 and n_tr % world == 0:
+        per = n_tr // world
+        if job.dist is not None:   # torchrun: this rank holds block `rank` of traces 0 .. n_tr-1
+            gen_traces(per, n, CFG3["seed0"], first=job.rank * per, out=host[:per])
+            ctx.ess_traces_put(host[:per])
+        else:                      # one process: the group deals the blocks itself
+            gen_traces(n_tr, n, CFG3["seed0"], first=0, out=host[:n_tr])
+            ctx.ess_traces_put(host[:n_tr])
+        for _ in range(warmup):
+            step()
+        job.barrier(ctx)
+        s_ms, (_, s_ess) = timed_steps(job, ctx, step, steps, flush=False)
+        strong = {"scaling": "strong", "traces_total": n_tr, "traces_per_gpu": per, "ms_per_step": s_ms,
+                  "value": n_tr * n / (s_ms * 1e-3), "unit": "trace-samples/s",
+                  "ess_checksum": format(int(np.ascontiguousarray(s_ess).view(np.uint64).sum(dtype=np.uint64)), "016x"),
+                  "note": "the 1,000 traces of the one-GPU cfg3 line (same ess_checksum) in contiguous blocks of n/N per GPU; "
+                          "with 125 traces per GPU every round is one latency-bound walk of a chain over the 1M samples"}
     from asm_b200.multi import java_min
     line = {"metric": "trace-samples/sec (ESS)", "value": value, "unit": "trace-samples/s", "n_gpus": world,
             "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
@@ -642,6 +661,8 @@ def bench_ess(job, args, steps, warmup, live):
             "min_ess": java_min(ess_all),
             "ess_checksum": format(int(np.ascontiguousarray(ess_all).view(np.uint64).sum(dtype=np.uint64)), "016x"),
             "bit_identical_e2e_vs_resident": bool(np.array_equal(ess_all, ess2, equal_nan=True))}
+    if strong is not None:
+        line["strong"] = strong
     ctx.close()
     return line
 

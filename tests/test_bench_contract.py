@@ -57,7 +57,7 @@ def test_live_gpu_line_has_the_contract_keys():
 
 def test_committed_gpu_line_is_a_record_of_the_same_contract():
     # an ARTIFACT check (documentation of the last full GPU run), not a check of the current code: see the live test above
-    path = os.path.join(ROOT, "profiles", "r02_bench_n1_ess_pilot_groups.json")
+    path = os.path.join(ROOT, "profiles", "r02_bench_n1_final.json")
     d = json.loads(open(path).read().strip().splitlines()[-1])
     _check_gpu_line(d)
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
