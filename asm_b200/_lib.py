@@ -79,6 +79,8 @@ SIGNATURES = {
     "asm_psrf_last_layout": (_i32, [_p, _i64p, _i64p, _i64p, _i64p]),
     "asm_encoder_create": (_i32, [C.POINTER(_p), _i32]),
     "asm_seq_sum": (_i32, [_p, _p, _i64, _p]),
+    "asm_trees_set_ids": (_i32, [_p, _i32, _i64, _i32, _p, _i32]),
+    "asm_trees_append_ids": (_i32, [_p, _i32, _i64, _i32, _p, _i32]),
     "asm_bind_thread_near_device": (_i32, [_i32]),
     "asm_encoder_destroy": (_i32, [_p]),
     "asm_encoder_add_topologies": (_i32, [_p, _i64, _p, _p, _p, _p]),
@@ -290,6 +292,25 @@ class GpuContext:
         if bits.ndim == 1:
             bits = bits[None, :]
         self._check(lib().asm_trees_append(self._h, chain, bits.shape[0], bits.shape[1], _ptr(bits)))
+
+    @staticmethod
+    def _ids16(ids):
+        """Clade ids as the ABI takes them: uint16, ASM_NO_CLADE (0xFFFF) in unused slots (the encoder writes -1 there)."""
+        ids = np.asarray(ids)
+        if ids.dtype != np.uint16:
+            if ids.size and (ids.max() > 0xFFFE or ids.min() < -1):
+                raise AsmGpuError(ASM_E_RANGE, "clade ids do not fit uint16; use trees_set with bit rows")
+            ids = ids.astype(np.uint16)  # -1 -> 0xFFFF
+        ids = np.ascontiguousarray(ids)
+        return ids[None, :] if ids.ndim == 1 else ids
+
+    def trees_set_ids(self, chain: int, ids, n_clades: int):
+        ids = self._ids16(ids)
+        self._check(lib().asm_trees_set_ids(self._h, chain, ids.shape[0], ids.shape[1], _ptr(ids), n_clades))
+
+    def trees_append_ids(self, chain: int, ids, n_clades: int):
+        ids = self._ids16(ids)
+        self._check(lib().asm_trees_append_ids(self._h, chain, ids.shape[0], ids.shape[1], _ptr(ids), n_clades))
 
     def trees_set_device(self, chain: int, d_ptr: int, n_trees: int, words: int):
         self._check(lib().asm_trees_set_device(self._h, chain, n_trees, words, C.c_void_p(d_ptr)))

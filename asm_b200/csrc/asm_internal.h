@@ -85,6 +85,11 @@ struct asm_ctx {
   void* h_pinned = nullptr;            // small page-locked scratch for asynchronous counters
   DevBuf top_word_dev;                 // fp4 path scalars: [0] highest non-zero word of the gathered rows (gather_f4_kernel ->
                                        // rf_f4x2_kernel), [kF4CounterOff] the contraction's work-slot counter
+  DevBuf ids_stage[2], ids_flag;       // clade ids on their way to bit rows (asm_trees_set_ids), double-buffered; "an id was out of range"
+  int ids_slot = 0;
+  cudaEvent_t ev_ids_used[2] = {};     // the expansion kernel has read ids_stage[slot]
+  bool ids_check_pending = false;      // ids_flag has not been looked at since the last ids upload (trees_ids_verify)
+  cudaEvent_t ev_ids = nullptr;        // the copy of the caller's ids has run
   void* h_stage = nullptr;             // page-locked staging of the per-step block tables
   size_t h_stage_bytes = 0;
   cudaEvent_t ev_stage = nullptr;      // the copy out of h_stage has run
@@ -133,7 +138,7 @@ struct asm_ctx {
   std::string err;
 };
 
-constexpr uint32_t kAttrPopc = 1, kAttrI8 = 2, kAttrI8Dump = 4, kAttrI8x2 = 8, kAttrEss = 16, kAttrF4x2 = 32, kAttrEssTicket = 64;
+constexpr uint32_t kAttrPopc = 1, kAttrI8 = 2, kAttrI8Dump = 4, kAttrI8x2 = 8, kAttrEss = 16, kAttrF4x2 = 32, kAttrEssTicket = 64, kAttrIdsToBits = 128;
 
 // ---- error plumbing ---------------------------------------------------------------------------------
 int32_t asm_fail(asm_ctx* ctx, int32_t code, const char* fmt, ...);
@@ -166,6 +171,7 @@ int32_t psrf_check_max_bits(asm_ctx* ctx, int32_t limit);  // ASM_E_UNSUPPORTED 
 int32_t psrf_compact(asm_ctx* ctx, asm_shard shard, int64_t* d_S_out);  // S_pad -> [C][n_rows][C], pad-corrected
 int32_t psrf_finish(asm_ctx* ctx, const int64_t* d_S, int32_t n_rows, double* psrf_rows_host, double* psrf_mean_host);
 int32_t seq_sum(asm_ctx* ctx, const double* values_host, int64_t n, double* sum_host);  // left-to-right sum, seq_sum.cuh
+int32_t trees_ids_verify(asm_ctx* ctx);  // asmgpu.cu: ASM_E_RANGE if an ids upload since the last check named a clade outside its dictionary
 // rf_popc.cu
 int32_t rf_popc_sums(asm_ctx* ctx, asm_shard shard);
 int32_t rf_popc_block(asm_ctx* ctx, int32_t chainA, int64_t r0, int64_t r1, int32_t chainB, int64_t c0, int64_t c1,

@@ -73,6 +73,33 @@ __global__ void restride_kernel(const uint64_t* __restrict__ src, int src_words,
 }
 
 
+// Clade ids -> bit rows, one warp per tree: the row is assembled in shared memory (ids of one tree hit the same few words)
+// and written out whole, so the stored rows never see an atomic.
+__global__ void __launch_bounds__(256) ids_to_bits_kernel(const uint16_t* __restrict__ ids, int ids_per_tree, int64_t n_trees,
+                                                           uint64_t* __restrict__ rows, int words, int n_clades,
+                                                           int* __restrict__ bad) {
+  extern __shared__ unsigned long long row_s[];  // [warps per block][words]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  unsigned long long* row = row_s + (size_t)warp * words;
+  for (int64_t t = (int64_t)blockIdx.x * wpb + warp; t < n_trees; t += (int64_t)gridDim.x * wpb) {
+    for (int w = lane; w < words; w += 32) row[w] = 0ull;
+    __syncwarp();
+    const uint16_t* src = ids + (size_t)t * ids_per_tree;
+    for (int k = lane; k < ids_per_tree; k += 32) {
+      const unsigned id = src[k];
+      if (id == ASM_NO_CLADE) continue;
+      if ((int)id >= n_clades) {
+        atomicExch(bad, 1);
+        continue;
+      }
+      atomicOr(&row[id >> 6], 1ull << (id & 63));
+    }
+    __syncwarp();
+    for (int w = lane; w < words; w += 32) rows[(size_t)t * words + w] = row[w];
+    __syncwarp();
+  }
+}
+
 __global__ void flush_kernel(uint4* p, size_t n, uint32_t v) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   for (; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = make_uint4(v, v, v, v);
@@ -160,6 +187,72 @@ static int32_t trees_put(asm_ctx* ctx, int32_t chain, int64_t at, int64_t n_new,
   if ((rc = trees_upload_rows(ctx, chain, at, n_new, words, bits, kind)) != ASM_OK) return rc;
   if (n_new > 0) ASM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the caller may free or overwrite `bits` on return
   ctx->trees[chain].n = at + n_new;
+  return ASM_OK;
+}
+
+// Rows [at, at + n_new) of `chain` from clade ids on the host (asm_trees_set_ids / asm_trees_append_ids).
+static int32_t trees_put_ids(asm_ctx* ctx, int32_t chain, int64_t at, int64_t n_new, int32_t ids_per_tree, const uint16_t* ids,
+                             int32_t n_clades) {
+  if (chain < 0 || chain >= ctx->n_chains || n_new < 0 || ids_per_tree < 1 || n_clades < 1 || n_clades > 0xFFFF || (n_new > 0 && !ids))
+    return asm_fail(ctx, ASM_E_INVALID, "trees (ids): bad argument (chain=%d n=%lld ids_per_tree=%d n_clades=%d)", chain,
+                    (long long)n_new, ids_per_tree, n_clades);
+  const int32_t words = std::max(4, (n_clades + 255) / 256 * 4);  // whole 256-clade units, as the host encoder lays rows out
+  int32_t rc = ensure_tree_capacity(ctx, chain, at + n_new, words);
+  if (rc != ASM_OK) return rc;
+  if (n_new > 0) {
+    const size_t bytes = sizeof(uint16_t) * (size_t)n_new * (size_t)ids_per_tree;
+    // Two staging buffers and the copy stream: the copy of one chain's ids runs while the previous chain's rows are
+    // still being built (a check uploads chain after chain).  ev_ids_used[slot] keeps a copy from overwriting ids the
+    // kernel two calls back has not read yet.
+    const int slot = (ctx->ids_slot ^= 1);
+    DevBuf& stage = ctx->ids_stage[slot];
+    if (stage.bytes < bytes) ASM_CUDA(ctx, cudaEventSynchronize(ctx->ev_ids_used[slot]));  // about to be freed
+    if ((rc = asm_reserve(ctx, stage, bytes)) != ASM_OK) return rc;
+    uint16_t* d_ids = (uint16_t*)stage.p;
+    if (!ctx->ids_flag.p) {  // set by the kernel when an id is outside the dictionary; read with the next evaluation
+      if ((rc = asm_reserve(ctx, ctx->ids_flag, sizeof(int))) != ASM_OK) return rc;
+      ASM_CUDA(ctx, cudaMemsetAsync(ctx->ids_flag.p, 0, sizeof(int), ctx->stream));
+    }
+    ASM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream_copy, ctx->ev_ids_used[slot], 0));
+    ASM_CUDA(ctx, cudaMemcpyAsync(d_ids, ids, bytes, cudaMemcpyHostToDevice, ctx->stream_copy));
+    ASM_CUDA(ctx, cudaEventRecord(ctx->ev_ids, ctx->stream_copy));
+    ASM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_ids, 0));
+    const int wpb = 8;
+    const size_t smem = sizeof(uint64_t) * (size_t)wpb * (size_t)ctx->words;
+    if (smem > 48 * 1024 && !(ctx->func_attr_done & kAttrIdsToBits)) {
+      ASM_CUDA(ctx, cudaFuncSetAttribute(ids_to_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin));
+      ctx->func_attr_done |= kAttrIdsToBits;
+    }
+    {
+      LaunchScope ls(ctx, ASM_K_MISC);
+      const int blocks = (int)std::min<int64_t>((n_new + wpb - 1) / wpb, (int64_t)ctx->sm_count * 8);
+      ids_to_bits_kernel<<<blocks, 32 * wpb, smem, ctx->stream>>>(d_ids, ids_per_tree, n_new,
+                                                                 ctx->trees[chain].d_bits + (size_t)at * ctx->words, ctx->words,
+                                                                 n_clades, (int*)ctx->ids_flag.p);
+    }
+    ASM_CUDA(ctx, cudaGetLastError());
+    ASM_CUDA(ctx, cudaEventRecord(ctx->ev_ids_used[slot], ctx->stream));
+    ctx->ids_check_pending = true;
+    // the caller may free `ids` on return: wait for the copy; the expansion runs behind it in stream order, and so does
+    // whatever reads the rows next
+    ASM_CUDA(ctx, cudaEventSynchronize(ctx->ev_ids));
+  }
+  ctx->trees[chain].n = at + n_new;
+  return ASM_OK;
+}
+
+// Did an asm_trees_*_ids call since the last check carry an id outside its dictionary?  (The flag is read here, by the
+// next call that looks at the trees, so that the upload itself waits for nothing but its copy.)
+int32_t trees_ids_verify(asm_ctx* ctx) {
+  if (!ctx->ids_check_pending) return ASM_OK;
+  int flag = 0;
+  ASM_CUDA(ctx, cudaMemcpyAsync(&flag, ctx->ids_flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  ASM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->ids_check_pending = false;
+  if (flag) {
+    ASM_CUDA(ctx, cudaMemsetAsync(ctx->ids_flag.p, 0, sizeof(int), ctx->stream));
+    return asm_fail(ctx, ASM_E_RANGE, "trees (ids): an uploaded clade id was not below its n_clades");
+  }
   return ASM_OK;
 }
 
@@ -289,6 +382,9 @@ int32_t asm_create(asm_ctx** out, int32_t device, int32_t n_chains) {
     cudaEventCreateWithFlags(&ctx->group_join[k], cudaEventDisableTiming);
   }
   cudaEventCreateWithFlags(&ctx->ev_stage, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->ev_ids, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->ev_ids_used[0], cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->ev_ids_used[1], cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
   for (auto& ev : ctx->timer) cudaEventCreate(&ev);
@@ -315,7 +411,7 @@ int32_t asm_destroy(asm_ctx* ctx) {
     if (t.d_vals) cudaFree(t.d_vals);
   DevBuf* bufs[] = {&ctx->opnd_bits, &ctx->opnd_i8, &ctx->opnd_f4, &ctx->nbits, &ctx->S_pad, &ctx->blk_meta,
                     &ctx->S_compact, &ctx->psrf_rows, &ctx->psrf_vals, &ctx->psrf_mean, &ctx->misc, &ctx->flush, &ctx->ess_tr,
-                    &ctx->ess_sls, &ctx->ess_out, &ctx->tile_counter, &ctx->rf_out, &ctx->walk_dev, &ctx->ess_res, &ctx->f4_blk_dev, &ctx->f4_walk_dev, &ctx->top_word_dev, &ctx->ess_park};
+                    &ctx->ess_sls, &ctx->ess_out, &ctx->tile_counter, &ctx->rf_out, &ctx->walk_dev, &ctx->ess_res, &ctx->f4_blk_dev, &ctx->f4_walk_dev, &ctx->top_word_dev, &ctx->ess_park, &ctx->ids_stage[0], &ctx->ids_stage[1], &ctx->ids_flag};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   for (auto& ev : ctx->timer)
@@ -323,6 +419,9 @@ int32_t asm_destroy(asm_ctx* ctx) {
   if (ctx->pe0) cudaEventDestroy(ctx->pe0);
   if (ctx->pe1) cudaEventDestroy(ctx->pe1);
   if (ctx->ev_stage) cudaEventDestroy(ctx->ev_stage);
+  if (ctx->ev_ids) cudaEventDestroy(ctx->ev_ids);
+  for (auto& ev : ctx->ev_ids_used)
+    if (ev) cudaEventDestroy(ev);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
@@ -394,6 +493,25 @@ int32_t asm_trees_append(asm_ctx* ctx, int32_t chain, int64_t n_new, int32_t wor
   return trees_put(ctx, chain, ctx->trees[chain].n, n_new, words_per_tree, bits, cudaMemcpyHostToDevice);
 }
 
+int32_t asm_trees_set_ids(asm_ctx* ctx, int32_t chain, int64_t n_trees, int32_t ids_per_tree, const uint16_t* ids,
+                          int32_t n_clades) {
+  ASM_NULLCHECK(ctx);
+  if (is_group(ctx))  // ids are small: every member takes them from the host itself and builds its own rows
+    return group_run(ctx, [=](asm_ctx* m, int) { return asm_trees_set_ids(m, chain, n_trees, ids_per_tree, ids, n_clades); });
+  ASM_ENTER(ctx);
+  return trees_put_ids(ctx, chain, 0, n_trees, ids_per_tree, ids, n_clades);
+}
+
+int32_t asm_trees_append_ids(asm_ctx* ctx, int32_t chain, int64_t n_new, int32_t ids_per_tree, const uint16_t* ids,
+                             int32_t n_clades) {
+  ASM_NULLCHECK(ctx);
+  if (is_group(ctx))
+    return group_run(ctx, [=](asm_ctx* m, int) { return asm_trees_append_ids(m, chain, n_new, ids_per_tree, ids, n_clades); });
+  ASM_ENTER(ctx);
+  if (chain < 0 || chain >= ctx->n_chains) return asm_fail(ctx, ASM_E_INVALID, "chain %d out of range", chain);
+  return trees_put_ids(ctx, chain, ctx->trees[chain].n, n_new, ids_per_tree, ids, n_clades);
+}
+
 int32_t asm_trees_count(const asm_ctx* ctx, int32_t chain, int64_t* n_trees, int32_t* words_per_tree) {
   if (is_group(ctx)) ctx = ctx->members[0];
   if (!ctx || chain < 0 || chain >= ctx->n_chains) return ASM_E_INVALID;
@@ -414,6 +532,10 @@ int32_t asm_rf_block(asm_ctx* ctx, int32_t chainA, int64_t r0, int64_t r1, int32
   if (r1 > ctx->trees[chainA].n || c1 > ctx->trees[chainB].n)
     return asm_fail(ctx, ASM_E_RANGE, "rf_block: range past the stored trees");
   if (r1 == r0 || c1 == c0) return ASM_OK;
+  {
+    const int32_t rcv = trees_ids_verify(ctx);
+    if (rcv != ASM_OK) return rcv;
+  }
   if (method == ASM_RF_POPC) return rf_popc_block(ctx, chainA, r0, r1, chainB, c0, c1, out);
   if (method == ASM_RF_I8) return rf_i8_block(ctx, chainA, r0, r1, chainB, c0, c1, out);
   if (method == ASM_RF_FP4) return asm_fail(ctx, ASM_E_UNSUPPORTED, "rf_block: the fp4 kernel has no distance dump; use ASM_RF_I8 or ASM_RF_POPC");
@@ -424,6 +546,10 @@ static int32_t clade_counts_rank(asm_ctx* ctx, int32_t chain, int64_t from, int6
   if (chain < 0 || chain >= ctx->n_chains || (want_out && !out) || from < 0 || to < from)
     return asm_fail(ctx, ASM_E_INVALID, "clade_counts: bad argument");
   if (to > ctx->trees[chain].n) return asm_fail(ctx, ASM_E_RANGE, "clade_counts: range past the stored trees");
+  {
+    const int32_t rcv = trees_ids_verify(ctx);
+    if (rcv != ASM_OK) return rcv;
+  }
   return clade_counts(ctx, chain, from, to, want_out ? out : nullptr);
 }
 
@@ -443,14 +569,16 @@ int32_t asm_clade_counts(asm_ctx* ctx, int32_t chain, int64_t from, int64_t to, 
 // Partial sums of this rank's share of the tile pairs, then (with a communicator) one int64 all-reduce on the same
 // stream: exact in any order, so every rank ends with the complete table.
 static int32_t psrf_sums_impl(asm_ctx* ctx, const int32_t* burnin, int32_t row_start, int32_t end, int32_t delta,
-                              int32_t method, asm_shard shard, int64_t* d_S_out) {
+                              int32_t method, asm_shard shard, int64_t* d_S_out, bool verify_ids = true) {
   if (shard.shard_count < 1 || shard.shard_index < 0 || shard.shard_index >= shard.shard_count)
     return asm_fail(ctx, ASM_E_INVALID, "psrf: bad shard {%d,%d}", shard.shard_index, shard.shard_count);
   if (method != ASM_RF_POPC && method != ASM_RF_I8 && method != ASM_RF_FP4)
     return asm_fail(ctx, ASM_E_INVALID, "psrf: unknown method %d", method);
   // the caller's split composes with the communicator's: slot t of the caller's shard goes to rank t % world
   const asm_shard eff{shard.shard_index * ctx->world + ctx->rank, shard.shard_count * ctx->world};
-  int32_t rc = psrf_build_layout(ctx, burnin, row_start, end, delta, method == ASM_RF_FP4 ? 240 : kBlockRows);
+  int32_t rc;
+  if (verify_ids && (rc = trees_ids_verify(ctx)) != ASM_OK) return rc;  // asm_psrf_eval checks with its final copy instead
+  rc = psrf_build_layout(ctx, burnin, row_start, end, delta, method == ASM_RF_FP4 ? 240 : kBlockRows);
   if (rc != ASM_OK) return rc;
   if (ctx->layout.n_rows == 0) return ASM_OK;
   if (method == ASM_RF_FP4) {
@@ -469,7 +597,7 @@ static int32_t psrf_sums_impl(asm_ctx* ctx, const int32_t* burnin, int32_t row_s
 
 // d_S == NULL: the table stays in the context's own buffer (members of a group other than the first)
 static int32_t psrf_sums_device_rank(asm_ctx* ctx, const int32_t* burnin, int32_t row_start, int32_t end, int32_t delta,
-                                     int32_t method, asm_shard shard, int64_t* d_S, bool sync) {
+                                     int32_t method, asm_shard shard, int64_t* d_S, bool sync, bool verify_ids = true) {
   if (!burnin) return asm_fail(ctx, ASM_E_INVALID, "psrf_sums: null argument");
   int32_t rc;
   if (!d_S) {
@@ -478,7 +606,7 @@ static int32_t psrf_sums_device_rank(asm_ctx* ctx, const int32_t* burnin, int32_
     if ((rc = asm_reserve(ctx, ctx->S_compact, bytes ? bytes : 8)) != ASM_OK) return rc;
     d_S = (int64_t*)ctx->S_compact.p;
   }
-  if ((rc = psrf_sums_impl(ctx, burnin, row_start, end, delta, method, shard, d_S)) != ASM_OK) return rc;
+  if ((rc = psrf_sums_impl(ctx, burnin, row_start, end, delta, method, shard, d_S, verify_ids)) != ASM_OK) return rc;
   if (sync) ASM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return ASM_OK;
 }
@@ -560,7 +688,7 @@ static int32_t psrf_eval_rank(asm_ctx* ctx, const int32_t* burnin, int32_t row_s
                               int32_t method, double* psrf_rows, double* psrf_mean) {
   if (!burnin) return asm_fail(ctx, ASM_E_INVALID, "psrf_eval: null argument");
   asm_shard all{0, 1};
-  int32_t rc = psrf_sums_device_rank(ctx, burnin, row_start, end, delta, method, all, nullptr, false);
+  int32_t rc = psrf_sums_device_rank(ctx, burnin, row_start, end, delta, method, all, nullptr, false, /*verify_ids=*/false);
   if (rc != ASM_OK) return rc;
   if (!psrf_mean) {
     ASM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

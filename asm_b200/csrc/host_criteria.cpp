@@ -206,10 +206,17 @@ void TraceInfo::flush() {
     if (!p.empty()) {
       const int per = nTaxa_ - 1;
       const int64_t n = (int64_t)(p.size() / (size_t)per);
-      const int words = asm_encoder_words(enc_);
-      bitsScratch_.resize((size_t)words * (size_t)n);
-      if (asm_encode_bits(p.data(), n, per, words, bitsScratch_.data()) != ASM_OK) throw std::runtime_error("asm_encode_bits failed");
-      GPU_CHECK(ctx_, asm_trees_append(ctx_, c, n, words, bitsScratch_.data()));
+      const int64_t D = cladeCount();
+      if (D <= 0xFFFF) {  // the ids themselves go up (half the bytes of the bit rows); the GPU builds the rows
+        ids16Scratch_.resize(p.size());
+        for (size_t k = 0; k < p.size(); k++) ids16Scratch_[k] = p[k] < 0 ? (uint16_t)ASM_NO_CLADE : (uint16_t)p[k];
+        GPU_CHECK(ctx_, asm_trees_append_ids(ctx_, c, n, per, ids16Scratch_.data(), (int32_t)D));
+      } else {
+        const int words = asm_encoder_words(enc_);
+        bitsScratch_.resize((size_t)words * (size_t)n);
+        if (asm_encode_bits(p.data(), n, per, words, bitsScratch_.data()) != ASM_OK) throw std::runtime_error("asm_encode_bits failed");
+        GPU_CHECK(ctx_, asm_trees_append(ctx_, c, n, words, bitsScratch_.data()));
+      }
       p.clear();
     }
     const int64_t up = linesUploaded_[(size_t)c], have = nLines_[(size_t)c];

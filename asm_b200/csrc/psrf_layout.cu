@@ -555,6 +555,8 @@ int32_t psrf_finish(asm_ctx* ctx, const int64_t* d_S, int32_t n_rows, double* ps
   ASM_CUDA(ctx, cudaMemcpyAsync(psrf_mean_host, ctx->psrf_mean.p, sizeof(double) * (size_t)C * C, cudaMemcpyDeviceToHost,
                                 ctx->stream));
   if (d_rows) ASM_CUDA(ctx, cudaMemcpyAsync(psrf_rows_host, d_rows, rows_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  // an ids upload that named a clade outside its dictionary fails the evaluation: its flag comes back with the results
+  if (ctx->ids_check_pending) return trees_ids_verify(ctx);  // synchronises
   ASM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return ASM_OK;
 }

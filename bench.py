@@ -172,6 +172,7 @@ def gen_psrf_input(cfg, n_trees, want_topologies=False):
         topo.append((l, r, root))
     words = enc.words
     bits = [enc.bits(i, words) for i in ids]
+    enc.chain_ids = ids  # the clade ids the rows were built from (what the end-to-end leg uploads)
     return enc, bits, (topo if want_topologies else None)
 
 
@@ -393,16 +394,26 @@ def bench_psrf(job, args, which, method_name, steps, warmup, live, others=False)
     ctx = job.make_ctx(C)
     pinned = [pinned_like(b) for b in bits]
     del bits
-    h2d_bytes = sum(p[1].nbytes for p in pinned)
+    # end-to-end leg: the host hands over what its encoder emits, uint16 clade ids (198 bytes per 100-taxon tree against
+    # 352 bytes of bit row); the library builds the bit rows on the GPU (asm_trees_set_ids)
+    use_ids = D <= 0xFFFF and not args.e2e_bits
+    pinned_ids = [pinned_like(i.astype(np.uint16)) for i in enc.chain_ids] if use_ids else None
+    h2d_bytes = sum(p[1].nbytes for p in (pinned_ids if use_ids else pinned))
 
-    def upload():  # at N > 1 every row crosses PCIe once per job: GPU r uploads the r-th slice, one all-gather replicates it
+    def upload_bits():  # at N > 1 every row crosses PCIe once per job: GPU r uploads the r-th slice, one all-gather replicates it
         for c in range(C):
             ctx.trees_set(c, pinned[c][1])
+
+    def upload():
+        if not use_ids:
+            return upload_bits()
+        for c in range(C):  # at N > 1 every GPU takes the ids itself
+            ctx.trees_set_ids(c, pinned_ids[c][1], D)
 
     def step():  # sums on every GPU's share of the tile pairs, ONE int64 all-reduce inside the library, finish
         return ctx.psrf_eval(burnin, 0, n_trees, 1, method)
 
-    upload()
+    upload_bits()
     for _ in range(warmup):
         mean = step()
         ctx.flush_l2()
@@ -475,7 +486,7 @@ def bench_psrf(job, args, which, method_name, steps, warmup, live, others=False)
     e_ms = job.reduce(float(np.mean(e2e_steps)), "max")
     e2e = {"value": T * T / (e_ms * 1e-3), "unit": "tree-pairs/s", "h2d_bytes_per_step": int(h2d_bytes),
            "d2h_bytes_per_step": int(C * C * 8), "ms_per_step": e_ms,
-           "timer": "host clock around asm_trees_set x C + asm_psrf_eval, max over ranks",
+           "timer": "host clock around asm_trees_set[_ids] x C + asm_psrf_eval, max over ranks",
            "bit_identical_to_resident": bool(np.array_equal(np.asarray(mean_e), np.asarray(mean), equal_nan=True))}
     S = ctx.psrf_sums(burnin, 0, n_trees, 1, method)  # the complete int64 table (all-reduced at N > 1)
     checksum = s_checksum(S)
@@ -493,9 +504,12 @@ def bench_psrf(job, args, which, method_name, steps, warmup, live, others=False)
                        "generator": {k: cfg[k] for k in ("beta", "moves", "start_seed", "seed0")},
                        "weak_scaling": ("trees per chain = 10000*sqrt(N); trees beyond the first 10000 are a seeded resample of them, so D "
                                         "(work per pair) is the same at every N") if which == "cfg2" else None,
-                       "e2e_upload": "asm_trees_set from pinned host rows" + ("" if world == 1 else
-                                     ": GPU r uploads the r-th slice of every chain, one in-library ncclAllGather replicates it "
-                                     "(h2d_bytes_per_step is the whole job's)"),
+                       "e2e_upload": ("asm_trees_set_ids from pinned uint16 clade ids (the encoder's output), bit rows built on the GPU" +
+                                      ("" if world == 1 else "; every GPU takes the ids itself (h2d_bytes_per_step is one GPU's)"))
+                       if use_ids else
+                                     ("asm_trees_set from pinned host rows" + ("" if world == 1 else
+                                      ": GPU r uploads the r-th slice of every chain, one in-library ncclAllGather replicates it "
+                                      "(h2d_bytes_per_step is the whole job's)")),
                        "psrf_mean_01": float(mean[0, 1]), "psrf_mean_10": float(mean[1, 0])},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(round(launches)), "roofline": roof,
             "step_breakdown_ms": fam_ms, "S_checksum": checksum}
@@ -680,6 +694,7 @@ def main():
                     help="row trees per chain per step of --impl reference (about 2 s of CPU work per step at cfg2)")
     ap.add_argument("--ess-traces", type=int, default=0, help="traces per GPU of the ESS block (default 1000 = cfg3)")
     ap.add_argument("--ess-first", type=int, default=0, help="index of the first synthetic trace (probe: the traces another rank would hold)")
+    ap.add_argument("--e2e-bits", action="store_true", help="end-to-end leg uploads finished bit rows (asm_trees_set) instead of clade ids")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ess", action="store_true", help="skip the ESS (cfg3) block")
     ap.add_argument("--no-cfg5", action="store_true", help="skip the cfg5 strong-scaling block")

@@ -90,6 +90,7 @@ class TraceInfo {  // TraceInfo.java
   int translateCount_ = 0;
   std::vector<int32_t> idsScratch_;
   std::vector<uint64_t> bitsScratch_;
+  std::vector<uint16_t> ids16Scratch_;
   std::vector<std::vector<int32_t>> pendingIds_;  // [chain]: clade ids of the trees not uploaded yet
   std::vector<int64_t> linesUploaded_;            // [chain]: lines of hostLogs_ already on the GPU
   void appendIds_(int chain);

@@ -114,6 +114,18 @@ int32_t asm_trees_set(asm_ctx* ctx, int32_t chain, int64_t n_trees, int32_t word
 /* Append n_new rows (the streaming runner adds one tree per chain per check).  words_per_tree
  * may exceed the stored width when the dictionary grew: older rows are zero-extended. */
 int32_t asm_trees_append(asm_ctx* ctx, int32_t chain, int64_t n_new, int32_t words_per_tree, const uint64_t* bits);
+/* The same two calls for callers that hold what the encoder emits -- the clade ids of every tree (CladeDifference's
+ * clade identity, CladeDifference.java:107-141; asm_encoder_add_*) -- instead of finished bit rows: `ids` is row-major
+ * [n_trees][ids_per_tree] uint16 dictionary ids, ASM_NO_CLADE in unused slots (a multifurcating tree has fewer clades);
+ * n_clades is the dictionary size the ids were drawn from (sets the row width, at most 65,535).  The rows are built
+ * on the GPU: a 100-taxon tree is 198 bytes of ids against 352 bytes of bits over PCIe.  The call returns when `ids`
+ * has been read; an id that is neither ASM_NO_CLADE nor below n_clades is reported (ASM_E_RANGE) by the next call that
+ * looks at the trees (asm_psrf_*, asm_rf_block, asm_clade_counts), which then fails. */
+#define ASM_NO_CLADE 0xFFFFu
+int32_t asm_trees_set_ids(asm_ctx* ctx, int32_t chain, int64_t n_trees, int32_t ids_per_tree, const uint16_t* ids,
+                          int32_t n_clades);
+int32_t asm_trees_append_ids(asm_ctx* ctx, int32_t chain, int64_t n_new, int32_t ids_per_tree, const uint16_t* ids,
+                             int32_t n_clades);
 int32_t asm_trees_count(const asm_ctx* ctx, int32_t chain, int64_t* n_trees, int32_t* words_per_tree);
 /* Same as asm_trees_set, but `d_bits` is a device pointer on the context's GPU (used by the
  * benchmark's "inputs already resident in HBM" leg and by multi-GPU replicas). */

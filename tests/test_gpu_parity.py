@@ -463,3 +463,53 @@ def test_fp4_k_extent_follows_the_highest_used_word(gpu, words, top):
             assert np.array_equal(got, ctx.psrf_sums([0, 0], 0, 100, 1, gpu.ASM_RF_POPC))
             ctx.psrf_sums([0, 0], 0, 100, 1, gpu.ASM_RF_FP4)
             assert ctx.last_layout()["padded_bits"] <= top * 64
+
+
+@pytest.mark.gpu
+def test_trees_from_clade_ids_equal_trees_from_bit_rows(gpu, multi_chains, ragged_chains):
+    """asm_trees_set_ids / asm_trees_append_ids build on the GPU the rows asm_encode_bits builds on the host: same S, same
+    means, same clade counts; a dictionary that grows between appends widens the stored rows; ASM_NO_CLADE slots and ids
+    outside the dictionary behave as documented."""
+    for ch in (multi_chains, ragged_chains):
+        C, D = ch.n_chains, ch.enc.num_clades
+        end = min(ch.n_trees)
+        with gpu.GpuContext(C) as a, gpu.GpuContext(C) as b:
+            ch.upload(a)
+            for c in range(C):
+                half = ch.n_trees[c] // 2
+                first = ch.ids[c][:half]
+                b.trees_set_ids(c, first, int(first.max()) + 1)          # the dictionary as it stood after these trees
+                b.trees_append_ids(c, ch.ids[c][half:], D)               # ... and now: wider rows
+                assert b.trees_count(c)[0] == ch.n_trees[c]
+            for m in (gpu.ASM_RF_POPC, gpu.ASM_RF_I8, gpu.ASM_RF_FP4):
+                assert np.array_equal(a.psrf_sums([0] * C, 0, end, 1, m), b.psrf_sums([0] * C, 0, end, 1, m))
+            ma, mb = a.psrf_eval([3] * C, 0, end, 1, gpu.ASM_RF_FP4), b.psrf_eval([3] * C, 0, end, 1, gpu.ASM_RF_FP4)
+            assert bits_equal(ma, mb)
+            for c in range(C):
+                assert np.array_equal(a.clade_counts(c, 0, ch.n_trees[c])[:D], b.clade_counts(c, 0, ch.n_trees[c])[:D])
+    # unused slots (a multifurcating tree has fewer clades) and a row of its own kind
+    ids = np.array([[0, 5, 0xFFFF, 70], [0xFFFF, 0xFFFF, 0xFFFF, 0xFFFF], [129, 128, 127, 126]], dtype=np.uint16)
+    want = np.zeros((3, 4), dtype=np.uint64)
+    for r, row in enumerate(ids):
+        for k in row:
+            if k != 0xFFFF:
+                want[r, k >> 6] |= np.uint64(1) << np.uint64(k & 63)
+    with gpu.GpuContext(2) as ctx:
+        ctx.trees_set_ids(0, ids, 130)
+        ctx.trees_set(1, want)
+        assert ctx.trees_count(0) == (3, 4)
+        d = ctx.rf_block(0, 0, 3, 1, 0, 3)
+        assert np.array_equal(np.diag(d), [0, 0, 0]) and d[0, 1] == 3 and d[0, 2] == 7
+        ctx.trees_set_ids(0, ids, 100)                                   # ids 126..129 are outside a 100-clade dictionary:
+        with pytest.raises(gpu.AsmGpuError) as e:                        # reported by the next call that looks at the trees
+            ctx.psrf_eval([0, 0], 0, 3, 1, gpu.ASM_RF_POPC)
+        assert e.value.code == gpu.ASM_E_RANGE
+        ctx.trees_set_ids(0, ids, 130)                                   # a good upload clears the condition
+        assert np.isfinite(ctx.psrf_eval([0, 0], 0, 3, 1, gpu.ASM_RF_POPC)).all()
+        ctx.trees_set_ids(0, ids, 100)
+        with pytest.raises(gpu.AsmGpuError) as e:
+            ctx.rf_block(0, 0, 3, 1, 0, 3)
+        assert e.value.code == gpu.ASM_E_RANGE
+        ctx.trees_set_ids(0, ids, 130)
+        with pytest.raises(gpu.AsmGpuError):
+            ctx.trees_set_ids(0, ids, 70000)                             # wider than uint16 ids can name

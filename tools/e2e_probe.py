@@ -16,11 +16,15 @@ C, n = cfg["n_chains"], cfg["n_trees"]
 enc, bits, _ = B.gen_psrf_input(cfg, n)
 pinned = [B.pinned_like(b) for b in bits]
 pageable = [np.array(b, copy=True) for b in bits]
-out = {"D": int(enc.num_clades), "words": int(enc.words), "bytes_per_chain": int(bits[0].nbytes)}
+ids16 = [B.pinned_like(i.astype(np.uint16)) for i in enc.chain_ids]
+D = int(enc.num_clades)
+out = {"D": int(enc.num_clades), "words": int(enc.words), "bytes_per_chain": int(bits[0].nbytes),
+       "id_bytes_per_chain": int(enc.chain_ids[0].size * 2)}
 with L.GpuContext(C, device=0) as ctx:
-    for label, src in (("pinned", [p[1] for p in pinned]), ("pageable", pageable)):
+    for label, src in (("pinned", [p[1] for p in pinned]), ("pageable", pageable), ("pinned_ids", [p[1] for p in ids16])):
+        put = (lambda c, a: ctx.trees_set_ids(c, a, D)) if label == "pinned_ids" else ctx.trees_set
         for c in range(C):
-            ctx.trees_set(c, src[c])
+            put(c, src[c])
         ctx.psrf_eval([0] * C, 0, n, 1, L.ASM_RF_FP4)
         t_set, t_eval, t_all = [], [], []
         for _ in range(30):
@@ -30,7 +34,7 @@ with L.GpuContext(C, device=0) as ctx:
             per = []
             for c in range(C):
                 t1 = time.perf_counter()
-                ctx.trees_set(c, src[c])
+                put(c, src[c])
                 per.append(time.perf_counter() - t1)
             t2 = time.perf_counter()
             ctx.psrf_eval([0] * C, 0, n, 1, L.ASM_RF_FP4)
