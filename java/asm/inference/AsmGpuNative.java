@@ -28,6 +28,8 @@ final class AsmGpuNative {
     static final MethodHandle asm_last_error = h("asm_last_error", FunctionDescriptor.of(ADDRESS, ADDRESS));
     static final MethodHandle asm_trees_append = h("asm_trees_append",
             FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_LONG, JAVA_INT, ADDRESS));
+    static final MethodHandle asm_trees_append_ids = h("asm_trees_append_ids",
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_LONG, JAVA_INT, ADDRESS, JAVA_INT));
     static final MethodHandle asm_psrf_eval = h("asm_psrf_eval",
             FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT, JAVA_INT, JAVA_INT, ADDRESS, ADDRESS));
     static final MethodHandle asm_rf_block = h("asm_rf_block",

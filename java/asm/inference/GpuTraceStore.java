@@ -87,16 +87,30 @@ final class GpuTraceStore implements AutoCloseable {
                 }
                 ids.add(row);
             }
-            int w = words();
             try (Arena a = Arena.ofConfined()) {
-                MemorySegment bits = a.allocate(JAVA_LONG, (long) nNew * w);
-                for (int t = 0; t < nNew; t++)
-                    for (int id : ids.get(t)) {
-                        long off = ((long) t * w + (id >> 6)) * 8;
-                        bits.set(JAVA_LONG, off, bits.get(JAVA_LONG, off) | (1L << (id & 63)));
+                if (dictionary.size() <= 0xFFFF) {
+                    // the ids themselves go up (two bytes per clade); the library builds the bit rows on the GPU
+                    int per = 1;
+                    for (int[] row : ids) per = Math.max(per, row.length);
+                    MemorySegment buf = a.allocate(JAVA_SHORT, (long) nNew * per);
+                    for (int t = 0; t < nNew; t++) {
+                        int[] row = ids.get(t);
+                        for (int k = 0; k < per; k++)   // ASM_NO_CLADE in the slots a multifurcating tree leaves empty
+                            buf.setAtIndex(JAVA_SHORT, (long) t * per + k, (short) (k < row.length ? row[k] : 0xFFFF));
                     }
-                int rc = (int) AsmGpuNative.asm_trees_append.invokeExact(ctx, chain, (long) nNew, w, bits);
-                AsmGpuNative.check(ctx, rc, "asm_trees_append");
+                    int rc = (int) AsmGpuNative.asm_trees_append_ids.invokeExact(ctx, chain, (long) nNew, per, buf, dictionary.size());
+                    AsmGpuNative.check(ctx, rc, "asm_trees_append_ids");
+                } else {
+                    int w = words();
+                    MemorySegment bits = a.allocate(JAVA_LONG, (long) nNew * w);
+                    for (int t = 0; t < nNew; t++)
+                        for (int id : ids.get(t)) {
+                            long off = ((long) t * w + (id >> 6)) * 8;
+                            bits.set(JAVA_LONG, off, bits.get(JAVA_LONG, off) | (1L << (id & 63)));
+                        }
+                    int rc = (int) AsmGpuNative.asm_trees_append.invokeExact(ctx, chain, (long) nNew, w, bits);
+                    AsmGpuNative.check(ctx, rc, "asm_trees_append");
+                }
             }
             treesSent[chain] = have;
         }
