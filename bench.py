@@ -396,7 +396,9 @@ def bench_psrf(job, args, which, method_name, steps, warmup, live, others=False)
     del bits
     # end-to-end leg: the host hands over what its encoder emits, uint16 clade ids (198 bytes per 100-taxon tree against
     # 352 bytes of bit row); the library builds the bit rows on the GPU (asm_trees_set_ids)
-    use_ids = D <= 0xFFFF and not args.e2e_bits
+    # (at N > 1 the sharded upload of finished rows -- each GPU 1/N of them over PCIe, one all-gather over NVLink -- moves
+    # fewer bytes per GPU than every GPU taking all the ids, so the multi-GPU lines keep it)
+    use_ids = D <= 0xFFFF and not args.e2e_bits and world == 1
     pinned_ids = [pinned_like(i.astype(np.uint16)) for i in enc.chain_ids] if use_ids else None
     h2d_bytes = sum(p[1].nbytes for p in (pinned_ids if use_ids else pinned))
 

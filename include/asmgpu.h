@@ -120,7 +120,9 @@ int32_t asm_trees_append(asm_ctx* ctx, int32_t chain, int64_t n_new, int32_t wor
  * n_clades is the dictionary size the ids were drawn from (sets the row width, at most 65,535).  The rows are built
  * on the GPU: a 100-taxon tree is 198 bytes of ids against 352 bytes of bits over PCIe.  The call returns when `ids`
  * has been read; an id that is neither ASM_NO_CLADE nor below n_clades is reported (ASM_E_RANGE) by the next call that
- * looks at the trees (asm_psrf_*, asm_rf_block, asm_clade_counts), which then fails. */
+ * looks at the trees (asm_psrf_*, asm_rf_block, asm_clade_counts), which then fails.  On a multi-GPU context every
+ * GPU takes the ids from the host itself (right for the runner's one tree per chain per check; for bulk loads over
+ * several GPUs asm_trees_set sends every row over PCIe only once). */
 #define ASM_NO_CLADE 0xFFFFu
 int32_t asm_trees_set_ids(asm_ctx* ctx, int32_t chain, int64_t n_trees, int32_t ids_per_tree, const uint16_t* ids,
                           int32_t n_clades);
