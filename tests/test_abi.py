@@ -128,3 +128,17 @@ def test_java_stub_handles_match_the_header():
             else:
                 assert "*" not in ca and any(w in ca for w in width[ja]), f"{name}: {ja} for `{ca}`"
         assert ("*" in m.group(1)) == (j_ret == "ADDRESS")
+
+
+def test_bind_thread_near_device_is_harmless():
+    """asm_bind_thread_near_device: an error code without a device, otherwise the number of CPUs bound to (0 where the
+    platform shows one NUMA node or hides the topology); the calling thread keeps a non-empty CPU set either way."""
+    before = os.sched_getaffinity(0)
+    rc = L.lib().asm_bind_thread_near_device(0)
+    after = os.sched_getaffinity(0)
+    if L.lib().asm_device_count() == 0:
+        assert rc == L.ASM_E_INVALID and after == before
+    else:
+        assert rc >= 0 and len(after) > 0 and (rc == 0 or len(after) == rc)
+    assert L.lib().asm_bind_thread_near_device(10 ** 6) == L.ASM_E_INVALID
+    os.sched_setaffinity(0, before)
