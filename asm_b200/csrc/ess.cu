@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(256) ess_lag_kernel(const double* __restrict__
     double xi[SB], wn[SB], xi_n[SB], wn_n[SB];
     load_block<SB, true>(ring, xo, xi);
     load_block<SB, kWinAligned>(ring, wo, wn);
-#pragma unroll 2
+#pragma unroll(R == 1 ? 1 : 2)
     for (int k = 0; k < n_blocks; k++) {
       xo += kStep;
       wo += kStep;
@@ -347,7 +347,7 @@ __device__ __forceinline__ void ess_ticket_body(const EssTicketParams& prm, cons
     double xi[SB], wn[SB], xi_n[SB], wn_n[SB];
     load_block<SB, true>(ring, xo, xi);
     load_block<SB, kWinAligned>(ring, wo, wn);
-#pragma unroll 2
+#pragma unroll(R == 1 ? 1 : 2)
     for (int kb = 0; kb < n_blocks; kb++) {
       xo += kStep;
       wo += kStep;
