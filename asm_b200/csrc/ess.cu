@@ -918,6 +918,10 @@ static size_t ess_ring_bytes(int R, int max_lag_end, int* ring_out, int* chunk_o
   };
   int ring = ring_for(kChunkMax);
   if (ring_for(kChunkMax / 2) < ring) chunk = kChunkMax / 2, ring = ring_for(kChunkMax / 2);
+  if (const char* e = getenv("ASM_ESS_CHUNK")) {  // tuning knob: force the cp.async chunk (256 or 512 samples)
+    const int c = atoi(e);
+    if (c == kChunkMax || c == kChunkMax / 2) chunk = c, ring = ring_for(c);
+  }
   *ring_out = ring;
   *chunk_out = chunk;
   switch (R) {
