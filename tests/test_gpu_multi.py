@@ -68,6 +68,16 @@ def test_group_equals_one_gpu(gpu, many_gpus, multi_chains, ragged_chains):
             # a caller-side shard composes with the group's own split
             parts = [ctx.psrf_sums(burnin, start, end, delta, gpu.ASM_RF_I8, shard=(i, 3)) for i in range(3)]
             assert np.array_equal(sum(parts), ref[gpu.ASM_RF_I8])
+            # the same trees handed over as clade ids (every member takes them and builds its own rows), half of each
+            # chain appended with the wider dictionary
+            D = ch.enc.num_clades
+            for c in range(ch.n_chains):
+                ctx.trees_set_ids(c, ch.ids[c][:350], int(ch.ids[c][:350].max()) + 1)
+                ctx.trees_append_ids(c, ch.ids[c][350:], D)
+            assert np.array_equal(ctx.psrf_sums(burnin, start, end, delta, gpu.ASM_RF_FP4), ref[gpu.ASM_RF_FP4])
+            rows, mean = ctx.psrf_eval(burnin, start, end, delta, gpu.ASM_RF_FP4, want_rows=True)
+            assert bits_equal(rows, ref_rows) and bits_equal(mean, ref_mean)
+            assert np.array_equal(ctx.clade_counts(2, 5, 699)[:D], ref_cc[:D])
             assert np.array_equal(ctx.clade_counts(2, 5, 699), ref_cc)          # sharded + ncclAllReduce(int32)
             assert np.array_equal(ref_cc[: ch.ts.num_clades], ch.ts.clade_counts(2, 5, 699))
             assert np.array_equal(ctx.rf_block(0, 10, 50, 3, 0, 64), ref_rf)
