@@ -15,6 +15,12 @@
 // where a conservative bound M + sum(q_k + 1) could reach 2^53 (the sum would leave the binade), or at an element
 // that is negative, non-finite or >= 2^(e+1); that element is added with a plain DADD and the walk restarts in the
 // new binade.  Binade changes are rare (log2 of the sum), so nearly all adds take the parallel path.
+//
+// Two layers on the device (block_sum): that walk, one block-wide pass per binade, correct on any input; and in front
+// of it plan_tile, which predicts the binade before every element from a parallel prefix sum, folds a whole tile in one
+// pass and lets thread 0 stitch the pieces with the exact running sum -- every piece is checked against the exact sum
+// before it is applied, and whatever fails the check is left to the walk.  tests/c/seq_sum_check.cpp walks both layers
+// on the host with this header's arithmetic.
 #pragma once
 #include <cstdint>
 #include <cstring>
