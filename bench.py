@@ -659,8 +659,8 @@ def bench_ess(job, args, steps, warmup, live):
         strong = {"scaling": "strong", "traces_total": n_tr, "traces_per_gpu": per, "ms_per_step": s_ms,
                   "value": n_tr * n / (s_ms * 1e-3), "unit": "trace-samples/s",
                   "ess_checksum": format(int(np.ascontiguousarray(s_ess).view(np.uint64).sum(dtype=np.uint64)), "016x"),
-                  "note": "the 1,000 traces of the one-GPU cfg3 line (same ess_checksum) in contiguous blocks of n/N per GPU; "
-                          "with 125 traces per GPU every round is one latency-bound walk of a chain over the 1M samples"}
+                  "note": f"the {n_tr} traces of the one-GPU cfg3 line (same ess_checksum) in contiguous blocks of {per} per GPU; "
+                          "the fewer traces a GPU holds, the more of its rounds are one latency-bound walk of a chain over all samples"}
     from asm_b200.multi import java_min
     line = {"metric": "trace-samples/sec (ESS)", "value": value, "unit": "trace-samples/s", "n_gpus": world,
             "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
